@@ -1,0 +1,231 @@
+/*
+ * gpr.h — C ABI of the B200-native batched simulator for GymPR's step path.
+ *
+ * The reference (ubi-coro/gymnasium-planar-robotics v1.1.0a2) is pure Python and has no FFI for this path: its "operator
+ * API" is gymnasium.Env (reset/step/compute_reward/...).  The entry points below are what a Python binding of that API
+ * needs; each cites the reference interface it replaces (paths relative to gymnasium_planar_robotics/):
+ *
+ *   gpr_create         <- BasicPlanarRoboticsEnv.__init__            envs/basic_envs.py:162-289
+ *                         BenchmarkPlanningEnv.__init__              envs/planning/benchmark_planning_env.py:165-291
+ *                         BenchmarkPushingEnv.__init__               envs/manipulation/benchmark_pushing_env.py:154-288
+ *   gpr_reset          <- BasicPlanarRoboticsSingleAgentEnv.reset    envs/basic_envs.py:1770-1833
+ *                         _reset_callback                            planning:355-418, pushing:373-417
+ *   gpr_step           <- BasicPlanarRoboticsSingleAgentEnv.step     envs/basic_envs.py:1835-1950
+ *                         (+ gymnasium TimeLimit(50)                 __init__.py:25-38)
+ *   gpr_step_host      <- same call made with host (NumPy) buffers, as a user of the reference makes it
+ *   gpr_compute_reward <- compute_reward / compute_terminated        planning:459-534, pushing:457-527   (HER relabelling)
+ *   gpr_get_state /
+ *   gpr_set_state      <- MjData.qpos/qvel/act/qacc access           utils/mujoco_utils.py:23-190 (parity + checkpoint)
+ *   gpr_destroy        <- Env.close                                  planning:604-608
+ *
+ * Conventions
+ *   - plain C, POD structs, raw pointers; no C++/torch types cross this boundary.
+ *   - every function returns GPR_OK (0) or a negative gpr_status; nothing throws; gpr_last_error() gives the text
+ *     (thread-local).  Device code never asserts: an out-of-grid mover is a wall collision (reference: AssertionError,
+ *     basic_envs.py:514-517).
+ *   - the caller owns all I/O buffers (device pointers unless the function name ends in _host); the handle owns only its
+ *     structure-of-arrays state.  All work is enqueued on the caller's stream (a cudaStream_t passed as void*); no hidden
+ *     synchronisation except in the *_host calls, which return when the host buffers are filled.
+ *   - one handle <-> one device; a handle is not thread-safe.
+ *   - state and arithmetic are IEEE float64 (the reference's dtype) evaluated in the reference's operation order without
+ *     FMA contraction, so collision/termination flags are bit-identical to the float64 oracle; observations, goals and
+ *     rewards are delivered as float32 (the float64 value rounded once on store); actions are float32.
+ */
+#ifndef GPR_H_
+#define GPR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPR_ABI_VERSION 1
+
+#define GPR_MAX_MOVERS 32   /* one lane per mover, one lane group (<= one warp) per environment */
+#define GPR_MAX_TILES_1D 32 /* tiles per axis */
+
+enum gpr_env_kind { GPR_ENV_PLANNING = 0, GPR_ENV_PUSHING = 1 };
+enum gpr_collision_shape { GPR_SHAPE_CIRCLE = 0, GPR_SHAPE_BOX = 1 };
+enum gpr_autoreset_mode {
+    GPR_AUTORESET_OFF = 0,       /* like the bare reference env: the caller resets; counters keep running */
+    GPR_AUTORESET_SAME_STEP = 1, /* finished envs are re-sampled inside the same kernel; terminal obs go to final_* */
+    GPR_AUTORESET_NEXT_STEP = 2  /* gymnasium>=1.0 vector default: the step after `done` performs the reset instead */
+};
+
+typedef enum gpr_status {
+    GPR_OK = 0,
+    GPR_ERR_INVALID_ARG = -1,
+    GPR_ERR_CUDA = -2,
+    GPR_ERR_NO_DEVICE = -3,
+    GPR_ERR_OUT_OF_MEMORY = -4,
+    GPR_ERR_UNSUPPORTED = -5,
+    GPR_ERR_ABI_MISMATCH = -6
+} gpr_status;
+
+/*
+ * Everything the step path needs, packed once by the host mirror (the Python env class) from the reference's constructor
+ * kwargs.  Derived numbers are computed on the host in float64 WITH THE REFERENCE'S EXPRESSIONS so thresholds are
+ * bit-identical (citations per field).
+ */
+typedef struct gpr_config {
+    uint32_t struct_bytes; /* sizeof(gpr_config) as seen by the caller; gpr_create rejects a mismatch */
+    uint32_t abi_version;  /* GPR_ABI_VERSION */
+    int32_t env_kind;      /* gpr_env_kind */
+    int32_t num_envs;      /* environments held by this handle (this rank's shard) */
+    int64_t env_index_base; /* global index of local env 0; part of the RNG key, so results do not depend on sharding */
+    uint64_t seed;          /* base RNG key; gpr_reset may replace it */
+
+    /* --- tile layout (basic_envs.py:194-221, 1292-1339) --- */
+    int32_t num_tiles_x, num_tiles_y;
+    uint8_t layout[GPR_MAX_TILES_1D * GPR_MAX_TILES_1D]; /* layout[ix * num_tiles_y + iy] in {0,1} */
+    double tile_half[2];                                 /* tile_size[:2] (half sizes), default 0.12 */
+    double tile_cx[GPR_MAX_TILES_1D];                    /* np.linspace centres along x (basic_envs.py:1300-1303) */
+    double tile_cy[GPR_MAX_TILES_1D];
+
+    /* --- collision shapes (basic_envs.py:257-264) --- */
+    int32_t c_shape;          /* gpr_collision_shape */
+    int32_t reference_quirks; /* 1: reproduce the (P,)x(P,1) broadcast of basic_envs.py:409 for per-mover radii */
+    /* [safety][mover][xy]; circle uses [.][.][0] only.
+       c_wall  = c_size + offset_wall + safety*offset   (basic_envs.py:487)
+       c_mover = c_size + safety*offset                 (basic_envs.py:390)                                   */
+    double c_wall[2][GPR_MAX_MOVERS][2];
+    double c_mover[2][GPR_MAX_MOVERS][2];
+
+    /* --- dynamics (planning:213-218, 420-450; basic_envs.py:283, 1740) --- */
+    int32_t num_movers;
+    int32_t learn_jerk;
+    int32_t num_cycles; /* control cycles per env-step, default 40 */
+    int32_t max_episode_steps; /* TimeLimit, 50 (__init__.py:28,37); <=0 disables truncation */
+    double cycle_time;  /* MuJoCo opt.timestep, 0.001 */
+    double v_max, a_max, j_max;
+
+    /* --- task (planning:220, 262-274; pushing:218, 250-288) --- */
+    double threshold_pos;
+    double min_xy_pos[2], max_xy_pos[2]; /* mover spawn box */
+    double min_goal_dist;                /* planning: strict '<' rejects (planning:410) */
+    double std_noise[3];                 /* sigma for position, velocity, acceleration (basic_envs.py:184-192) */
+    int32_t autoreset_mode;              /* gpr_autoreset_mode */
+    int32_t max_reset_attempts;          /* cap on the rejection-sampling loops (reference: unbounded) */
+
+    /* --- pushing only (pushing:172-178, 250-288, 332-342; utils/impedance_control.py:28-55) --- */
+    double object_min_xy_pos[2], object_max_xy_pos[2];
+    double min_mo_dist;     /* strict '>' accepts (pushing:404) */
+    double object_noise_xy; /* 1e-5 (pushing:178) */
+    double object_half_xy;  /* 0.035 */
+    double object_mass;     /* 0.01 */
+    double object_damping;  /* free-joint damping 0.01 on every DOF (pushing:337) */
+    double mover_half[2];   /* physical mover half sizes (0.0775, 0.0775) */
+    double mover_mass;      /* 1.24 */
+    double imp_k_rot;       /* rotational stiffness 0.1 */
+    double gravity;         /* 9.81 */
+    double friction;        /* MuJoCo default geom friction 1.0 */
+    double solref[2];       /* MuJoCo default (0.02, 1) */
+    double solimp[5];       /* MuJoCo default (0.9, 0.95, 0.001, 0.5, 2) */
+    int32_t contact_iterations; /* projected Gauss-Seidel sweeps of the planar contact solve */
+    int32_t reserved_i32;
+} gpr_config;
+
+/* Per-step results. Device pointers (host pointers for *_host calls), caller-owned, row-major; NULL = do not write.
+ * planning: obs_dim = 2*N*(1+learn_jerk) (planning:242-254), goal_dim = 2*N
+ * pushing : obs_dim = 2*(2+learn_jerk)   (pushing:232-247),  goal_dim = 2                                           */
+typedef struct gpr_outputs {
+    float* observation;   /* [num_envs, obs_dim]  */
+    float* achieved_goal; /* [num_envs, goal_dim] */
+    float* desired_goal;  /* [num_envs, goal_dim] */
+    float* reward;        /* [num_envs] */
+    uint8_t* terminated;  /* [num_envs] compute_terminated (planning:459-479, pushing:457-476) */
+    uint8_t* truncated;   /* [num_envs] TimeLimit: elapsed_steps >= max_episode_steps */
+    uint8_t* is_success;  /* [num_envs] info['is_success'] (planning:596-601) */
+    uint8_t* mover_collision;
+    uint8_t* wall_collision;
+    /* SAME_STEP autoreset only: terminal observation of the envs that finished in this step (rows of other envs are
+       left untouched).  observation/achieved_goal/desired_goal above then hold the first observation of the new episode. */
+    float* final_observation;
+    float* final_achieved_goal;
+    float* final_desired_goal;
+} gpr_outputs;
+
+/* Structure-of-arrays state, float64. Device pointers, caller-owned copies; NULL = skip that field.
+ * planning: pos/vel/acc/goal are [num_envs, N, 2]; `acc` is MuJoCo's qacc == the jerk integrator state `act`.
+ * pushing : pos/vel/acc are [num_envs, 1, 2]; goal is [num_envs, 2]; the extra fields below are used.                */
+typedef struct gpr_state {
+    double* pos;
+    double* vel;
+    double* acc;
+    double* goal;
+    int32_t* elapsed_steps; /* [num_envs] TimeLimit counter */
+    uint32_t* rng_counter;  /* [num_envs] number of step/reset events consumed so far (Philox counter word) */
+    /* pushing only */
+    double* act;         /* [num_envs, 2] jerk-mode integrator state (differs from qacc under contact) */
+    double* mover_yaw;   /* [num_envs, 2] yaw, yaw rate */
+    double* object_pos;  /* [num_envs, 3] x, y, yaw */
+    double* object_vel;  /* [num_envs, 3] */
+} gpr_state;
+
+typedef struct gpr_handle gpr_handle;
+
+/* sizeof(gpr_config) / ABI version as compiled into the library (binding self-check). */
+uint32_t gpr_config_bytes(void);
+uint32_t gpr_abi_version(void);
+
+/* Text of the last error on the calling thread ("" if none). */
+const char* gpr_last_error(void);
+
+/* Allocate the SoA state for cfg->num_envs environments on `device`. State is undefined until gpr_reset. */
+int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_handle);
+void gpr_destroy(gpr_handle* h);
+
+/* Dimensions implied by the config (so bindings need not duplicate the formulas). */
+int gpr_obs_dim(const gpr_handle* h);
+int gpr_goal_dim(const gpr_handle* h);
+int gpr_action_dim(const gpr_handle* h);
+
+/*
+ * Start new episodes.
+ *   reset_mask   : [num_envs] device bytes, non-zero = reset that env; NULL = all.
+ *   seed         : if reseed != 0 the RNG key becomes `seed` and all RNG counters restart at 0 (reference: reset(seed=..)).
+ *   inject_start : NULL -> rejection-sample like planning:369-385 / pushing:386-404; else device float64
+ *                  [num_envs, N, 2] mover start positions taken as given (parity tests; reference: reload_model(...)).
+ *   inject_goal  : same for goals [num_envs, goal_dim/2, 2] (pushing: object goal).
+ *   inject_object: pushing only, [num_envs, 2] object start position; NULL -> sampled.
+ *   out          : observation / achieved / desired / is_success / mover_collision / wall_collision are written for the
+ *                  reset envs (reset() returns (obs, info), basic_envs.py:1807-1833); reward/terminated/truncated untouched.
+ */
+int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, uint64_t seed, const double* inject_start,
+              const double* inject_goal, const double* inject_object, const gpr_outputs* out, void* stream);
+
+/* One env-step for every environment: action clip, num_cycles x {limit control, integrate, wall + mover checks, break on
+ * collision}, observation, info, reward, terminated, truncated, optional auto-reset.  action: device float32
+ * [num_envs, action_dim]. */
+int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* out, void* stream);
+
+/* Same step, called the way a user of the reference calls it: HOST buffers in, HOST buffers out.  The action is staged
+ * through pinned memory, copied to the device, stepped, and every non-NULL output is copied back; returns after the host
+ * buffers are valid.  `host_out` holds host pointers. */
+int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out);
+int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_outputs* host_out);
+
+/* Copy state out of / into the handle (device pointers, float64). */
+int gpr_get_state(gpr_handle* h, const gpr_state* dst, void* stream);
+int gpr_set_state(gpr_handle* h, const gpr_state* src, void* stream);
+
+/* HER relabelling: batched compute_reward / compute_terminated on device.
+ *   achieved, desired : float32 [batch, goal_dim]; mover_collision, wall_collision: [batch] bytes (NULL = all false)
+ *   reward : float32 [batch] or NULL; terminated : bytes [batch] or NULL                                             */
+int gpr_compute_reward(gpr_handle* h, int batch, const float* achieved, const float* desired,
+                       const uint8_t* mover_collision, const uint8_t* wall_collision, float* reward, uint8_t* terminated,
+                       void* stream);
+
+/* Episode statistics accumulated on device since the last call with reset_after != 0 (6 float64 values):
+ * [episodes finished, sum of returns, sum of lengths, successes, mover collisions, wall collisions].
+ * `dst` is a device pointer; the caller may all-reduce it over ranks (NCCL) — nothing on the step path communicates. */
+int gpr_episode_stats(gpr_handle* h, double* dst, int reset_after, void* stream);
+
+/* Number of kernels this library has launched on behalf of the handle (bench "gpu_launches" evidence). */
+uint64_t gpr_launch_count(const gpr_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPR_H_ */
