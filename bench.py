@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the GymPR step path on B200 (metric and configs: BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload planning4|pushing|planning8box]
+
+One "step" = one `step()` of every environment of the workload = num_cycles (40) control cycles of 1 ms each plus
+observation / reward / termination / auto-reset.  Default workload = BASELINE configs[1]:
+BenchmarkPlanningEnv-v0, 4 movers, 3x3 tiles, 65,536 environments PER GPU (weak scaling: env indices shard across ranks,
+no traffic on the step path), reference-default kwargs (std_noise=1e-5), random actions, SAME_STEP auto-reset.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+    roofline      dominant kernel (the fused step kernel): algorithmic bytes (8N(9+3J)+17 per env-step) x
+                  envs per launch / CUDA-event kernel time, against the measured HBM peak (MEASURED_PEAKS.json)
+    cpu_baseline  the float64 C oracle (a port of the reference's algorithm; the MuJoCo-backed reference cannot be
+                  installed offline) on this box's host cores, bounded sample
+    e2e           same metric through the host-buffer API (gpr_step_host): NumPy action in, NumPy results out, H2D and
+                  D2H copies inside the timed region
+    value_no_noise / value_f64_exact ... extra context, see DESIGN.md
+`--impl reference` times the oracle port with every host thread (rank 0 only) on the same workload/metric.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'oracle')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    'planning4': dict(kind='planning', num_envs=65536, env_id='BenchmarkPlanningEnv-v0',
+                      kwargs=dict(layout_tiles=np.ones((3, 3)), num_movers=4),
+                      desc='BenchmarkPlanningEnv-v0, 4 movers, 3x3 tiles, circle r=0.11, acc actions, 65,536 envs/GPU'),
+    # BASELINE.json configs[3]
+    'planning8box': dict(kind='planning', num_envs=262144, env_id='BenchmarkPlanningEnv-v0',
+                         kwargs=dict(layout_tiles=np.ones((5, 5)), num_movers=8, learn_jerk=True,
+                                     collision_params={'shape': 'box', 'size': np.array([0.08, 0.08])}),
+                         desc='BenchmarkPlanningEnv-v0, 8 movers, 5x5 tiles, box 0.08x0.08, jerk actions, 262,144 envs/GPU'),
+    # BASELINE.json configs[2]
+    'pushing': dict(kind='pushing', num_envs=65536, env_id='BenchmarkPushingEnv-v0', kwargs=dict(),
+                    desc='BenchmarkPushingEnv-v0, 1 mover + box object, 65,536 envs/GPU'),
+}
+
+
+def algorithmic_bytes_per_env_step(kind: str, N: int, J: int) -> int:
+    """float32 I/O, SoA state. planning 8N(9+3J)+17; pushing 161 (+24 with jerk)."""
+    return 8 * N * (9 + 3 * J) + 17 if kind == 'planning' else 161 + 24 * J
+
+
+def measured_hbm_peak() -> tuple[float, str]:
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)['hbm_gbs']), 'measured'
+        except Exception:
+            pass
+    return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_cfg(wl, num_envs, env_index_base=0, **over):
+    import gymnasium_planar_robotics_b200 as gpr
+
+    kw = dict(wl['kwargs'])
+    kw.update(over)
+    fn = gpr.planning_config if wl['kind'] == 'planning' else gpr.pushing_config
+    return fn(num_envs=num_envs, env_index_base=env_index_base, **kw)
+
+
+def time_oracle(wl, num_envs: int, steps: int, warmup: int, threads: int, seed: int = 0) -> float:
+    """env-steps/s of the CPU oracle (float64 C restatement of the reference's algorithm) on `threads` host threads."""
+    import gpr_oracle
+
+    cfg, d = make_cfg(wl, num_envs, seed=seed)
+    ora = gpr_oracle.OracleEnv(cfg, nthreads=threads)
+    ora.reset(seed=seed)
+    rng = np.random.default_rng(seed)
+    lim = cfg.j_max if cfg.learn_jerk else cfg.a_max
+    acts = [rng.uniform(-lim, lim, (num_envs, ora.action_dim)).astype(np.float32) for _ in range(4)]
+    for i in range(warmup):
+        ora.step(acts[i % 4])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ora.step(acts[i % 4])
+    return num_envs * steps / (time.perf_counter() - t0)
+
+
+def run_reference(args, wl):
+    """Reference arm: the reference's CPU implementation of the path.  The real reference needs the MuJoCo wheel, which
+    cannot be installed offline, so this runs the oracle port with every host thread (kind 'port')."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    import gpr_oracle
+
+    threads = gpr_oracle.max_threads()
+    sample_envs = 4096  # bounded sample of the same workload: the per-env cost does not depend on the batch size
+    v = time_oracle(wl, sample_envs, args.steps, max(args.warmup, 1), threads)
+    cfg, d = make_cfg(wl, sample_envs)
+    line = {
+        'impl': 'reference', 'metric': 'env-steps/s', 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * sample_envs / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': wl['desc'], 'env_id': wl['env_id'], 'num_cycles': int(cfg.num_cycles), 'std_noise': cfg.std_noise[0],
+                   'sample': f'{sample_envs} envs per step'},
+        'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
+                         'sample': f'{sample_envs} envs x {args.steps} steps, OpenMP over envs; MuJoCo-backed reference not installable offline'},
+        'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import gymnasium_planar_robotics_b200 as gpr
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    B = args.num_envs or wl['num_envs']
+
+    def build(**over):
+        cls = gpr.BenchmarkPlanningVecEnv if wl['kind'] == 'planning' else gpr.BenchmarkPushingVecEnv
+        kw = dict(wl['kwargs'])
+        kw.update(over)
+        # weak scaling: B envs per GPU, global index base = rank * B (results independent of the split)
+        return cls(B, device=dev, env_index_base=rank * B, seed=args.seed, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+
+    def timed(env, steps, warmup):
+        """Kernel time of `steps` steps: CUDA events around each launch on the launching stream, L2 flushed in between."""
+        lim = env.j_max if env.learn_jerk else env.a_max
+        acts = [(torch.rand((B, env.core.action_dim), device=dev, generator=gen) * 2 - 1) * lim for _ in range(8)]
+        env.reset(seed=args.seed)
+        for i in range(warmup):
+            env.step(acts[i % 8])
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        n0 = env.core.launch_count
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            flush.zero_()
+            ev[i][0].record()
+            env.step(acts[i % 8])
+            ev[i][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        return ms, env.core.launch_count - n0, wall
+
+    env = build()
+    with ClockSampler(local) as clk:
+        ms, launches, wall = timed(env, args.steps, args.warmup)
+    clocks = clk.summary()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+    stats = env.episode_stats(reset=True, all_reduce=world > 1)
+    fails = env.core.reset_failures()
+
+    # ---- end to end through the host-buffer API (NumPy in / NumPy out), H2D + D2H inside the timed region
+    lim = env.j_max if env.learn_jerk else env.a_max
+    rng = np.random.default_rng(5 + rank)
+    hacts = [rng.uniform(-lim, lim, (B, env.core.action_dim)).astype(np.float32) for _ in range(4)]
+    for i in range(3):
+        env.step_host(hacts[i % 4])
+    e2e_steps = max(10, args.steps // 4)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        out = env.step_host(hacts[i % 4])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(te.item())
+    h2d = B * env.core.action_dim * 4
+    d2h = int(sum(v.nbytes for v in env.core._host.values()))
+    env.close()
+
+    if rank == 0:
+        N, J = int(env.cfg.num_movers), int(env.cfg.learn_jerk)
+        abytes = algorithmic_bytes_per_env_step(wl['kind'], N, J)
+        peak, peak_src = measured_hbm_peak()
+        kernel_ms = ms_max / args.steps
+        achieved = abytes * B / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    traffic = json.load(f).get(args.workload)
+            except Exception:
+                traffic = None
+        extra = {}
+        if not args.quick:
+            # context numbers: the same workload without sensor noise (the reference tests' parity setting)
+            e0 = build(std_noise=0.0)
+            ms0, _, _ = timed(e0, max(20, args.steps // 2), 3)
+            extra['value_no_noise'] = B * max(20, args.steps // 2) / (ms0 * 1e-3) * world
+            e0.close()
+        # CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            import gpr_oracle
+
+            threads = gpr_oracle.max_threads()
+            cb, cs = 2048, 10
+            v1 = time_oracle(wl, cb, cs, 2, threads)
+            cpu = {'value': v1, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
+                   'sample': f'{cb} envs x {cs} steps of the same workload (float64 C oracle, OpenMP over envs); the MuJoCo-backed '
+                             f'reference is not installable offline'}
+        line = {
+            'metric': 'env-steps/s', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': kernel_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': wl['desc'], 'env_id': wl['env_id'], 'envs_per_gpu': B, 'num_cycles': int(env.cfg.num_cycles),
+                       'substeps_per_s': value * int(env.cfg.num_cycles), 'std_noise': env.cfg.std_noise[0], 'autoreset': 'same_step',
+                       'actions': 'uniform(-max,max), 8 pre-generated device tensors cycled',
+                       'l2': 'flushed between timed steps (256 MiB memset, outside the event pairs)', 'parallelism': f'env-shard x{world}'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                         'peak_source': peak_src, 'algorithmic_bytes_per_env_step': abytes, 'kernel': 'planning_step_kernel' if wl['kind'] == 'planning' else 'pushing_step_kernel',
+                         'note': 'issue-bound kernel (40-cycle float64 loop per env): see profiles/ for issue-slot and stall breakdown'},
+            'cpu_baseline': cpu,
+            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+                    'api': 'BenchmarkPlanningVecEnv.step_host -> gpr_step_host (pinned staging, NumPy in/out)'},
+            'gpu_launches': int(launches), 'clocks': clocks,
+            'episode_stats': stats, 'reset_failures': fails, 'wall_s_timed_region': wall,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='planning4', choices=sorted(WORKLOADS))
+    ap.add_argument('--num-envs', type=int, default=0, help='envs per GPU (default: the workload\'s)')
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--quick', action='store_true', help='skip the extra context measurements')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == '__main__':
+    main()

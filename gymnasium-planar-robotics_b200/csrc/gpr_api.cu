@@ -1,0 +1,605 @@
+// gpr_api.cu — host side of the C ABI declared in include/gpr.h (the drop-in boundary).
+//
+// The handle owns the structure-of-arrays state and the small read-only tables derived from the config; all kernels are
+// enqueued on the caller's stream.  Nothing here depends on torch.  There is no CPU fallback: every entry point either
+// launches the CUDA kernels or fails with an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "gpr_planning.cuh"
+#include "gpr_pushing.cuh"
+
+using namespace gpr;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(e_ == cudaErrorMemoryAllocation ? GPR_ERR_OUT_OF_MEMORY : GPR_ERR_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e_));                                                        \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------------------------
+struct gpr_handle {
+    gpr_config cfg;
+    int device = 0;
+    int G = 1;  // lanes per environment
+    bool noise = false;
+    uint64_t seed = 0;
+    uint64_t launches = 0;
+    int obs_dim = 0, goal_dim = 0, action_dim = 0;
+    // state
+    double2 *pos = nullptr, *vel = nullptr, *acc = nullptr, *goal = nullptr;
+    int32_t* elapsed = nullptr;
+    uint32_t* rng = nullptr;
+    uint8_t* needs_reset = nullptr;
+    float* ep_return = nullptr;
+    double* stats = nullptr;
+    uint32_t* fail_count = nullptr;
+    // pushing state
+    double2* act = nullptr;        // [B] jerk integrator state
+    double2* mover_yaw = nullptr;  // [B] (yaw, yaw rate)
+    double* obj_pos = nullptr;     // [B,3]
+    double* obj_vel = nullptr;     // [B,3]
+    // tables
+    double *cx = nullptr, *cy = nullptr, *c_wall = nullptr, *c_mover = nullptr;
+    uint16_t* cell = nullptr;
+    double quirk_rsum[2] = {0, 0};
+    // staging for the *_host entry points
+    cudaStream_t host_stream = nullptr;
+    void* d_stage = nullptr;  // device: action + all outputs
+    void* h_stage = nullptr;  // pinned mirror
+    size_t stage_bytes = 0;
+};
+
+template <typename T>
+static int dalloc(T** p, size_t n) {
+    CU(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    CU(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return GPR_OK;
+}
+
+static uint16_t cell_code(const gpr_config& c, int i, int j) {
+    auto L = [&](int a, int b) -> int {
+        if (a < 0 || b < 0 || a >= c.num_tiles_x || b >= c.num_tiles_y) return 0;
+        return c.layout[a * c.num_tiles_y + b] != 0;
+    };
+    auto in = [&](int a, int b) { return a >= 0 && b >= 0 && a < c.num_tiles_x && b < c.num_tiles_y; };
+    uint32_t code = 0;
+    if (L(i, j)) code |= CELL_T;
+    if (L(i - 1, j)) code |= CELL_W;
+    if (L(i + 1, j)) code |= CELL_E;
+    if (L(i, j - 1)) code |= CELL_S;
+    if (L(i, j + 1)) code |= CELL_N;
+    if (L(i - 1, j - 1)) code |= CELL_SW;
+    if (L(i - 1, j + 1)) code |= CELL_NW;
+    if (L(i + 1, j - 1)) code |= CELL_SE;
+    if (L(i + 1, j + 1)) code |= CELL_NE;
+    bool full = i >= 1 && j >= 1 && i <= c.num_tiles_x - 2 && j <= c.num_tiles_y - 2;
+    for (int a = -1; a <= 1 && full; ++a)
+        for (int b = -1; b <= 1; ++b) full = full && L(i + a, j + b);
+    if (full) code |= CELL_3X3;
+    auto ic = [&](int di, int dj) { return L(i, j) && L(i + di, j) && L(i, j + dj) && in(i + di, j + dj) && !L(i + di, j + dj); };
+    if (ic(+1, -1)) code |= CELL_IC_SE;
+    if (ic(+1, +1)) code |= CELL_IC_NE;
+    if (ic(-1, -1)) code |= CELL_IC_SW;
+    if (ic(-1, +1)) code |= CELL_IC_NW;
+    return (uint16_t)code;
+}
+
+static int next_pow2(int n) {
+    int g = 1;
+    while (g < n) g <<= 1;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ABI: introspection
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" uint32_t gpr_config_bytes(void) { return (uint32_t)sizeof(gpr_config); }
+extern "C" uint32_t gpr_abi_version(void) { return GPR_ABI_VERSION; }
+extern "C" const char* gpr_last_error(void) { return g_err; }
+extern "C" int gpr_obs_dim(const gpr_handle* h) { return h ? h->obs_dim : GPR_ERR_INVALID_ARG; }
+extern "C" int gpr_goal_dim(const gpr_handle* h) { return h ? h->goal_dim : GPR_ERR_INVALID_ARG; }
+extern "C" int gpr_action_dim(const gpr_handle* h) { return h ? h->action_dim : GPR_ERR_INVALID_ARG; }
+extern "C" uint64_t gpr_launch_count(const gpr_handle* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------------------------------------------------
+static int validate(const gpr_config* c) {
+    if (!c) return fail(GPR_ERR_INVALID_ARG, "config is NULL");
+    if (c->struct_bytes != sizeof(gpr_config) || c->abi_version != GPR_ABI_VERSION)
+        return fail(GPR_ERR_ABI_MISMATCH, "gpr_config mismatch: caller %u bytes / ABI %u, library %zu bytes / ABI %d",
+                    c->struct_bytes, c->abi_version, sizeof(gpr_config), GPR_ABI_VERSION);
+    if (c->env_kind != GPR_ENV_PLANNING && c->env_kind != GPR_ENV_PUSHING)
+        return fail(GPR_ERR_INVALID_ARG, "env_kind %d unknown", c->env_kind);
+    if (c->num_envs <= 0) return fail(GPR_ERR_INVALID_ARG, "num_envs must be > 0");
+    if (c->num_movers <= 0 || c->num_movers > GPR_MAX_MOVERS)
+        return fail(GPR_ERR_INVALID_ARG, "num_movers must be in [1, %d]", GPR_MAX_MOVERS);
+    if (c->env_kind == GPR_ENV_PUSHING && c->num_movers != 1)
+        return fail(GPR_ERR_INVALID_ARG, "the pushing env has exactly one mover (pushing:196)");
+    if (c->num_tiles_x <= 0 || c->num_tiles_y <= 0 || c->num_tiles_x > GPR_MAX_TILES_1D || c->num_tiles_y > GPR_MAX_TILES_1D)
+        return fail(GPR_ERR_INVALID_ARG, "tile grid must be within [1, %d] per axis", GPR_MAX_TILES_1D);
+    if (!(c->tile_half[0] > 0) || !(c->tile_half[1] > 0)) return fail(GPR_ERR_INVALID_ARG, "tile_half must be > 0");
+    if (c->c_shape != GPR_SHAPE_CIRCLE && c->c_shape != GPR_SHAPE_BOX) return fail(GPR_ERR_INVALID_ARG, "c_shape unknown");
+    if (c->num_cycles <= 0) return fail(GPR_ERR_INVALID_ARG, "num_cycles must be > 0");
+    if (!(c->cycle_time > 0)) return fail(GPR_ERR_INVALID_ARG, "cycle_time must be > 0");
+    if (!(c->v_max > 0) || !(c->a_max > 0) || !(c->j_max > 0)) return fail(GPR_ERR_INVALID_ARG, "v/a/j limits must be > 0");
+    if (c->autoreset_mode < GPR_AUTORESET_OFF || c->autoreset_mode > GPR_AUTORESET_NEXT_STEP)
+        return fail(GPR_ERR_INVALID_ARG, "autoreset_mode unknown");
+    if (c->env_index_base < 0 || (uint64_t)c->env_index_base + (uint64_t)c->num_envs > (1ull << 32))
+        return fail(GPR_ERR_INVALID_ARG, "global env indices must fit 32 bits");
+    for (int m = 0; m < c->num_movers; ++m)
+        for (int s = 0; s < 2; ++s) {
+            if (!(c->c_wall[s][m][0] > 0) || !(c->c_mover[s][m][0] > 0))
+                return fail(GPR_ERR_INVALID_ARG, "collision sizes must be > 0");
+            // basic_envs.py:650 asserts when a shape is as wide as a tile; refuse such configs up front
+            if (c->c_shape == GPR_SHAPE_CIRCLE && c->c_wall[s][m][0] >= std::min(c->tile_half[0], c->tile_half[1]))
+                return fail(GPR_ERR_INVALID_ARG, "collision circle must be smaller than half a tile");
+        }
+    return GPR_OK;
+}
+
+extern "C" void gpr_destroy(gpr_handle* h) {
+    if (!h) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    void* ptrs[] = {h->pos, h->vel, h->acc, h->goal, h->elapsed, h->rng, h->needs_reset, h->ep_return, h->stats,
+                    h->fail_count, h->act, h->mover_yaw, h->obj_pos, h->obj_vel, h->cx, h->cy, h->c_wall, h->c_mover,
+                    h->cell, h->d_stage};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    cudaSetDevice(prev);
+    delete h;
+}
+
+extern "C" int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_handle) {
+    if (!out_handle) return fail(GPR_ERR_INVALID_ARG, "out_handle is NULL");
+    *out_handle = nullptr;
+    int rc = validate(cfg);
+    if (rc != GPR_OK) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(GPR_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(GPR_ERR_INVALID_ARG, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    gpr_handle* h = new (std::nothrow) gpr_handle();
+    if (!h) return fail(GPR_ERR_OUT_OF_MEMORY, "host allocation failed");
+    h->cfg = *cfg;
+    h->device = device;
+    h->seed = cfg->seed;
+    h->G = next_pow2(cfg->num_movers);
+    h->noise = cfg->std_noise[0] != 0.0 || cfg->std_noise[1] != 0.0 ||
+               (cfg->env_kind == GPR_ENV_PUSHING && cfg->object_noise_xy != 0.0);
+    const int N = cfg->num_movers, J = cfg->learn_jerk != 0;
+    if (cfg->env_kind == GPR_ENV_PLANNING) {
+        h->obs_dim = 2 * N * (1 + J);
+        h->goal_dim = 2 * N;
+        h->action_dim = 2 * N;
+    } else {
+        h->obs_dim = 2 * (2 + J);
+        h->goal_dim = 2;
+        h->action_dim = 2;
+    }
+    const size_t B = (size_t)cfg->num_envs, BN = B * (size_t)N;
+#define TRY(x)                 \
+    do {                       \
+        rc = (x);              \
+        if (rc != GPR_OK) {    \
+            gpr_destroy(h);    \
+            return rc;         \
+        }                      \
+    } while (0)
+    TRY(dalloc(&h->pos, BN));
+    TRY(dalloc(&h->vel, BN));
+    TRY(dalloc(&h->acc, BN));
+    TRY(dalloc(&h->goal, cfg->env_kind == GPR_ENV_PLANNING ? BN : B));
+    TRY(dalloc(&h->elapsed, B));
+    TRY(dalloc(&h->rng, B));
+    TRY(dalloc(&h->needs_reset, B));
+    TRY(dalloc(&h->ep_return, B));
+    TRY(dalloc(&h->stats, 6));
+    TRY(dalloc(&h->fail_count, 1));
+    if (cfg->env_kind == GPR_ENV_PUSHING) {
+        TRY(dalloc(&h->act, B));
+        TRY(dalloc(&h->mover_yaw, B));
+        TRY(dalloc(&h->obj_pos, 3 * B));
+        TRY(dalloc(&h->obj_vel, 3 * B));
+    }
+    TRY(dalloc(&h->cx, GPR_MAX_TILES_1D));
+    TRY(dalloc(&h->cy, GPR_MAX_TILES_1D));
+    TRY(dalloc(&h->c_wall, 2 * GPR_MAX_MOVERS * 2));
+    TRY(dalloc(&h->c_mover, 2 * GPR_MAX_MOVERS * 2));
+    TRY(dalloc(&h->cell, GPR_MAX_TILES_1D * GPR_MAX_TILES_1D));
+#undef TRY
+    std::vector<uint16_t> codes((size_t)cfg->num_tiles_x * cfg->num_tiles_y);
+    for (int i = 0; i < cfg->num_tiles_x; ++i)
+        for (int j = 0; j < cfg->num_tiles_y; ++j) codes[(size_t)i * cfg->num_tiles_y + j] = cell_code(*cfg, i, j);
+    auto up = [&](void* dst, const void* src, size_t n) { return cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); };
+    cudaError_t e = up(h->cx, cfg->tile_cx, sizeof(cfg->tile_cx));
+    if (e == cudaSuccess) e = up(h->cy, cfg->tile_cy, sizeof(cfg->tile_cy));
+    if (e == cudaSuccess) e = up(h->c_wall, cfg->c_wall, sizeof(cfg->c_wall));
+    if (e == cudaSuccess) e = up(h->c_mover, cfg->c_mover, sizeof(cfg->c_mover));
+    if (e == cudaSuccess) e = up(h->cell, codes.data(), codes.size() * sizeof(uint16_t));
+    if (e != cudaSuccess) {
+        gpr_destroy(h);
+        return fail(GPR_ERR_CUDA, "table upload: %s", cudaGetErrorString(e));
+    }
+    // basic:409 quirk: one threshold for all pairs = max over pairs of r_i + r_j
+    for (int s = 0; s < 2; ++s) {
+        double mx = -INFINITY;
+        for (int i = 0; i < N - 1; ++i)
+            for (int j = i + 1; j < N; ++j) mx = std::max(mx, cfg->c_mover[s][i][0] + cfg->c_mover[s][j][0]);
+        h->quirk_rsum[s] = mx;
+    }
+    *out_handle = h;
+    g_err[0] = 0;
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// argument packing and dispatch
+// ---------------------------------------------------------------------------------------------------------------------
+static LayoutArgs layout_args(const gpr_handle* h) {
+    const gpr_config& c = h->cfg;
+    LayoutArgs L;
+    L.nx = c.num_tiles_x;
+    L.ny = c.num_tiles_y;
+    L.hx = c.tile_half[0];
+    L.hy = c.tile_half[1];
+    L.inv_wx = 1.0 / (2.0 * c.tile_half[0]);
+    L.inv_wy = 1.0 / (2.0 * c.tile_half[1]);
+    L.cx = h->cx;
+    L.cy = h->cy;
+    L.cell = h->cell;
+    return L;
+}
+
+static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
+    const gpr_config& c = h->cfg;
+    PlanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = c.num_envs;
+    a.N = c.num_movers;
+    a.learn_jerk = c.learn_jerk != 0;
+    a.num_cycles = c.num_cycles;
+    a.max_episode_steps = c.max_episode_steps;
+    a.autoreset = c.autoreset_mode;
+    a.max_reset_attempts = c.max_reset_attempts;
+    a.quirks = c.reference_quirks != 0 && c.c_shape == GPR_SHAPE_CIRCLE;
+    a.env_base = (uint32_t)c.env_index_base;
+    a.seed = h->seed;
+    a.dt = c.cycle_time;
+    a.v_max = c.v_max;
+    a.a_max = c.a_max;
+    a.j_max = c.j_max;
+    a.act_lim = c.learn_jerk ? c.j_max : c.a_max;  // plan:257-259
+    a.v_max2_lo = c.v_max * c.v_max * (1.0 - 1e-14);
+    a.a_max2_lo = c.a_max * c.a_max * (1.0 - 1e-14);
+    a.threshold = c.threshold_pos;
+    a.min_goal_dist = c.min_goal_dist;
+    for (int k = 0; k < 2; ++k) {
+        a.min_xy[k] = c.min_xy_pos[k];
+        a.span_xy[k] = c.max_xy_pos[k] - c.min_xy_pos[k];  // numpy uniform: low + (high-low)*u
+        a.quirk_rsum[k] = h->quirk_rsum[k];
+    }
+    a.sigma_p = c.std_noise[0];
+    a.sigma_v = c.std_noise[1];
+    a.L = layout_args(h);
+    a.c_wall = h->c_wall;
+    a.c_mover = h->c_mover;
+    a.pos = h->pos;
+    a.vel = h->vel;
+    a.acc = h->acc;
+    a.goal = h->goal;
+    a.elapsed = h->elapsed;
+    a.rng = h->rng;
+    a.needs_reset = h->needs_reset;
+    a.ep_return = h->ep_return;
+    a.stats = h->stats;
+    a.fail_count = h->fail_count;
+    if (out) a.out = *out;
+    return a;
+}
+
+template <int G, bool BOX>
+static cudaError_t launch_plan_gb(bool reset, bool noise, const PlanArgs& a, cudaStream_t s) {
+    const int threads = 256;
+    const long long lanes = (long long)a.B * G;
+    const unsigned blocks = (unsigned)((lanes + threads - 1) / threads);
+    if (reset) {
+        if (noise)
+            planning_reset_kernel<G, BOX, true><<<blocks, threads, 0, s>>>(a);
+        else
+            planning_reset_kernel<G, BOX, false><<<blocks, threads, 0, s>>>(a);
+    } else {
+        if (noise)
+            planning_step_kernel<G, BOX, true><<<blocks, threads, 0, s>>>(a);
+        else
+            planning_step_kernel<G, BOX, false><<<blocks, threads, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+template <int G>
+static cudaError_t launch_plan_g(bool reset, bool box, bool noise, const PlanArgs& a, cudaStream_t s) {
+    return box ? launch_plan_gb<G, true>(reset, noise, a, s) : launch_plan_gb<G, false>(reset, noise, a, s);
+}
+
+static cudaError_t launch_plan(const gpr_handle* h, bool reset, const PlanArgs& a, cudaStream_t s) {
+    const bool box = h->cfg.c_shape == GPR_SHAPE_BOX;
+    switch (h->G) {
+        case 1: return launch_plan_g<1>(reset, box, h->noise, a, s);
+        case 2: return launch_plan_g<2>(reset, box, h->noise, a, s);
+        case 4: return launch_plan_g<4>(reset, box, h->noise, a, s);
+        case 8: return launch_plan_g<8>(reset, box, h->noise, a, s);
+        case 16: return launch_plan_g<16>(reset, box, h->noise, a, s);
+        default: return launch_plan_g<32>(reset, box, h->noise, a, s);
+    }
+}
+
+static PushArgs push_args(const gpr_handle* h, const gpr_outputs* out) {
+    PushArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = h->cfg.num_envs;
+    if (out) a.out = *out;
+    return a;
+}
+static cudaError_t launch_push(const gpr_handle*, bool, const PushArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// reset / step
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, uint64_t seed, const double* inject_start,
+                         const double* inject_goal, const double* inject_object, const gpr_outputs* out, void* stream) {
+    if (!h) return fail(GPR_ERR_INVALID_ARG, "handle is NULL");
+    DeviceGuard g(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (reseed) {
+        // reference: reset(seed=...) re-creates np_random and rng_noise (basic_envs.py:1789-1791)
+        h->seed = seed;
+        CU(cudaMemsetAsync(h->rng, 0, sizeof(uint32_t) * (size_t)h->cfg.num_envs, s));
+    }
+    if (h->cfg.env_kind == GPR_ENV_PLANNING) {
+        if (inject_object) return fail(GPR_ERR_INVALID_ARG, "inject_object is for the pushing env");
+        PlanArgs a = plan_args(h, out);
+        a.reset_mask = reset_mask;
+        a.inject_start = reinterpret_cast<const double2*>(inject_start);
+        a.inject_goal = reinterpret_cast<const double2*>(inject_goal);
+        CU(launch_plan(h, true, a, s));
+    } else {
+        PushArgs a = push_args(h, out);
+        a.reset_mask = reset_mask;
+        a.inject_start = reinterpret_cast<const double2*>(inject_start);
+        a.inject_goal = reinterpret_cast<const double2*>(inject_goal);
+        a.inject_object = reinterpret_cast<const double2*>(inject_object);
+        CU(launch_push(h, true, a, s));
+    }
+    h->launches += 1;
+    return GPR_OK;
+}
+
+extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* out, void* stream) {
+    if (!h) return fail(GPR_ERR_INVALID_ARG, "handle is NULL");
+    if (!action) return fail(GPR_ERR_INVALID_ARG, "action is NULL");
+    if (!out) return fail(GPR_ERR_INVALID_ARG, "outputs struct is NULL");
+    DeviceGuard g(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->cfg.env_kind == GPR_ENV_PLANNING) {
+        PlanArgs a = plan_args(h, out);
+        a.action = reinterpret_cast<const float2*>(action);
+        CU(launch_plan(h, false, a, s));
+    } else {
+        PushArgs a = push_args(h, out);
+        a.action = reinterpret_cast<const float2*>(action);
+        CU(launch_push(h, false, a, s));
+    }
+    h->launches += 1;
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host-buffer entry points (what a user of the reference calls: NumPy in, NumPy out)
+// ---------------------------------------------------------------------------------------------------------------------
+struct StageLayout {
+    size_t off_action, off[12], bytes[12], total;
+};
+
+static StageLayout stage_layout(const gpr_handle* h) {
+    const size_t B = (size_t)h->cfg.num_envs;
+    StageLayout L;
+    size_t cur = 0;
+    auto take = [&](size_t n) {
+        size_t o = cur;
+        cur += (n + 255) & ~(size_t)255;
+        return o;
+    };
+    L.off_action = take(B * h->action_dim * sizeof(float));
+    const size_t sz[12] = {B * h->obs_dim * sizeof(float), B * h->goal_dim * sizeof(float), B * h->goal_dim * sizeof(float),
+                           B * sizeof(float), B, B, B, B, B,
+                           B * h->obs_dim * sizeof(float), B * h->goal_dim * sizeof(float), B * h->goal_dim * sizeof(float)};
+    for (int k = 0; k < 12; ++k) {
+        L.bytes[k] = sz[k];
+        L.off[k] = take(sz[k]);
+    }
+    L.total = cur;
+    return L;
+}
+
+static int ensure_stage(gpr_handle* h) {
+    if (h->d_stage) return GPR_OK;
+    const StageLayout L = stage_layout(h);
+    CU(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&h->d_stage, L.total));
+    CU(cudaMemset(h->d_stage, 0, L.total));
+    CU(cudaMallocHost(&h->h_stage, L.total));
+    h->stage_bytes = L.total;
+    return GPR_OK;
+}
+
+static void** out_slot(gpr_outputs* o, int k) {
+    void** slots[12] = {(void**)&o->observation,      (void**)&o->achieved_goal,       (void**)&o->desired_goal,
+                        (void**)&o->reward,           (void**)&o->terminated,          (void**)&o->truncated,
+                        (void**)&o->is_success,       (void**)&o->mover_collision,     (void**)&o->wall_collision,
+                        (void**)&o->final_observation, (void**)&o->final_achieved_goal, (void**)&o->final_desired_goal};
+    return slots[k];
+}
+
+static int copy_back(gpr_handle* h, const StageLayout& L, const gpr_outputs* host_out) {
+    gpr_outputs ho = *host_out;
+    char* hs = (char*)h->h_stage;
+    char* ds = (char*)h->d_stage;
+    for (int k = 0; k < 12; ++k)
+        if (*out_slot(&ho, k)) CU(cudaMemcpyAsync(hs + L.off[k], ds + L.off[k], L.bytes[k], cudaMemcpyDeviceToHost, h->host_stream));
+    CU(cudaStreamSynchronize(h->host_stream));
+    for (int k = 0; k < 12; ++k)
+        if (*out_slot(&ho, k)) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
+    return GPR_OK;
+}
+
+static gpr_outputs device_outputs(gpr_handle* h, const StageLayout& L, const gpr_outputs* host_out) {
+    gpr_outputs ho = *host_out, dv;
+    memset(&dv, 0, sizeof(dv));
+    for (int k = 0; k < 12; ++k)
+        if (*out_slot(&ho, k)) *out_slot(&dv, k) = (char*)h->d_stage + L.off[k];
+    return dv;
+}
+
+extern "C" int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out) {
+    if (!h || !host_action || !host_out) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(h->device);
+    int rc = ensure_stage(h);
+    if (rc != GPR_OK) return rc;
+    const StageLayout L = stage_layout(h);
+    const size_t abytes = (size_t)h->cfg.num_envs * h->action_dim * sizeof(float);
+    memcpy((char*)h->h_stage + L.off_action, host_action, abytes);
+    CU(cudaMemcpyAsync((char*)h->d_stage + L.off_action, (char*)h->h_stage + L.off_action, abytes, cudaMemcpyHostToDevice,
+                       h->host_stream));
+    gpr_outputs dv = device_outputs(h, L, host_out);
+    rc = gpr_step(h, (const float*)((char*)h->d_stage + L.off_action), &dv, h->host_stream);
+    if (rc != GPR_OK) return rc;
+    return copy_back(h, L, host_out);
+}
+
+extern "C" int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_outputs* host_out) {
+    if (!h || !host_out) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(h->device);
+    int rc = ensure_stage(h);
+    if (rc != GPR_OK) return rc;
+    const StageLayout L = stage_layout(h);
+    gpr_outputs dv = device_outputs(h, L, host_out);
+    rc = gpr_reset(h, nullptr, reseed, seed, nullptr, nullptr, nullptr, &dv, h->host_stream);
+    if (rc != GPR_OK) return rc;
+    return copy_back(h, L, host_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// state access, HER rewards, statistics
+// ---------------------------------------------------------------------------------------------------------------------
+static int copy_state(gpr_handle* h, const gpr_state* st, bool to_handle, cudaStream_t s) {
+    const size_t B = (size_t)h->cfg.num_envs, BN = B * (size_t)h->cfg.num_movers;
+    const bool push = h->cfg.env_kind == GPR_ENV_PUSHING;
+    struct Item {
+        void* mine;
+        void* theirs;
+        size_t bytes;
+    } items[] = {
+        {h->pos, st->pos, BN * sizeof(double2)},
+        {h->vel, st->vel, BN * sizeof(double2)},
+        {h->acc, st->acc, BN * sizeof(double2)},
+        {h->goal, st->goal, (push ? B : BN) * sizeof(double2)},
+        {h->elapsed, st->elapsed_steps, B * sizeof(int32_t)},
+        {h->rng, st->rng_counter, B * sizeof(uint32_t)},
+        {h->act, st->act, B * sizeof(double2)},
+        {h->mover_yaw, st->mover_yaw, B * sizeof(double2)},
+        {h->obj_pos, st->object_pos, 3 * B * sizeof(double)},
+        {h->obj_vel, st->object_vel, 3 * B * sizeof(double)},
+    };
+    for (const Item& it : items) {
+        if (!it.theirs) continue;
+        if (!it.mine) return fail(GPR_ERR_INVALID_ARG, "state field not present for this env kind");
+        CU(cudaMemcpyAsync(to_handle ? it.mine : it.theirs, to_handle ? it.theirs : it.mine, it.bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    return GPR_OK;
+}
+
+extern "C" int gpr_get_state(gpr_handle* h, const gpr_state* dst, void* stream) {
+    if (!h || !dst) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(h->device);
+    return copy_state(h, dst, false, (cudaStream_t)stream);
+}
+
+extern "C" int gpr_set_state(gpr_handle* h, const gpr_state* src, void* stream) {
+    if (!h || !src) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(h->device);
+    return copy_state(h, src, true, (cudaStream_t)stream);
+}
+
+extern "C" int gpr_compute_reward(gpr_handle* h, int batch, const float* achieved, const float* desired,
+                                  const uint8_t* mover_collision, const uint8_t* wall_collision, float* reward,
+                                  uint8_t* terminated, void* stream) {
+    if (!h || !achieved || !desired) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    if (batch < 0) return fail(GPR_ERR_INVALID_ARG, "batch < 0");
+    if (batch == 0) return GPR_OK;
+    DeviceGuard g(h->device);
+    const int threads = 256;
+    compute_reward_kernel<<<(batch + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+        h->cfg.env_kind, h->cfg.num_movers, batch, h->cfg.threshold_pos, achieved, desired, mover_collision, wall_collision,
+        reward, terminated);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return GPR_OK;
+}
+
+extern "C" int gpr_episode_stats(gpr_handle* h, double* dst, int reset_after, void* stream) {
+    if (!h || !dst) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(dst, h->stats, 6 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (reset_after) CU(cudaMemsetAsync(h->stats, 0, 6 * sizeof(double), s));
+    return GPR_OK;
+}
+
+extern "C" int gpr_reset_failures(gpr_handle* h, uint32_t* host_count) {
+    if (!h || !host_count) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(h->device);
+    CU(cudaMemcpy(host_count, h->fail_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return GPR_OK;
+}

@@ -42,6 +42,12 @@ extern "C" {
 
 #define GPR_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define GPR_API __attribute__((visibility("default")))
+#else
+#define GPR_API
+#endif
+
 #define GPR_MAX_MOVERS 32   /* one lane per mover, one lane group (<= one warp) per environment */
 #define GPR_MAX_TILES_1D 32 /* tiles per axis */
 
@@ -166,20 +172,20 @@ typedef struct gpr_state {
 typedef struct gpr_handle gpr_handle;
 
 /* sizeof(gpr_config) / ABI version as compiled into the library (binding self-check). */
-uint32_t gpr_config_bytes(void);
-uint32_t gpr_abi_version(void);
+GPR_API uint32_t gpr_config_bytes(void);
+GPR_API uint32_t gpr_abi_version(void);
 
 /* Text of the last error on the calling thread ("" if none). */
-const char* gpr_last_error(void);
+GPR_API const char* gpr_last_error(void);
 
 /* Allocate the SoA state for cfg->num_envs environments on `device`. State is undefined until gpr_reset. */
-int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_handle);
-void gpr_destroy(gpr_handle* h);
+GPR_API int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_handle);
+GPR_API void gpr_destroy(gpr_handle* h);
 
 /* Dimensions implied by the config (so bindings need not duplicate the formulas). */
-int gpr_obs_dim(const gpr_handle* h);
-int gpr_goal_dim(const gpr_handle* h);
-int gpr_action_dim(const gpr_handle* h);
+GPR_API int gpr_obs_dim(const gpr_handle* h);
+GPR_API int gpr_goal_dim(const gpr_handle* h);
+GPR_API int gpr_action_dim(const gpr_handle* h);
 
 /*
  * Start new episodes.
@@ -192,38 +198,41 @@ int gpr_action_dim(const gpr_handle* h);
  *   out          : observation / achieved / desired / is_success / mover_collision / wall_collision are written for the
  *                  reset envs (reset() returns (obs, info), basic_envs.py:1807-1833); reward/terminated/truncated untouched.
  */
-int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, uint64_t seed, const double* inject_start,
+GPR_API int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, uint64_t seed, const double* inject_start,
               const double* inject_goal, const double* inject_object, const gpr_outputs* out, void* stream);
 
 /* One env-step for every environment: action clip, num_cycles x {limit control, integrate, wall + mover checks, break on
  * collision}, observation, info, reward, terminated, truncated, optional auto-reset.  action: device float32
  * [num_envs, action_dim]. */
-int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* out, void* stream);
+GPR_API int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* out, void* stream);
 
 /* Same step, called the way a user of the reference calls it: HOST buffers in, HOST buffers out.  The action is staged
  * through pinned memory, copied to the device, stepped, and every non-NULL output is copied back; returns after the host
  * buffers are valid.  `host_out` holds host pointers. */
-int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out);
-int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_outputs* host_out);
+GPR_API int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out);
+GPR_API int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_outputs* host_out);
 
 /* Copy state out of / into the handle (device pointers, float64). */
-int gpr_get_state(gpr_handle* h, const gpr_state* dst, void* stream);
-int gpr_set_state(gpr_handle* h, const gpr_state* src, void* stream);
+GPR_API int gpr_get_state(gpr_handle* h, const gpr_state* dst, void* stream);
+GPR_API int gpr_set_state(gpr_handle* h, const gpr_state* src, void* stream);
 
 /* HER relabelling: batched compute_reward / compute_terminated on device.
  *   achieved, desired : float32 [batch, goal_dim]; mover_collision, wall_collision: [batch] bytes (NULL = all false)
  *   reward : float32 [batch] or NULL; terminated : bytes [batch] or NULL                                             */
-int gpr_compute_reward(gpr_handle* h, int batch, const float* achieved, const float* desired,
+GPR_API int gpr_compute_reward(gpr_handle* h, int batch, const float* achieved, const float* desired,
                        const uint8_t* mover_collision, const uint8_t* wall_collision, float* reward, uint8_t* terminated,
                        void* stream);
 
 /* Episode statistics accumulated on device since the last call with reset_after != 0 (6 float64 values):
  * [episodes finished, sum of returns, sum of lengths, successes, mover collisions, wall collisions].
  * `dst` is a device pointer; the caller may all-reduce it over ranks (NCCL) — nothing on the step path communicates. */
-int gpr_episode_stats(gpr_handle* h, double* dst, int reset_after, void* stream);
+GPR_API int gpr_episode_stats(gpr_handle* h, double* dst, int reset_after, void* stream);
+
+/* Number of resets whose rejection-sampling loop hit max_reset_attempts since creation (synchronous D2H read). */
+GPR_API int gpr_reset_failures(gpr_handle* h, uint32_t* host_count);
 
 /* Number of kernels this library has launched on behalf of the handle (bench "gpu_launches" evidence). */
-uint64_t gpr_launch_count(const gpr_handle* h);
+GPR_API uint64_t gpr_launch_count(const gpr_handle* h);
 
 #ifdef __cplusplus
 }

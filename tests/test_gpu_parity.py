@@ -1,0 +1,382 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): the CUDA step path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): collision / termination / done flags bit-exact; positions, velocities, observations and
+rewards within a float32 tolerance.  The path computes in float64 in the reference's operation order, so the tests demand
+MORE than the bar: the float64 state is compared for exact equality, and the float32 outputs must equal the oracle's
+float64 values rounded once.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import gpr_oracle as oracle
+import gymnasium_planar_robotics_b200 as gpr
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+
+L_RAGGED = np.array([[1, 1, 0, 1], [1, 1, 1, 1], [0, 1, 1, 0], [1, 1, 1, 1], [1, 0, 1, 1]])
+L_HOLE = np.array([[1, 1, 1, 1], [1, 0, 1, 1], [1, 1, 1, 1], [1, 1, 1, 1]])
+
+
+def make_pair(num_envs, **kw):
+    env = gpr.BenchmarkPlanningVecEnv(num_envs, device=DEV, **kw)
+    cfg, _ = gpr.planning_config(num_envs=num_envs, **kw)
+    return env, oracle.OracleEnv(cfg, nthreads=oracle.max_threads())
+
+
+def sample_starts(rng, ora, spread=1.0):
+    """Collision-free-ish injected starts/goals inside the spawn box (validity is not required: flags must still agree)."""
+    c = ora.cfg
+    lo = np.array([c.min_xy_pos[0], c.min_xy_pos[1]])
+    hi = np.array([c.max_xy_pos[0], c.max_xy_pos[1]])
+    st = rng.uniform(lo, lo + (hi - lo) * spread, (ora.B, ora.N, 2))
+    gl = rng.uniform(lo, hi, (ora.B, ora.N, 2))
+    return st, gl
+
+
+def assert_outputs_equal(env, ora, what):
+    b = env.core.buf
+    torch.cuda.synchronize()
+    for k in ('terminated', 'truncated', 'is_success', 'mover_collision', 'wall_collision'):
+        got, ref = b[k].cpu().numpy(), getattr(ora, k)
+        assert np.array_equal(got, ref), f'{what}: {k} differs in {np.count_nonzero(got != ref)} envs'
+    assert np.array_equal(b['reward'].cpu().numpy(), ora.reward.astype(np.float32)), f'{what}: reward'
+    for k in ('observation', 'achieved_goal', 'desired_goal'):
+        got, ref = b[k].cpu().numpy(), getattr(ora, k).astype(np.float32)
+        assert np.array_equal(got, ref), f'{what}: {k} max|d|={np.abs(got - ref).max()}'
+
+
+def assert_state_equal(env, ora, what):
+    st = env.get_state()
+    torch.cuda.synchronize()
+    for k in ('pos', 'vel', 'acc', 'goal'):
+        got, ref = st[k].cpu().numpy(), getattr(ora, k)
+        assert np.array_equal(got, ref), f'{what}: state {k} max|d|={np.abs(got - ref).max()}'
+    assert np.array_equal(st['elapsed_steps'].cpu().numpy(), ora.elapsed_steps), f'{what}: elapsed'
+    assert np.array_equal(st['rng_counter'].cpu().numpy().view(np.uint32), ora.rng_counter), f'{what}: rng counter'
+
+
+def run_lockstep(env, ora, steps, rng, scale, inject=True, seed=3):
+    if inject:
+        st, gl = sample_starts(rng, ora)
+        env.reset(seed=seed, options={'mover_start_xy_pos': st, 'mover_goal_xy_pos': gl})
+        ora.reset(seed=seed, inject_start=st, inject_goal=gl)
+    else:
+        env.reset(seed=seed)
+        ora.reset(seed=seed)
+    torch.cuda.synchronize()
+    for k in ('observation', 'achieved_goal', 'desired_goal'):
+        assert np.array_equal(env.core.buf[k].cpu().numpy(), getattr(ora, k).astype(np.float32)), f'reset {k}'
+    for k in ('is_success', 'mover_collision', 'wall_collision'):
+        assert np.array_equal(env.core.buf[k].cpu().numpy(), getattr(ora, k)), f'reset {k}'
+    assert_state_equal(env, ora, 'reset')
+    events = 0
+    for t in range(steps):
+        a = rng.uniform(-scale, scale, (ora.B, ora.action_dim)).astype(np.float32)
+        env.step(torch.as_tensor(a, device=DEV))
+        ora.step(a)
+        assert_outputs_equal(env, ora, f'step {t}')
+        events += int(ora.terminated.sum())
+    assert_state_equal(env, ora, 'final')
+    return events
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('learn_jerk', [False, True])
+@pytest.mark.parametrize('num_movers', [1, 2, 3, 4])
+def test_planning_circle_injected(num_movers, learn_jerk):
+    """BASELINE configs[0]/[1] shape: circle r=0.11 on 3x3, acc and jerk mode, no noise, injected starts and goals."""
+    rng = np.random.default_rng(100 + num_movers + 10 * learn_jerk)
+    env, ora = make_pair(1024, layout_tiles=np.ones((3, 3)), num_movers=num_movers, std_noise=0.0, learn_jerk=learn_jerk,
+                         autoreset_mode='off', max_episode_steps=50)
+    lim = 100.0 if learn_jerk else 10.0
+    ev = run_lockstep(env, ora, 30, rng, 1.3 * lim)
+    assert ev > 0  # collisions did occur and were reproduced
+    env.close()
+
+
+def test_planning_velocity_and_acceleration_clipping():
+    """The reference's own closed-form test setup (tests/test_benchmark_planning_env.py:31-45): tiny v_max / a_max on a
+    9x9 layout so both ensure_max_dyn_val clips are active nearly every cycle."""
+    rng = np.random.default_rng(5)
+    for jerk in (False, True):
+        env, ora = make_pair(512, layout_tiles=np.ones((9, 9)), num_movers=2, std_noise=0.0, learn_jerk=jerk, v_max=0.01,
+                             a_max=0.2, j_max=150.0, num_cycles=42, autoreset_mode='off', max_episode_steps=0)
+        st = np.tile(np.array([[0.96, 0.96], [1.2, 1.2]]), (512, 1, 1))
+        gl = np.tile(np.array([[0.5, 0.5], [1.5, 1.5]]), (512, 1, 1))
+        env.reset(seed=1, options={'mover_start_xy_pos': st, 'mover_goal_xy_pos': gl})
+        ora.reset(seed=1, inject_start=st, inject_goal=gl)
+        for t in range(40):
+            a = rng.uniform(-150, 150, (512, 4)).astype(np.float32)
+            env.step(torch.as_tensor(a, device=DEV))
+            ora.step(a)
+        assert_state_equal(env, ora, f'clip jerk={jerk}')
+        s = env.get_state()
+        vn = s['vel'].norm(dim=-1).max().item()
+        an = s['acc'].norm(dim=-1).max().item()
+        assert vn <= 0.01 * (1 + 1e-12) and an <= 0.2 * (1 + 1e-9)  # tests/test_benchmark_planning_env.py:116-117
+        env.close()
+
+
+@pytest.mark.parametrize('layout', [np.ones((5, 5)), L_RAGGED, L_HOLE], ids=['5x5', 'ragged', 'hole'])
+@pytest.mark.parametrize('shape', ['circle', 'box'])
+def test_planning_layouts_and_shapes(layout, shape):
+    """Arbitrary tile layouts (inner corners, holes, missing tiles) with circle and box collision shapes."""
+    rng = np.random.default_rng(11)
+    cp = {'shape': shape, 'size': 0.09 if shape == 'circle' else np.array([0.08, 0.06]), 'offset': 0.004, 'offset_wall': 0.002}
+    env, ora = make_pair(1024, layout_tiles=layout, num_movers=4, std_noise=0.0, collision_params=cp, autoreset_mode='off')
+    # starts anywhere over the grid, including over missing tiles and borders
+    W, H = layout.shape[0] * 0.24, layout.shape[1] * 0.24
+    st = rng.uniform([0.01, 0.01], [W - 0.01, H - 0.01], (1024, 4, 2))
+    st[:64] = np.round(st[:64] / 0.12) * 0.12  # exactly on tile borders / centres
+    st = np.clip(st, 0.0, [W, H])
+    gl = rng.uniform([0.1, 0.1], [W - 0.1, H - 0.1], (1024, 4, 2))
+    env.reset(seed=2, options={'mover_start_xy_pos': st, 'mover_goal_xy_pos': gl})
+    ora.reset(seed=2, inject_start=st, inject_goal=gl)
+    torch.cuda.synchronize()
+    assert np.array_equal(env.core.buf['wall_collision'].cpu().numpy(), ora.wall_collision)
+    assert np.array_equal(env.core.buf['mover_collision'].cpu().numpy(), ora.mover_collision)
+    assert 0.05 < ora.wall_collision.mean() < 0.999
+    for t in range(10):
+        a = rng.uniform(-10, 10, (1024, 8)).astype(np.float32)
+        env.step(torch.as_tensor(a, device=DEV))
+        ora.step(a)
+        assert_outputs_equal(env, ora, f'{shape} step {t}')
+    assert_state_equal(env, ora, shape)
+    env.close()
+
+
+def test_planning_box_eight_movers_jerk():
+    """BASELINE configs[3] shape: 8 movers, box 0.08 x 0.08, learn_jerk=True, 5x5 tiles."""
+    rng = np.random.default_rng(12)
+    env, ora = make_pair(1024, layout_tiles=np.ones((5, 5)), num_movers=8, std_noise=0.0, learn_jerk=True,
+                         collision_params={'shape': 'box', 'size': np.array([0.08, 0.08])}, autoreset_mode='off')
+    ev = run_lockstep(env, ora, 25, rng, 120.0)
+    assert ev > 0
+    env.close()
+
+
+@pytest.mark.parametrize('shape', ['circle', 'box'])
+def test_planning_with_sensor_noise(shape):
+    """std_noise = reference default 1e-5 (and a large 1e-3): the portable RNG makes the noise bit-identical on CPU and
+    GPU, so even noisy runs must agree exactly."""
+    for sigma in (1e-5, np.array([1e-3, 2e-3, 0.0])):
+        rng = np.random.default_rng(13)
+        cp = {'shape': shape} if shape == 'circle' else {'shape': 'box', 'size': np.array([0.08, 0.08])}
+        env, ora = make_pair(768, layout_tiles=np.ones((4, 4)), num_movers=3, std_noise=sigma, learn_jerk=True,
+                             collision_params=cp, autoreset_mode='off')
+        run_lockstep(env, ora, 12, rng, 100.0)
+        env.close()
+
+
+@pytest.mark.parametrize('mode', ['same_step', 'next_step'])
+@pytest.mark.parametrize('num_movers,layout', [(4, np.ones((3, 3))), (2, L_RAGGED), (1, np.ones((3, 3)))], ids=['4m3x3', '2mragged', '1m'])
+def test_planning_autoreset_sampled_on_device(mode, num_movers, layout):
+    """Full episodes with on-device rejection sampling of starts and goals (planning:355-418) and TimeLimit(50)."""
+    rng = np.random.default_rng(14)
+    env, ora = make_pair(512, layout_tiles=layout, num_movers=num_movers, std_noise=1e-5, autoreset_mode=mode, seed=99,
+                         max_episode_steps=12)
+    env.reset(seed=99)
+    ora.reset(seed=99)
+    done_total = 0
+    for t in range(40):
+        a = rng.uniform(-10, 10, (512, 2 * num_movers)).astype(np.float32)
+        env.step(torch.as_tensor(a, device=DEV))
+        ora.step(a)
+        assert_outputs_equal(env, ora, f'{mode} step {t}')
+        done = (ora.terminated | ora.truncated).astype(bool)
+        done_total += int(done.sum())
+        if mode == 'same_step' and done.any():
+            torch.cuda.synchronize()
+            for k in ('observation', 'achieved_goal', 'desired_goal'):
+                got = env.core.buf['final_' + k].cpu().numpy()[done]
+                assert np.array_equal(got, getattr(ora, 'final_' + k).astype(np.float32)[done]), f'final_{k}'
+    assert done_total > 100
+    assert_state_equal(env, ora, mode)
+    assert env.core.reset_failures() == int(ora.reset_failed.sum()) == 0
+    # sampled starts respect the reference's spawn box and separation
+    st = env.get_state()
+    assert (st['goal'] >= 0.11 - 1e-12).all() and (st['goal'] <= layout.shape[0] * 0.24).all()
+    env.close()
+
+
+def test_planning_per_mover_radii_and_quirk():
+    """Per-mover circle radii: pairwise semantics by default, the reference's broadcast quirk (basic_envs.py:409) on demand."""
+    for quirk in (False, True):
+        rng = np.random.default_rng(15)
+        cp = {'shape': 'circle', 'size': np.array([0.06, 0.11, 0.08])}
+        env, ora = make_pair(1024, layout_tiles=np.ones((4, 4)), num_movers=3, std_noise=0.0, collision_params=cp,
+                             autoreset_mode='off', reference_quirks=quirk)
+        st = rng.uniform(0.12, 0.84, (1024, 3, 2))
+        st[:, 1] = st[:, 0] + rng.uniform(-0.2, 0.2, (1024, 2))
+        gl = rng.uniform(0.12, 0.84, (1024, 3, 2))
+        env.reset(seed=4, options={'mover_start_xy_pos': st, 'mover_goal_xy_pos': gl})
+        ora.reset(seed=4, inject_start=st, inject_goal=gl)
+        torch.cuda.synchronize()
+        assert np.array_equal(env.core.buf['mover_collision'].cpu().numpy(), ora.mover_collision)
+        assert 0.05 < ora.mover_collision.mean() < 0.95
+        env.close()
+
+
+def test_threshold_edges_are_bit_exact():
+    """Movers placed exactly on the decision thresholds: centre distance == r_i + r_j (collision, '<='), one ulp beyond
+    (no collision); wall distance == c (collision, strict '<') and one ulp inside."""
+    B = 8
+    env, ora = make_pair(B, layout_tiles=np.ones((3, 3)), num_movers=2, std_noise=0.0, autoreset_mode='off')
+    st = np.zeros((B, 2, 2))
+    st[:, 0] = [0.3, 0.3]
+    st[:, 1] = [0.3 + 0.22, 0.3]
+    st[1, 1, 0] = np.nextafter(0.3 + 0.22, 1.0)
+    st[2, 0] = [0.11, 0.3]                       # x - c == 0 -> not strictly inside
+    st[2, 1] = [0.5, 0.5]
+    st[3, 0] = [np.nextafter(0.11, 1.0), 0.3]
+    st[3, 1] = [0.5, 0.5]
+    st[4, 0] = [0.61, 0.3]                       # x + c == 0.72 (computed as centre + half)
+    st[4, 1] = [0.3, 0.6]
+    st[5, 0] = [np.nextafter(0.61, 0.0), 0.3]
+    st[5, 1] = [0.3, 0.6]
+    st[6, 0] = [0.24, 0.24]                      # on the corner shared by four tiles
+    st[6, 1] = [0.48, 0.48]
+    st[7, 0] = [0.36, 0.36]
+    st[7, 1] = [0.36, 0.36 + 0.22]
+    gl = np.tile(np.array([[0.2, 0.2], [0.5, 0.5]]), (B, 1, 1))
+    env.reset(seed=0, options={'mover_start_xy_pos': st, 'mover_goal_xy_pos': gl})
+    ora.reset(seed=0, inject_start=st, inject_goal=gl)
+    torch.cuda.synchronize()
+    mc, wc = env.core.buf['mover_collision'].cpu().numpy(), env.core.buf['wall_collision'].cpu().numpy()
+    assert np.array_equal(mc, ora.mover_collision) and np.array_equal(wc, ora.wall_collision)
+    assert mc.tolist() == [1, 0, 0, 0, 0, 0, 0, 1]
+    assert wc.tolist() == [0, 0, 1, 0, 1, 0, 0, 0]
+    env.close()
+
+
+def test_compute_reward_kernel_matches_oracle():
+    """HER relabelling entry point (planning:459-534): batched rewards / terminated on device."""
+    rng = np.random.default_rng(16)
+    env, ora = make_pair(4, layout_tiles=np.ones((3, 3)), num_movers=4, std_noise=0.0)
+    b = 20000
+    dg = rng.uniform(0.11, 0.55, (b, 8)).astype(np.float32)
+    ag = (dg + rng.normal(0, 0.07, (b, 8))).astype(np.float32)
+    ag[:500] = dg[:500]
+    mc, wc = rng.random(b) < 0.1, rng.random(b) < 0.1
+    r, t = env.core.compute_reward(ag, dg, mc, wc)
+    r2, t2 = oracle.compute_reward(ora.cfg, ag, dg, mc, wc)
+    assert np.array_equal(r.cpu().numpy(), r2) and np.array_equal(t.cpu().numpy(), t2)
+    assert len(np.unique(r2)) >= 5
+    env.close()
+
+
+def test_step_host_matches_device_step():
+    """gpr_step_host (NumPy in / NumPy out) is the same computation as gpr_step on device tensors."""
+    rng = np.random.default_rng(17)
+    kw = dict(layout_tiles=np.ones((3, 3)), num_movers=4, std_noise=1e-5, seed=5)
+    e1 = gpr.BenchmarkPlanningVecEnv(2048, device=DEV, **kw)
+    e2 = gpr.BenchmarkPlanningVecEnv(2048, device=DEV, **kw)
+    e1.reset(seed=5)
+    e2.reset(seed=5)
+    for _ in range(8):
+        a = rng.uniform(-10, 10, (2048, 8)).astype(np.float32)
+        o1, r1, t1, tr1, i1 = e1.step(torch.as_tensor(a, device=DEV))
+        o2, r2, t2, tr2, i2 = e2.step_host(a)
+        torch.cuda.synchronize()
+        assert np.array_equal(o1['observation'].cpu().numpy(), o2['observation'])
+        assert np.array_equal(o1['achieved_goal'].cpu().numpy(), o2['achieved_goal'])
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(t1.cpu().numpy(), t2)
+        assert np.array_equal(i1['wall_collision'].cpu().numpy(), i2['wall_collision'])
+    e1.close()
+    e2.close()
+
+
+def test_sharding_does_not_change_results():
+    """Multi-GPU rule: the RNG is keyed by the GLOBAL env index, so one handle with 4096 envs and two
+    handles with 2048 each (env_index_base 0 / 2048) produce identical trajectories."""
+    rng = np.random.default_rng(18)
+    kw = dict(layout_tiles=np.ones((3, 3)), num_movers=4, std_noise=1e-5, seed=21)
+    whole = gpr.BenchmarkPlanningVecEnv(4096, device=DEV, **kw)
+    parts = [gpr.BenchmarkPlanningVecEnv(0, device=DEV, total_envs=4096, rank=r, world_size=2, **kw) for r in range(2)]
+    whole.reset(seed=21)
+    for p in parts:
+        p.reset(seed=21)
+    for _ in range(15):
+        a = torch.as_tensor(rng.uniform(-10, 10, (4096, 8)).astype(np.float32), device=DEV)
+        o, r, t, tr, _ = whole.step(a)
+        outs = [p.step(a[i * 2048:(i + 1) * 2048].contiguous()) for i, p in enumerate(parts)]
+        assert torch.equal(o['observation'], torch.cat([x[0]['observation'] for x in outs]))
+        assert torch.equal(o['desired_goal'], torch.cat([x[0]['desired_goal'] for x in outs]))
+        assert torch.equal(r, torch.cat([x[1] for x in outs])) and torch.equal(t, torch.cat([x[2] for x in outs]))
+    whole.close()
+    for p in parts:
+        p.close()
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] at full size (65,536 envs, 4 movers, 3x3): size-independent properties over 60 steps with
+    auto-reset — kinematic limits, flag/reward consistency, spawn validity, determinism, episode accounting."""
+    B = 65536
+    kw = dict(layout_tiles=np.ones((3, 3)), num_movers=4, std_noise=1e-5, seed=1234)
+    env = gpr.BenchmarkPlanningVecEnv(B, device=DEV, **kw)
+    env2 = gpr.BenchmarkPlanningVecEnv(B, device=DEV, **kw)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    env.reset(seed=1234)
+    env2.reset(seed=1234)
+    finished = 0
+    for t in range(60):
+        a = (torch.rand((B, 8), device=DEV, generator=g) * 2 - 1) * 10
+        obs, r, term, trunc, info = env.step(a)
+        o2, r2, term2, _, _ = env2.step(a)
+        assert torch.equal(r, r2) and torch.equal(term, term2) and torch.equal(obs['achieved_goal'], o2['achieved_goal'])
+        coll = info['mover_collision'] | info['wall_collision']
+        assert torch.equal(term, coll | info['is_success'])                     # planning:477-478
+        assert torch.equal(r == -50, coll) and torch.equal(r == 50, info['is_success'])
+        assert ((r[~term] <= -1) & (r[~term] >= -4)).all()                     # -(N - reached), at least one missing
+        st = env.get_state()
+        assert (st['vel'].norm(dim=-1) <= 2.0 * (1 + 1e-12)).all()              # plan:437 ||v|| <= v_max
+        assert (st['acc'].abs() <= 10.0).all()                                  # clipped action
+        # envs that were just re-sampled: starts inside the spawn box, pairwise separation > 2r, zero velocity
+        done = term | trunc
+        finished += int(done.sum())
+        if done.any():
+            p = st['pos'][done]
+            assert (p >= 0.11).all() and (p <= 0.55).all()                      # planning:262-267 quirk: max is 0.55
+            d = torch.cdist(p, p) + torch.eye(4, device=DEV, dtype=torch.float64) * 10
+            assert (d > 0.22).all()
+            assert (st['vel'][done] == 0).all() and (st['elapsed_steps'][done] == 0).all()
+            gl = st['goal'][done]
+            dg = torch.cdist(gl, gl) + torch.eye(4, device=DEV, dtype=torch.float64) * 10
+            assert (dg >= 0.22).all()                                           # planning:410
+    stats = env.episode_stats(reset=True)
+    assert stats['episodes'] == finished and finished > B // 2
+    assert 1.0 <= stats['mean_length'] <= 50.0
+    assert env.core.reset_failures() == 0
+    env.close()
+    env2.close()
+
+
+def test_single_env_and_pettingzoo_forms():
+    """The reference's single-env call signatures (NumPy float64) and the PettingZoo-parallel re-keying."""
+    env = gpr.BenchmarkPlanningEnv(layout_tiles=np.ones((3, 3)), num_movers=2, show_2D_plot=False, render_mode=None, std_noise=0.0)
+    obs, info = env.reset(seed=0)
+    assert set(obs) == {'observation', 'achieved_goal', 'desired_goal'} and obs['observation'].shape == (4,)
+    assert obs['achieved_goal'].dtype == np.float64 and set(info) == {'is_success', 'mover_collision', 'wall_collision'}
+    o, r, term, trunc, info = env.step(np.array([1.0, 0.0, 0.0, -1.0]))
+    assert isinstance(r, float) and isinstance(term, bool) and trunc is False
+    # closed form after one env-step of 40 cycles from rest: v = 40*dt*a, p = p0 + dt^2*a*(1+...+40)
+    assert np.allclose(o['observation'], [0.04, 0, 0, -0.04], atol=1e-9)
+    assert np.allclose(o['achieved_goal'][0] - obs['achieved_goal'][0], 1e-6 * 820, atol=1e-9)
+    assert env.compute_reward(o['achieved_goal'], o['desired_goal'], info) == r
+    env.close()
+
+    pz = gpr.BenchmarkPlanningParallelEnv(64, np.ones((3, 3)), 3, device=DEV, std_noise=0.0, learn_jerk=True)
+    obs, infos = pz.reset(seed=1)
+    assert pz.agents == ['mover_0', 'mover_1', 'mover_2'] and obs['mover_1']['observation'].shape == (64, 4)
+    acts = {a: torch.full((64, 2), 50.0 * (i + 1), device=DEV) for i, a in enumerate(pz.agents)}
+    obs, rew, term, trunc, infos = pz.step(acts)
+    full = pz._vec.core.buf['observation']
+    assert torch.equal(obs['mover_2']['observation'][:, :2], full[:, 4:6]) and torch.equal(obs['mover_2']['observation'][:, 2:], full[:, 10:12])
+    alive = ~term['mover_0']
+    assert torch.allclose(obs['mover_1']['observation'][alive, 2:], torch.full((int(alive.sum()), 2), 4.0, device=DEV), atol=1e-5)
+    pz.close()
