@@ -291,7 +291,6 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     a.max_episode_steps = c.max_episode_steps;
     a.autoreset = c.autoreset_mode;
     a.max_reset_attempts = c.max_reset_attempts;
-    a.quirks = c.reference_quirks != 0 && c.c_shape == GPR_SHAPE_CIRCLE;
     a.env_base = (uint32_t)c.env_index_base;
     a.seed = h->seed;
     a.dt = c.cycle_time;
@@ -306,7 +305,29 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     for (int k = 0; k < 2; ++k) {
         a.min_xy[k] = c.min_xy_pos[k];
         a.span_xy[k] = c.max_xy_pos[k] - c.min_xy_pos[k];  // numpy uniform: low + (high-low)*u
-        a.quirk_rsum[k] = h->quirk_rsum[k];
+    }
+    // lazy-noise bounds: |normal| <= GPR_NORMAL_ABS_MAX, both components of a (x,y) noise vector share one Box-Muller
+    // radius, so the vector norm is bounded by the same number.  6 > 5.77 and 12 > 2*5.77 leave slack for rounding.
+    const double vb = 6.0 * c.std_noise[1] + 1e-12;
+    a.v_lazy2 = (c.v_max - vb) > 0.0 ? (c.v_max - vb) * (c.v_max - vb) * (1.0 - 1e-14) : -1.0;
+    a.pair_margin = h->noise ? 12.0 * c.std_noise[0] + 1e-12 : 0.0;
+    a.wall_delta = (float)(6.0 * c.std_noise[0]) * 1.01f + 2e-6f;
+    a.wxf = (float)(2.0 * c.tile_half[0]);
+    a.wyf = (float)(2.0 * c.tile_half[1]);
+    // circle: one threshold for every pair when all radii are equal, or under the basic:409 broadcast quirk
+    bool equal = true;
+    for (int s = 0; s < 2; ++s)
+        for (int m = 1; m < c.num_movers; ++m) equal = equal && c.c_mover[s][m][0] == c.c_mover[s][0][0];
+    const bool quirk = c.reference_quirks != 0 && c.c_shape == GPR_SHAPE_CIRCLE;
+    a.uniform_pairs = c.c_shape == GPR_SHAPE_CIRCLE && (equal || quirk);
+    for (int s = 0; s < 2; ++s) {
+        const double t = (quirk && !equal) ? h->quirk_rsum[s] : c.c_mover[s][0][0] + c.c_mover[s][0][0];
+        a.pair_t[s] = t;
+        for (int nz = 0; nz < 2; ++nz) {
+            const double mg = nz ? a.pair_margin : 0.0;
+            a.band_lo2[s][nz] = (t - mg) > 0.0 ? (t - mg) * (t - mg) * (1.0 - 1e-14) : -1.0;
+            a.band_hi2[s][nz] = (t + mg) * (t + mg) * (1.0 + 1e-14);
+        }
     }
     a.sigma_p = c.std_noise[0];
     a.sigma_v = c.std_noise[1];

@@ -6,6 +6,17 @@
 //                          plan:459-479 terminated, TimeLimit truncation, episode statistics and auto-reset
 //                          (plan:355-418 rejection sampling with the counter-based RNG of include/gpr_rng.h).
 //   planning_reset_kernel: basic:1770-1833 for a masked subset, optionally with injected starts / goals.
+//
+// Two exact optimisations shape the code (DESIGN.md "Kernels"):
+//   * LAZY NOISE.  The sensor noise of the reference (sigma = 1e-5 by default) is drawn three times per mover and cycle
+//     (plan:430, basic:1888-1901) but only ever feeds comparisons.  The portable normal generator is bounded
+//     (|n| <= GPR_NORMAL_ABS_MAX), the RNG is counter-based (skipping a draw changes no other draw), so a comparison whose
+//     noise-free margin exceeds the noise bound has the same outcome with and without the noise.  The kernel evaluates
+//     each check noise-free first and generates the noise only inside the band where it can matter — bit-identical to
+//     always drawing it (which is what the oracle does).
+//   * WARP-COOPERATIVE REJECTION SAMPLING.  Acceptance of "all movers at once" sampling is ~1% for 4 movers on 3x3 tiles.
+//     All 32/G lane groups of the warp test DIFFERENT attempts of ONE environment in parallel (two attempts per Philox
+//     block) and the lowest accepted attempt index wins, which is exactly the sequential loop's result.
 #pragma once
 
 #include "gpr_device.cuh"
@@ -14,15 +25,22 @@ namespace gpr {
 
 struct PlanArgs {
     int B, N;
-    int learn_jerk, num_cycles, max_episode_steps, autoreset, max_reset_attempts, quirks;
+    int learn_jerk, num_cycles, max_episode_steps, autoreset, max_reset_attempts;
+    int uniform_pairs;  // circle: one threshold for every pair (equal radii, or the basic:409 broadcast quirk)
     uint32_t env_base;
     uint64_t seed;
     double dt, v_max, a_max, j_max, act_lim;
     double v_max2_lo, a_max2_lo;  // max^2 * (1 - 1e-14), see ensure_max
+    double v_lazy2;               // (v_max - vel-noise bound)^2: below it the velocity clip cannot trigger (or -1)
     double threshold, min_goal_dist;
     double min_xy[2], span_xy[2];
     double sigma_p, sigma_v;
-    double quirk_rsum[2];  // [safety] max over pairs of r_i + r_j (basic:409 broadcast quirk)
+    double pair_margin;     // bound on |noisy distance - distance| (0 without noise)
+    double pair_t[2];       // [safety] common pair threshold when uniform_pairs
+    double band_lo2[2][2];  // [safety][noisy] d^2 below  -> certain hit   (uniform_pairs)
+    double band_hi2[2][2];  // [safety][noisy] d^2 above  -> certain miss
+    float wall_delta;       // bound on the position noise per coordinate (+ float slack)
+    float wxf, wyf;         // tile widths as float (closeness test only)
     LayoutArgs L;
     const double* c_wall;   // [2][GPR_MAX_MOVERS][2] device
     const double* c_mover;  // [2][GPR_MAX_MOVERS][2] device
@@ -35,7 +53,7 @@ struct PlanArgs {
     uint32_t* rng;
     uint8_t* needs_reset;
     float* ep_return;
-    double* stats;        // 6 accumulators, see gpr_episode_stats
+    double* stats;         // 6 accumulators, see gpr_episode_stats
     uint32_t* fail_count;  // number of resets whose rejection loop hit max_reset_attempts
     // per-call I/O
     const float2* action;
@@ -58,6 +76,88 @@ struct Lane {
     uint32_t env_global;
 };
 
+template <int G>
+__device__ __forceinline__ Lane<G> make_lane(const PlanArgs& a) {
+    Lane<G> ln;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    ln.lane = threadIdx.x & 31u;
+    ln.gmask = group_mask<G>(ln.lane);
+    ln.env = (int)(gtid / G);
+    ln.m = (int)(gtid % G);
+    ln.env_ok = ln.env < a.B;
+    ln.active = ln.env_ok && ln.m < a.N;
+    ln.idx = (size_t)ln.env * (size_t)a.N + (size_t)ln.m;
+    ln.env_global = a.env_base + (uint32_t)ln.env;
+    return ln;
+}
+
+__device__ __forceinline__ double noisy(double x, float n, double sigma) { return dadd(x, dmul((double)n, sigma)); }
+
+// ---- circle pair check with the lazy-noise band (basic:392-409), warp-collective --------------------------------------
+//   NOISY: the positions carry the mover-check noise of (event, stream) — generated only inside the uncertainty band.
+template <int G, bool NOISY>
+__device__ __forceinline__ bool pair_circle(const PlanArgs& a, unsigned lane, int m, bool part, double x, double y,
+                                            double r, int safety, uint32_t env_global, uint32_t event, uint32_t stream) {
+    bool hit = false;
+    if (G == 1) return false;
+    const unsigned base = lane & ~(unsigned)(G - 1);
+#pragma unroll
+    for (int k = 1; k <= G / 2; ++k) {
+        const int pm = (m + k) & (G - 1);
+        const int src = (int)(base | (unsigned)pm);
+        const double ox = __shfl_sync(FULL, x, src);
+        const double oy = __shfl_sync(FULL, y, src);
+        const bool opart = __shfl_sync(FULL, (int)part, src) != 0;
+        const bool mine = part && opart && !(k == G / 2 && m >= G / 2);
+        const double dx = dsub(x, ox), dy = dsub(y, oy);
+        const double d2 = dadd(dmul(dx, dx), dmul(dy, dy));
+        double t, lo2, hi2;
+        if (a.uniform_pairs) {
+            t = a.pair_t[safety];
+            lo2 = a.band_lo2[safety][NOISY ? 1 : 0];
+            hi2 = a.band_hi2[safety][NOISY ? 1 : 0];
+        } else {
+            const double orr = __shfl_sync(FULL, r, src);
+            t = dadd(r, orr);  // basic:409
+            const double mg = NOISY ? a.pair_margin : 0.0;
+            const double tl = t - mg, th = t + mg;
+            lo2 = tl > 0.0 ? tl * tl * (1.0 - 1e-14) : -1.0;
+            hi2 = th * th * (1.0 + 1e-14);
+        }
+        if (mine) {
+            if (d2 <= lo2) {
+                hit = true;
+            } else if (!(d2 >= hi2)) {  // uncertain band (or NaN): decide exactly like the reference
+                double xi = x, yi = y, xj = ox, yj = oy;
+                if (NOISY) {
+                    float k4[4];
+                    gpr_normal4(a.seed, env_global, event, stream, (uint32_t)m, k4);
+                    xi = noisy(x, k4[0], a.sigma_p);
+                    yi = noisy(y, k4[1], a.sigma_p);
+                    gpr_normal4(a.seed, env_global, event, stream, (uint32_t)pm, k4);
+                    xj = noisy(ox, k4[0], a.sigma_p);
+                    yj = noisy(oy, k4[1], a.sigma_p);
+                }
+                const double ex = dsub(xi, xj), ey = dsub(yi, yj);
+                if (dsqrt(dadd(dmul(ex, ex), dmul(ey, ey))) <= t) hit = true;
+            }
+        }
+    }
+    return hit;
+}
+
+// Is (x, y) within `delta` of any value where a circle wall-check comparison of its cell flips?  float32, conservative.
+__device__ __forceinline__ bool wall_close(const PlanArgs& a, const Tables& tb, double x, double y, float c) {
+    int gi = __double2int_rd(dmul(x, a.L.inv_wx));
+    int gj = __double2int_rd(dmul(y, a.L.inv_wy));
+    gi = min(max(gi, 0), a.L.nx - 1);
+    gj = min(max(gj, 0), a.L.ny - 1);
+    const float fx = (float)dsub(x, tb.xlo[gi]), fy = (float)dsub(y, tb.ylo[gj]);
+    const float mx = fminf(fminf(fabsf(fx), fabsf(fx - c)), fminf(fabsf(fx - (a.wxf - c)), fabsf(fx - a.wxf)));
+    const float my = fminf(fminf(fabsf(fy), fabsf(fy - c)), fminf(fabsf(fy - (a.wyf - c)), fabsf(fy - a.wyf)));
+    return !(fminf(mx, my) >= a.wall_delta);
+}
+
 // One observation row (plan:536-573) + the per-env reductions the reward needs.
 template <int G, bool NOISE>
 __device__ __forceinline__ void observe(const PlanArgs& a, const Lane<G>& ln, uint32_t event, double2 p, double2 v,
@@ -67,10 +167,10 @@ __device__ __forceinline__ void observe(const PlanArgs& a, const Lane<G>& ln, ui
     if (NOISE) {
         float n4[4];
         gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_OBS, (uint32_t)ln.m, n4);
-        ag.x = dadd(p.x, dmul((double)n4[0], a.sigma_p));
-        ag.y = dadd(p.y, dmul((double)n4[1], a.sigma_p));
-        ov.x = dadd(v.x, dmul((double)n4[2], a.sigma_v));
-        ov.y = dadd(v.y, dmul((double)n4[3], a.sigma_v));
+        ag.x = noisy(p.x, n4[0], a.sigma_p);
+        ag.y = noisy(p.y, n4[1], a.sigma_p);
+        ov.x = noisy(v.x, n4[2], a.sigma_v);
+        ov.y = noisy(v.y, n4[3], a.sigma_v);
     }
     const double dx = dsub(ag.x, goal.x), dy = dsub(ag.y, goal.y);
     const bool reached = ln.active && sqrt_le(dadd(dmul(dx, dx), dmul(dy, dy)), a.threshold);  // plan:521
@@ -91,6 +191,102 @@ __device__ __forceinline__ void store_obs(const PlanArgs& a, const Lane<G>& ln, 
     if (DG) reinterpret_cast<float2*>(DG)[ln.idx] = make_float2((float)goal.x, (float)goal.y);
 }
 
+// ---- warp-cooperative rejection sampling (plan:369-385 starts / plan:395-413 goals) ----------------------------------
+// For every lane group with `need`, find the FIRST attempt t (t = 0, 1, 2, ...) whose N positions pass the test, exactly as
+// the reference's sequential while-loop would, but with all 32/G groups of the warp testing different attempts of the
+// same environment concurrently.  KIND 0: wall check with safety offset + mover collision with safety offset;
+// KIND 1: wall check with safety offset + pairwise distance >= min_goal_dist.
+template <int G, bool BOX, int KIND>
+__device__ __forceinline__ void sample_positions(const PlanArgs& a, const Tables& tb, const Lane<G>& ln, bool need,
+                                                 uint32_t event, double2& out, bool& failed) {
+    constexpr int S = 32 / G;  // attempts tested per half-iteration
+    const int slot = (int)(ln.lane / G);
+    const int m = ln.m;  // == lane % G
+    const bool has_mover = m < a.N;
+    const int mm = has_mover ? m : 0;
+    const double cw0 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 0], cw1 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 1];
+    const double cs0 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0], cs1 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
+    const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
+    unsigned todo = __ballot_sync(FULL, need && m == 0);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t eg = __shfl_sync(FULL, ln.env_global, leader);
+        const uint32_t ev = __shfl_sync(FULL, event, leader);
+        const bool target = (ln.lane / G) == (unsigned)(leader / G);
+        bool found = false;
+        for (int t0 = 0; t0 < cap && !found; t0 += 2 * S) {
+            const uint32_t blk = (uint32_t)(t0 / 2 + slot);
+            const gpr_u32x4 r = gpr_rng_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)KIND, (uint32_t)m);
+            double xs[2], ys[2];
+            unsigned okmask[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = 2 * (int)blk + h;
+                const double x = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform32(r.v[2 * h])));      // plan:377/405
+                const double y = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform32(r.v[2 * h + 1])));
+                xs[h] = x;
+                ys[h] = y;
+                const bool part = has_mover && t < cap;
+                Rect rw, rm;
+                bool hit;
+                if (KIND == 0) {
+                    if (BOX) {
+                        rect_vertices_axis(x, y, cs0, cs1, rm);
+                        hit = pair_check<G, true>(ln.lane, m, part, x, y, cs0, cs1, rm, false, 0.0);
+                    } else {
+                        hit = pair_circle<G, false>(a, ln.lane, m, part, x, y, cs0, 1, eg, ev, 0u);  // plan:381
+                    }
+                } else {
+                    hit = false;  // plan:408-413: any pair closer than min_goal_dist (strict '<') rejects
+                    if (G > 1) {
+                        const unsigned base = ln.lane & ~(unsigned)(G - 1);
+#pragma unroll
+                        for (int k = 1; k <= G / 2; ++k) {
+                            const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
+                            const double ox = __shfl_sync(FULL, x, src), oy = __shfl_sync(FULL, y, src);
+                            const bool opart = __shfl_sync(FULL, (int)part, src) != 0;
+                            const double dx = dsub(x, ox), dy = dsub(y, oy);
+                            if (part && opart && sqrt_lt(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_goal_dist)) hit = true;
+                        }
+                    }
+                }
+                // the pair test rejects ~99% of the attempts: only survivors pay for the wall check (plan:379 / 406)
+                const bool alive_grp = (__ballot_sync(FULL, hit) & ln.gmask) == 0u;
+                bool bad = false;
+                if (alive_grp && part) {
+                    if (BOX) rect_vertices_axis(x, y, cw0, cw1, rw);
+                    bad = !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);
+                }
+                // NB: every ballot is evaluated unconditionally (no short-circuit in front of a collective)
+                const unsigned badmask = __ballot_sync(FULL, bad);
+                const bool ok_grp = alive_grp && (badmask & ln.gmask) == 0u && t < cap;
+                okmask[h] = __ballot_sync(FULL, ok_grp && m == 0);
+            }
+            if (okmask[0] | okmask[1]) {
+                // sequential order is t = t0, t0+1, ...: slot-major, half-minor
+                const int s0 = okmask[0] ? (__ffs(okmask[0]) - 1) / G : 1 << 20;
+                const int s1 = okmask[1] ? (__ffs(okmask[1]) - 1) / G : 1 << 20;
+                const int hw = (2 * s0 <= 2 * s1 + 1) ? 0 : 1;
+                const int sw = hw == 0 ? s0 : s1;
+                const double wx = __shfl_sync(FULL, hw == 0 ? xs[0] : xs[1], sw * G + m);
+                const double wy = __shfl_sync(FULL, hw == 0 ? ys[0] : ys[1], sw * G + m);
+                if (target) out = make_double2(wx, wy);
+                found = true;
+            }
+        }
+        if (!found) {
+            // the reference would loop forever (plan:369); keep the last attempt's sample and report the failure
+            double ux, uy;
+            gpr_sample_xy(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE, (uint32_t)KIND, (uint32_t)(cap - 1), (uint32_t)m, &ux, &uy);
+            if (target) {
+                out = make_double2(dadd(a.min_xy[0], dmul(a.span_xy[0], ux)), dadd(a.min_xy[1], dmul(a.span_xy[1], uy)));
+                failed = true;
+            }
+        }
+    }
+}
+
 // plan:355-418 + basic:1797-1805 for the envs with `need` set; warp-collective (every lane of the warp calls it).
 template <int G, bool BOX, bool NOISE>
 __device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb, const Lane<G>& ln, bool need,
@@ -98,67 +294,14 @@ __device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb,
                                             double2& p, double2& v, double2& acc, double2& goal, bool& mc, bool& wc,
                                             bool& failed) {
     const int mm = ln.active ? ln.m : 0;
-    const double cw0 = a.c_wall[(1 * GPR_MAX_MOVERS + mm) * 2 + 0], cw1 = a.c_wall[(1 * GPR_MAX_MOVERS + mm) * 2 + 1];
-    const double cms0 = a.c_mover[(1 * GPR_MAX_MOVERS + mm) * 2 + 0], cms1 = a.c_mover[(1 * GPR_MAX_MOVERS + mm) * 2 + 1];
-    const double cm0 = a.c_mover[(0 * GPR_MAX_MOVERS + mm) * 2 + 0], cm1 = a.c_mover[(0 * GPR_MAX_MOVERS + mm) * 2 + 1];
-    const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
-    Rect rw, rm;
+    const double cw0 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 0], cw1 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 1];
+    const double cm0 = a.c_mover[mm * 2 + 0], cm1 = a.c_mover[mm * 2 + 1];
     failed = false;
-
-    // ---- loop A: all starts at once (plan:369-385)
-    bool pend = need && (inj_start == nullptr);
     if (need && inj_start != nullptr && ln.active) p = inj_start[ln.idx];
-    for (int t = 0; t < cap; ++t) {
-        if (!__any_sync(FULL, pend)) break;
-        const gpr_u32x4 r = gpr_rng_block(a.seed, ln.env_global, event, GPR_RNG_RESET_SAMPLE + 2u * (uint32_t)t, (uint32_t)ln.m);
-        const double x = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform53(r.v[0], r.v[1])));  // plan:377
-        const double y = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform53(r.v[2], r.v[3])));
-        const bool part = pend && ln.active;
-        if (BOX) {
-            rect_vertices_axis(x, y, cw0, cw1, rw);
-            rect_vertices_axis(x, y, cms0, cms1, rm);
-        }
-        const bool bad = part && !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);                               // plan:379
-        const bool hit = pair_check<G, BOX>(ln.lane, ln.m, part, x, y, cms0, cms1, rm, a.quirks != 0, a.quirk_rsum[1]);  // plan:381
-        const bool rej = (__ballot_sync(FULL, bad || hit) & ln.gmask) != 0u;
-        if (pend) {
-            p = make_double2(x, y);
-            if (!rej) pend = false;
-        }
-    }
-    failed |= pend;
-
-    // ---- loop B: all goals at once (plan:395-413)
-    pend = need && (inj_goal == nullptr);
     if (need && inj_goal != nullptr && ln.active) goal = inj_goal[ln.idx];
-    for (int t = 0; t < cap; ++t) {
-        if (!__any_sync(FULL, pend)) break;
-        const gpr_u32x4 r =
-            gpr_rng_block(a.seed, ln.env_global, event, GPR_RNG_RESET_SAMPLE + 2u * (uint32_t)t + 1u, (uint32_t)ln.m);
-        const double x = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform53(r.v[0], r.v[1])));  // plan:405
-        const double y = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform53(r.v[2], r.v[3])));
-        const bool part = pend && ln.active;
-        if (BOX) rect_vertices_axis(x, y, cw0, cw1, rw);
-        bool bad = part && !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);  // plan:406
-        // plan:408-413: any pair closer than min_goal_dist (strict '<') rejects
-        if (G > 1) {
-            const unsigned base = ln.lane & ~(unsigned)(G - 1);
-#pragma unroll
-            for (int k = 1; k <= G / 2; ++k) {
-                const int src = (int)(base | (unsigned)((ln.m + k) & (G - 1)));
-                const double ox = __shfl_sync(FULL, x, src), oy = __shfl_sync(FULL, y, src);
-                const bool opart = __shfl_sync(FULL, (int)part, src) != 0;
-                const double dx = dsub(x, ox), dy = dsub(y, oy);
-                if (part && opart && sqrt_lt(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_goal_dist)) bad = true;
-            }
-        }
-        const bool rej = (__ballot_sync(FULL, bad) & ln.gmask) != 0u;
-        if (pend) {
-            goal = make_double2(x, y);
-            if (!rej) pend = false;
-        }
-    }
-    failed |= pend;
+    sample_positions<G, BOX, 0>(a, tb, ln, need && inj_start == nullptr, event, p, failed);
+    sample_positions<G, BOX, 1>(a, tb, ln, need && inj_goal == nullptr, event, goal, failed);
+    failed = (__ballot_sync(FULL, failed) & ln.gmask) != 0u;
 
     // ---- fresh MjData (plan:336-353): qvel = act = qacc = 0
     if (need) {
@@ -166,38 +309,86 @@ __device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb,
         acc = make_double2(0.0, 0.0);
     }
     // ---- basic:1799-1805: wall check WITH the safety offset, mover check WITHOUT, on independently noisy qpos
-    double wx = p.x, wy = p.y, mx = p.x, my = p.y;
     const bool part = need && ln.active;
-    if (NOISE) {
-        float n4[4];
-        gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, n4);
-        wx = dadd(p.x, dmul((double)n4[0], a.sigma_p));
-        wy = dadd(p.y, dmul((double)n4[1], a.sigma_p));
-        mx = dadd(p.x, dmul((double)n4[2], a.sigma_p));
-        my = dadd(p.y, dmul((double)n4[3], a.sigma_p));
-        if (BOX) {
-            float q[4];
-            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_WQUAT, (uint32_t)ln.m, q);
-            rect_vertices(wx, wy, dadd(1.0, dmul((double)q[0], a.sigma_p)), dmul((double)q[1], a.sigma_p),
-                          dmul((double)q[2], a.sigma_p), dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
-            if (G > 1) {
-                gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_MQUAT, (uint32_t)ln.m, q);
-                rect_vertices(mx, my, dadd(1.0, dmul((double)q[0], a.sigma_p)), dmul((double)q[1], a.sigma_p),
-                              dmul((double)q[2], a.sigma_p), dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
+    bool bad, hit;
+    if (!BOX) {
+        double wx = p.x, wy = p.y;
+        if (NOISE && part && wall_close(a, tb, p.x, p.y, (float)cw0)) {
+            float n4[4];
+            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, n4);
+            wx = noisy(p.x, n4[0], a.sigma_p);
+            wy = noisy(p.y, n4[1], a.sigma_p);
+        }
+        Rect dummy;
+        bad = part && !wall_valid<false>(tb, a.L, wx, wy, cw0, dummy);
+        // the mover-check noise of reset() lives in words 2,3 of the same block
+        hit = false;
+        if (G > 1) {
+            const unsigned base = ln.lane & ~(unsigned)(G - 1);
+#pragma unroll
+            for (int k = 1; k <= G / 2; ++k) {
+                const int pm = (ln.m + k) & (G - 1);
+                const int src = (int)(base | (unsigned)pm);
+                const double ox = __shfl_sync(FULL, p.x, src), oy = __shfl_sync(FULL, p.y, src);
+                const double orr = __shfl_sync(FULL, cm0, src);
+                const bool opart = __shfl_sync(FULL, (int)part, src) != 0;
+                const bool mine = part && opart && !(k == G / 2 && ln.m >= G / 2);
+                const double t = a.uniform_pairs ? a.pair_t[0] : dadd(cm0, orr);
+                const double mg = NOISE ? a.pair_margin : 0.0;
+                const double dx = dsub(p.x, ox), dy = dsub(p.y, oy);
+                const double d2 = dadd(dmul(dx, dx), dmul(dy, dy));
+                const double tl = t - mg, th = t + mg;
+                if (mine) {
+                    if (tl > 0.0 && d2 <= tl * tl * (1.0 - 1e-14)) {
+                        hit = true;
+                    } else if (!(d2 >= th * th * (1.0 + 1e-14))) {
+                        double xi = p.x, yi = p.y, xj = ox, yj = oy;
+                        if (NOISE) {
+                            float k4[4];
+                            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, k4);
+                            xi = noisy(p.x, k4[2], a.sigma_p);
+                            yi = noisy(p.y, k4[3], a.sigma_p);
+                            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)pm, k4);
+                            xj = noisy(ox, k4[2], a.sigma_p);
+                            yj = noisy(oy, k4[3], a.sigma_p);
+                        }
+                        const double ex = dsub(xi, xj), ey = dsub(yi, yj);
+                        if (dsqrt(dadd(dmul(ex, ex), dmul(ey, ey))) <= t) hit = true;
+                    }
+                }
             }
         }
-    } else if (BOX) {
-        rect_vertices_axis(wx, wy, cw0, cw1, rw);
-        rect_vertices_axis(mx, my, cm0, cm1, rm);
-    }
-    const bool bad = part && !wall_valid<BOX>(tb, a.L, wx, wy, cw0, rw);
-    const bool hit = pair_check<G, BOX>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, a.quirks != 0, a.quirk_rsum[0]);
-    if (need) {
-        wc = (__ballot_sync(FULL, bad) & ln.gmask) != 0u;
-        mc = (__ballot_sync(FULL, hit) & ln.gmask) != 0u;
     } else {
-        (void)__ballot_sync(FULL, bad);
-        (void)__ballot_sync(FULL, hit);
+        double wx = p.x, wy = p.y, mx = p.x, my = p.y;
+        Rect rw, rm;
+        if (NOISE) {
+            float n4[4];
+            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, n4);
+            wx = noisy(p.x, n4[0], a.sigma_p);
+            wy = noisy(p.y, n4[1], a.sigma_p);
+            mx = noisy(p.x, n4[2], a.sigma_p);
+            my = noisy(p.y, n4[3], a.sigma_p);
+            float q[4];
+            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_WQUAT, (uint32_t)ln.m, q);
+            rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                          dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
+            if (G > 1) {
+                gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_MQUAT, (uint32_t)ln.m, q);
+                rect_vertices(mx, my, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                              dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
+            }
+        } else {
+            rect_vertices_axis(wx, wy, cw0, cw1, rw);
+            rect_vertices_axis(mx, my, cm0, cm1, rm);
+        }
+        bad = part && !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
+        hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0);
+    }
+    const bool wnow = (__ballot_sync(FULL, bad) & ln.gmask) != 0u;
+    const bool mnow = (__ballot_sync(FULL, hit) & ln.gmask) != 0u;
+    if (need) {
+        wc = wnow;
+        mc = mnow;
     }
 }
 
@@ -211,21 +402,6 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
     succ = all && !coll;
 }
 
-template <int G>
-__device__ __forceinline__ Lane<G> make_lane(const PlanArgs& a) {
-    Lane<G> ln;
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    ln.lane = threadIdx.x & 31u;
-    ln.gmask = group_mask<G>(ln.lane);
-    ln.env = (int)(gtid / G);
-    ln.m = (int)(gtid % G);
-    ln.env_ok = ln.env < a.B;
-    ln.active = ln.env_ok && ln.m < a.N;
-    ln.idx = (size_t)ln.env * (size_t)a.N + (size_t)ln.m;
-    ln.env_global = a.env_base + (uint32_t)ln.env;
-    return ln;
-}
-
 template <int G, bool BOX, bool NOISE>
 __global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
     __shared__ Tables tb;
@@ -233,8 +409,9 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
     __syncthreads();
     const Lane<G> ln = make_lane<G>(a);
     const int mm = ln.active ? ln.m : 0;
-    const double cw0 = a.c_wall[mm * 2 + 0], cw1 = a.c_wall[mm * 2 + 1];    // safety = 0 (basic:1888-1901)
+    const double cw0 = a.c_wall[mm * 2 + 0], cw1 = a.c_wall[mm * 2 + 1];  // safety = 0 (basic:1888-1901)
     const double cm0 = a.c_mover[mm * 2 + 0], cm1 = a.c_mover[mm * 2 + 1];
+    const float cw0f = (float)cw0;
 
     double2 p = make_double2(0, 0), v = p, acc = p, goal = p;
     double2 u = p;
@@ -260,24 +437,37 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
     // ------------------------------------------------------------------ the 40-cycle loop (basic:1879-1905)
     bool alive = ln.env_ok && !pending_reset;
     bool mc = false, wc = false;
-    Rect rw, rm;
     for (int cyc = 0; cyc < a.num_cycles; ++cyc) {
         if (!__any_sync(FULL, alive)) break;
+        const uint32_t s0 = (uint32_t)cyc * 4u;
+        const bool part = alive && ln.active;
         float n4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (NOISE) gpr_normal4(a.seed, ln.env_global, event, (uint32_t)cyc * 4u + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
-        if (alive && ln.active) {
-            // plan:420-450 _mujoco_step_callback
+        bool have0 = false;  // block 0 of this cycle generated?
+        if (NOISE && BOX) {
+            gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
+            have0 = true;
+        }
+        if (part) {
+            // plan:420-450 _mujoco_step_callback; d = derivative entering the velocity clip (action or limited acc)
+            double dxv = u.x, dyv = u.y, jx = 0.0, jy = 0.0;
+            if (a.learn_jerk) ensure_max(acc.x, acc.y, a.a_max, a.a_max2_lo, u.x, u.y, a.dt, dxv, dyv, jx, jy);  // plan:434
             double velx = v.x, vely = v.y;
             if (NOISE) {
-                velx = dadd(v.x, dmul((double)n4[0], a.sigma_v));  // plan:430
-                vely = dadd(v.y, dmul((double)n4[1], a.sigma_v));
+                // the velocity noise (plan:430) can only matter if the un-noised |dt*d + v| is within its bound of v_max
+                const double tx = dadd(dmul(a.dt, dxv), v.x), ty = dadd(dmul(a.dt, dyv), v.y);
+                if (!(dadd(dmul(tx, tx), dmul(ty, ty)) < a.v_lazy2)) {
+                    if (!have0) {
+                        gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
+                        have0 = true;
+                    }
+                    velx = noisy(v.x, n4[0], a.sigma_v);
+                    vely = noisy(v.y, n4[1], a.sigma_v);
+                }
             }
             double t0, t1, ax, ay;
+            ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);  // plan:437 / 442
             if (a.learn_jerk) {
-                double atx, aty, jx, jy;
-                ensure_max(acc.x, acc.y, a.a_max, a.a_max2_lo, u.x, u.y, a.dt, atx, aty, jx, jy);  // plan:434
-                ensure_max(velx, vely, a.v_max, a.v_max2_lo, atx, aty, a.dt, t0, t1, ax, ay);      // plan:437
-                if (atx != ax || aty != ay) {                                                      // plan:438
+                if (dxv != ax || dyv != ay) {  // plan:438
                     jx = ddiv(dsub(ax, acc.x), a.dt);
                     jy = ddiv(dsub(ay, acc.y), a.dt);
                 }
@@ -285,7 +475,6 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
                 acc.x = dadd(acc.x, dmul(a.dt, jx));
                 acc.y = dadd(acc.y, dmul(a.dt, jy));
             } else {
-                ensure_max(velx, vely, a.v_max, a.v_max2_lo, u.x, u.y, a.dt, t0, t1, ax, ay);  // plan:442
                 acc.x = ax;  // dyntype none, gain = mass (plan:314-320): qacc = ctrl
                 acc.y = ay;
             }
@@ -295,36 +484,45 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
             p.x = dadd(p.x, dmul(a.dt, v.x));
             p.y = dadd(p.y, dmul(a.dt, v.y));
         }
-        // basic:1888-1894 wall check (noisy qpos, no safety offset)
-        double wx = p.x, wy = p.y, mx = p.x, my = p.y;
-        if (NOISE) {
-            wx = dadd(p.x, dmul((double)n4[2], a.sigma_p));
-            wy = dadd(p.y, dmul((double)n4[3], a.sigma_p));
-            if (G > 1) {
-                float k4[4];
-                gpr_normal4(a.seed, ln.env_global, event, (uint32_t)cyc * 4u + GPR_RNG_BLOCK_MOVER, (uint32_t)ln.m, k4);
-                mx = dadd(p.x, dmul((double)k4[0], a.sigma_p));
-                my = dadd(p.y, dmul((double)k4[1], a.sigma_p));
+        bool bad, hit;
+        if (!BOX) {
+            // basic:1888-1894 wall check on noisy qpos: noise-free unless a comparison is within the noise bound
+            double wx = p.x, wy = p.y;
+            if (NOISE && part && wall_close(a, tb, p.x, p.y, cw0f)) {
+                if (!have0) gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
+                wx = noisy(p.x, n4[2], a.sigma_p);
+                wy = noisy(p.y, n4[3], a.sigma_p);
             }
-            if (BOX) {
+            Rect dummy;
+            bad = part && !wall_valid<false>(tb, a.L, wx, wy, cw0, dummy);
+            // basic:1895-1901 mover check on an independently noisy qpos
+            hit = pair_circle<G, NOISE>(a, ln.lane, ln.m, part, p.x, p.y, cm0, 0, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER);
+        } else {
+            double wx = p.x, wy = p.y, mx = p.x, my = p.y;
+            Rect rw, rm;
+            if (NOISE) {
+                wx = noisy(p.x, n4[2], a.sigma_p);
+                wy = noisy(p.y, n4[3], a.sigma_p);
                 float q[4];
-                gpr_normal4(a.seed, ln.env_global, event, (uint32_t)cyc * 4u + GPR_RNG_BLOCK_WALL_QUAT, (uint32_t)ln.m, q);
-                rect_vertices(wx, wy, dadd(1.0, dmul((double)q[0], a.sigma_p)), dmul((double)q[1], a.sigma_p),
-                              dmul((double)q[2], a.sigma_p), dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
+                gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT, (uint32_t)ln.m, q);
+                rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                              dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
                 if (G > 1) {
-                    gpr_normal4(a.seed, ln.env_global, event, (uint32_t)cyc * 4u + GPR_RNG_BLOCK_MOVER_QUAT, (uint32_t)ln.m, q);
-                    rect_vertices(mx, my, dadd(1.0, dmul((double)q[0], a.sigma_p)), dmul((double)q[1], a.sigma_p),
-                                  dmul((double)q[2], a.sigma_p), dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
+                    float k4[4];
+                    gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER, (uint32_t)ln.m, k4);
+                    mx = noisy(p.x, k4[0], a.sigma_p);
+                    my = noisy(p.y, k4[1], a.sigma_p);
+                    gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER_QUAT, (uint32_t)ln.m, q);
+                    rect_vertices(mx, my, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                                  dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
                 }
+            } else {
+                rect_vertices_axis(wx, wy, cw0, cw1, rw);
+                rect_vertices_axis(mx, my, cm0, cm1, rm);
             }
-        } else if (BOX) {
-            rect_vertices_axis(wx, wy, cw0, cw1, rw);
-            rect_vertices_axis(mx, my, cm0, cm1, rm);
+            bad = part && !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
+            hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0);
         }
-        const bool part = alive && ln.active;
-        const bool bad = part && !wall_valid<BOX>(tb, a.L, wx, wy, cw0, rw);
-        // basic:1895-1901 mover check (independent noisy qpos)
-        const bool hit = pair_check<G, BOX>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, a.quirks != 0, a.quirk_rsum[0]);
         const bool wnow = (__ballot_sync(FULL, bad) & ln.gmask) != 0u;
         const bool mnow = (__ballot_sync(FULL, hit) & ln.gmask) != 0u;
         if (alive) {
@@ -355,9 +553,9 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
         float ret = 0.f;
         if (lead && stepped) ret = a.ep_return[ln.env] + reward;
         const bool fin = lead && done;
-        double s_ep = fin ? 1.0 : 0.0, s_ret = fin ? (double)ret : 0.0, s_len = fin ? (double)elapsed : 0.0;
-        double s_succ = (fin && succ) ? 1.0 : 0.0, s_mc = (fin && mc) ? 1.0 : 0.0, s_wc = (fin && wc) ? 1.0 : 0.0;
         if (__any_sync(FULL, fin)) {
+            double s_ep = fin ? 1.0 : 0.0, s_ret = fin ? (double)ret : 0.0, s_len = fin ? (double)elapsed : 0.0;
+            double s_succ = (fin && succ) ? 1.0 : 0.0, s_mc = (fin && mc) ? 1.0 : 0.0, s_wc = (fin && wc) ? 1.0 : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 s_ep += __shfl_xor_sync(FULL, s_ep, o);

@@ -8,8 +8,8 @@
  *
  * This header is therefore a specification of its own, not a restatement of reference code:
  *   - generator: Philox4x32-10 (Salmon et al., SC'11), key = 64-bit seed, counter = (env, event, stream, lane);
- *   - uniform double: 53 random bits * 2^-53 in [0,1), `low + (high-low)*u` with separate multiply and add
- *     (numpy's `uniform` does the same);
+ *   - uniform coordinate: 32 random bits * 2^-32 in [0,1), `low + (high-low)*u` with separate multiply and add
+ *     (numpy's `uniform` does the same with 53 bits; 32 bits resolve 1e-10 m and let one block feed two attempts);
  *   - normal float: Box-Muller whose log / sin / cos are fixed polynomials evaluated with IEEE float32 operations only
  *     (explicit fma, correctly-rounded div and sqrt), so the CPU oracle and the GPU produce BIT-IDENTICAL noise and
  *     noisy-mode parity tests can still demand exact collision flags.
@@ -57,8 +57,12 @@
 #define GPR_RNG_RESET_CHECK_WQUAT 0x40000002u
 #define GPR_RNG_RESET_CHECK_MQUAT 0x40000003u
 #define GPR_RNG_OBJECT 0x40000004u     /* pushing: normals [obj_x, obj_y, -, -]       (pushing:565)                      */
-#define GPR_RNG_RESET_SAMPLE 0x80000000u /* + 2*attempt + {0: start, 1: goal}         (planning:377,405)                 */
-#define GPR_RNG_RESET_OBJECT 0xC0000000u /* pushing: + 2*attempt + {0: object start, 1: object goal} (pushing:401,409)   */
+/* rejection sampling: attempt t of kind k (0 start, 1 goal) reads block (t >> 1) of stream BASE + 2*(t >> 1) + k and
+   takes words (0,1) for even t, (2,3) for odd t as (x, y): one Philox block feeds two attempts of one mover */
+#define GPR_RNG_RESET_SAMPLE 0x80000000u /* planning:377,405 / pushing:388 */
+#define GPR_RNG_RESET_OBJECT 0xC0000000u /* pushing: k = 0 object start, 1 object goal (pushing:401,409) */
+/* largest |value| gpr_normal_pair can return: sqrt(-2 ln 2^-24) = 5.7677..., polynomial error < 1e-6 */
+#define GPR_NORMAL_ABS_MAX 5.77
 
 typedef struct gpr_u32x4 {
     uint32_t v[4];
@@ -111,6 +115,18 @@ GPR_HD gpr_u32x4 gpr_rng_block(uint64_t seed, uint32_t env_global, uint32_t even
 GPR_HD double gpr_uniform53(uint32_t hi, uint32_t lo) {
     uint64_t bits = (((uint64_t)hi << 32) | (uint64_t)lo) >> 11;
     return (double)bits * (1.0 / 9007199254740992.0);
+}
+
+/* 32-bit uniform in [0,1): the resolution of sampled start / goal coordinates (span * 2^-32 ~ 1e-10 m). */
+GPR_HD double gpr_uniform32(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+
+/* coordinates of rejection-sampling attempt t for (env, event, kind, lane): low + span * u, multiply and add rounded
+   separately like numpy's Generator.uniform */
+GPR_HD void gpr_sample_xy(uint64_t seed, uint32_t env_global, uint32_t event, uint32_t base, uint32_t kind, uint32_t t,
+                          uint32_t lane, double* ux, double* uy) {
+    gpr_u32x4 r = gpr_rng_block(seed, env_global, event, base + 2u * (t >> 1) + kind, lane);
+    *ux = gpr_uniform32(r.v[2u * (t & 1u)]);
+    *uy = gpr_uniform32(r.v[2u * (t & 1u) + 1u]);
 }
 
 /* Two independent standard normals from two words (Box-Muller, fixed float32 polynomials). */

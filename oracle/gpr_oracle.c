@@ -473,10 +473,11 @@ static int planning_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_g
         int ok = 0;
         for (int t = 0; t < cap && !ok; ++t) {
             for (int m = 0; m < N; ++m) {
-                gpr_u32x4 r = gpr_rng_block(seed, env_global, event, GPR_RNG_RESET_SAMPLE + 2u * (uint32_t)t, (uint32_t)m);
+                double ux, uy;
+                gpr_sample_xy(seed, env_global, event, GPR_RNG_RESET_SAMPLE, 0u, (uint32_t)t, (uint32_t)m, &ux, &uy);
                 /* plan:377 np_random.uniform(low, high): low + (high-low)*u */
-                p[2 * m] = c->min_xy_pos[0] + (c->max_xy_pos[0] - c->min_xy_pos[0]) * gpr_uniform53(r.v[0], r.v[1]);
-                p[2 * m + 1] = c->min_xy_pos[1] + (c->max_xy_pos[1] - c->min_xy_pos[1]) * gpr_uniform53(r.v[2], r.v[3]);
+                p[2 * m] = c->min_xy_pos[0] + (c->max_xy_pos[0] - c->min_xy_pos[0]) * ux;
+                p[2 * m + 1] = c->min_xy_pos[1] + (c->max_xy_pos[1] - c->min_xy_pos[1]) * uy;
             }
             noisy_qpos(c, p, N, NULL, NULL, qpos); /* no noise inside the sampling loop (plan:379-383 pass qpos) */
             for (int m = 0; m < N; ++m) { qpos[7 * m] = p[2 * m]; qpos[7 * m + 1] = p[2 * m + 1]; }
@@ -495,10 +496,10 @@ static int planning_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_g
         int ok = 0;
         for (int t = 0; t < cap && !ok; ++t) {
             for (int m = 0; m < N; ++m) {
-                gpr_u32x4 r =
-                    gpr_rng_block(seed, env_global, event, GPR_RNG_RESET_SAMPLE + 2u * (uint32_t)t + 1u, (uint32_t)m);
-                g[2 * m] = c->min_xy_pos[0] + (c->max_xy_pos[0] - c->min_xy_pos[0]) * gpr_uniform53(r.v[0], r.v[1]);
-                g[2 * m + 1] = c->min_xy_pos[1] + (c->max_xy_pos[1] - c->min_xy_pos[1]) * gpr_uniform53(r.v[2], r.v[3]);
+                double ux, uy;
+                gpr_sample_xy(seed, env_global, event, GPR_RNG_RESET_SAMPLE, 1u, (uint32_t)t, (uint32_t)m, &ux, &uy);
+                g[2 * m] = c->min_xy_pos[0] + (c->max_xy_pos[0] - c->min_xy_pos[0]) * ux;
+                g[2 * m + 1] = c->min_xy_pos[1] + (c->max_xy_pos[1] - c->min_xy_pos[1]) * uy;
             }
             for (int m = 0; m < N; ++m) {
                 double* q = qpos + 7 * m;
