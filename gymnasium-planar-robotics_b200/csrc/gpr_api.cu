@@ -311,9 +311,20 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     const double vb = 6.0 * c.std_noise[1] + 1e-12;
     a.v_lazy2 = (c.v_max - vb) > 0.0 ? (c.v_max - vb) * (c.v_max - vb) * (1.0 - 1e-14) : -1.0;
     a.pair_margin = h->noise ? 12.0 * c.std_noise[0] + 1e-12 : 0.0;
-    a.wall_delta = (float)(6.0 * c.std_noise[0]) * 1.01f + 2e-6f;
     a.wxf = (float)(2.0 * c.tile_half[0]);
     a.wyf = (float)(2.0 * c.tile_half[1]);
+    // float32 prefilter slacks: float rounding of coordinates (<= nx*w) and of the thresholds, generously bounded
+    const double extent = std::max(c.num_tiles_x * 2.0 * c.tile_half[0], c.num_tiles_y * 2.0 * c.tile_half[1]);
+    const double fslack = 4e-6 * std::max(1.0, extent) + 2e-6;
+    a.wall_delta = (float)((h->noise ? 6.0 * c.std_noise[0] * 1.01 : 0.0) + 1e-5 * std::max(2.0 * c.tile_half[0], 2.0 * c.tile_half[1]));
+    a.pair_mgf[0] = (float)fslack;
+    a.pair_mgf[1] = (float)(a.pair_margin + fslack);
+    a.goal_lo2f = (float)std::pow(std::max(c.min_goal_dist - fslack, 0.0), 2);
+    a.goal_hi2f = (float)std::pow(c.min_goal_dist + fslack, 2);
+    a.minxf = (float)c.min_xy_pos[0];
+    a.minyf = (float)c.min_xy_pos[1];
+    a.spanxf = (float)(c.max_xy_pos[0] - c.min_xy_pos[0]);
+    a.spanyf = (float)(c.max_xy_pos[1] - c.min_xy_pos[1]);
     // circle: one threshold for every pair when all radii are equal, or under the basic:409 broadcast quirk
     bool equal = true;
     for (int s = 0; s < 2; ++s)
@@ -327,6 +338,9 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
             const double mg = nz ? a.pair_margin : 0.0;
             a.band_lo2[s][nz] = (t - mg) > 0.0 ? (t - mg) * (t - mg) * (1.0 - 1e-14) : -1.0;
             a.band_hi2[s][nz] = (t + mg) * (t + mg) * (1.0 + 1e-14);
+            const double mf = a.pair_mgf[nz];
+            a.pair_lo2f[s][nz] = (t - mf) > 0.0 ? (float)((t - mf) * (t - mf)) : -1.f;
+            a.pair_hi2f[s][nz] = (float)((t + mf) * (t + mf));
         }
     }
     a.sigma_p = c.std_noise[0];

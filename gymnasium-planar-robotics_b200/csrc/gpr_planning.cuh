@@ -40,7 +40,13 @@ struct PlanArgs {
     double band_lo2[2][2];  // [safety][noisy] d^2 below  -> certain hit   (uniform_pairs)
     double band_hi2[2][2];  // [safety][noisy] d^2 above  -> certain miss
     float wall_delta;       // bound on the position noise per coordinate (+ float slack)
-    float wxf, wyf;         // tile widths as float (closeness test only)
+    float wxf, wyf;         // tile widths as float (prefilter only)
+    // float32 prefilters: decide a comparison in float32 when its margin exceeds noise bound + float rounding slack,
+    // fall back to the exact float64 evaluation otherwise
+    float pair_lo2f[2][2], pair_hi2f[2][2];  // [safety][noisy] squared-distance bands (uniform_pairs)
+    float pair_mgf[2];                       // [noisy] distance margin for per-mover radii
+    float goal_lo2f, goal_hi2f;              // min_goal_dist bands
+    float minxf, minyf, spanxf, spanyf;      // spawn box as float
     LayoutArgs L;
     const double* c_wall;   // [2][GPR_MAX_MOVERS][2] device
     const double* c_mover;  // [2][GPR_MAX_MOVERS][2] device
@@ -146,16 +152,85 @@ __device__ __forceinline__ bool pair_circle(const PlanArgs& a, unsigned lane, in
     return hit;
 }
 
-// Is (x, y) within `delta` of any value where a circle wall-check comparison of its cell flips?  float32, conservative.
-__device__ __forceinline__ bool wall_close(const PlanArgs& a, const Tables& tb, double x, double y, float c) {
-    int gi = __double2int_rd(dmul(x, a.L.inv_wx));
-    int gj = __double2int_rd(dmul(y, a.L.inv_wy));
-    gi = min(max(gi, 0), a.L.nx - 1);
-    gj = min(max(gj, 0), a.L.ny - 1);
+// Circle wall check in float32 for the tracked cell (gi, gj): returns 1 valid / 0 invalid when every comparison of
+// basic:507-558 has a margin larger than `wall_delta` (noise bound + float rounding slack) — the float32 signs are then
+// certain and equal the reference's float64 ones — and 2 when some comparison is too close to call (or the mover left
+// the tracked cell): the caller then runs the exact float64 check (with the noise, if any).
+__device__ __forceinline__ int wall_fast(const PlanArgs& a, const Tables& tb, double x, double y, float c, int gi, int gj) {
     const float fx = (float)dsub(x, tb.xlo[gi]), fy = (float)dsub(y, tb.ylo[gj]);
-    const float mx = fminf(fminf(fabsf(fx), fabsf(fx - c)), fminf(fabsf(fx - (a.wxf - c)), fabsf(fx - a.wxf)));
-    const float my = fminf(fminf(fabsf(fy), fabsf(fy - c)), fminf(fabsf(fy - (a.wyf - c)), fabsf(fy - a.wyf)));
-    return !(fminf(mx, my) >= a.wall_delta);
+    const float wc = a.wxf - c, hc = a.wyf - c;
+    const float mx = fminf(fminf(fabsf(fx), fabsf(fx - c)), fminf(fabsf(fx - wc), fabsf(fx - a.wxf)));
+    const float my = fminf(fminf(fabsf(fy), fabsf(fy - c)), fminf(fabsf(fy - hc), fabsf(fy - a.wyf)));
+    const bool inside = fx > 0.f && fx < a.wxf && fy > 0.f && fy < a.wyf;
+    if (!(fminf(mx, my) >= a.wall_delta) || !inside) return 2;
+    const uint32_t u = (fx < c ? 1u : 0u) | (fx > wc ? 2u : 0u) | (fy < c ? 4u : 0u) | (fy > hc ? 8u : 0u);
+    const uint32_t code = tb.cell[gi * a.L.ny + gj];
+    return ((code & CELL_3X3) || sides_ok(u, code)) ? 1 : 0;
+}
+
+__device__ __forceinline__ void guess_cell(const PlanArgs& a, double x, double y, int& gi, int& gj) {
+    gi = min(max(__double2int_rd(dmul(x, a.L.inv_wx)), 0), a.L.nx - 1);
+    gj = min(max(__double2int_rd(dmul(y, a.L.inv_wy)), 0), a.L.ny - 1);
+}
+
+// basic:1888-1894 for one mover (circle): float32 prefilter, exact float64 fallback with lazily generated noise.
+//   n4/have : this cycle's noise block 0 (words 2,3 = wall noise), generated on demand
+template <bool NOISE>
+__device__ __forceinline__ bool wall_bad_circle(const PlanArgs& a, const Tables& tb, bool part, double x, double y,
+                                                double c, float cf, int& gi, int& gj, uint32_t env_global, uint32_t event,
+                                                uint32_t stream, int m, int w0, float (&n4)[4], bool& have) {
+    if (!part) return false;
+    const int f = wall_fast(a, tb, x, y, cf, gi, gj);
+    if (f != 2) return f == 0;
+    double wx = x, wy = y;
+    if (NOISE) {
+        if (!have) {
+            gpr_normal4(a.seed, env_global, event, stream, (uint32_t)m, n4);
+            have = true;
+        }
+        wx = noisy(x, n4[w0], a.sigma_p);
+        wy = noisy(y, n4[w0 + 1], a.sigma_p);
+    }
+    guess_cell(a, x, y, gi, gj);  // refresh the tracked cell
+    Rect dummy;
+    return !wall_valid<false>(tb, a.L, wx, wy, c, dummy);
+}
+
+// Circle pair check with a float32 prefilter (warp-collective).  xf/yf are this lane's float coordinates (1e30f when the
+// lane does not take part); a pair is decided in float32 when its squared distance is outside the band, and only if some
+// lane of the warp meets an undecided pair does the whole warp run the exact float64 check.
+template <int G, bool NOISY>
+__device__ __forceinline__ bool pair_circle_fast(const PlanArgs& a, unsigned lane, int m, bool part, double x, double y,
+                                                 double r, int safety, uint32_t env_global, uint32_t event,
+                                                 uint32_t stream) {
+    if (G == 1) return false;
+    const float xf = part ? (float)x : 1e30f, yf = part ? (float)y : 1e30f;
+    const float rf = (float)r;
+    const unsigned base = lane & ~(unsigned)(G - 1);
+    bool hit = false, unc = false;
+#pragma unroll
+    for (int k = 1; k <= G / 2; ++k) {
+        const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
+        const float oxf = __shfl_sync(FULL, xf, src), oyf = __shfl_sync(FULL, yf, src);
+        float lo2, hi2;
+        if (a.uniform_pairs) {
+            lo2 = a.pair_lo2f[safety][NOISY ? 1 : 0];
+            hi2 = a.pair_hi2f[safety][NOISY ? 1 : 0];
+        } else {
+            const float t = rf + __shfl_sync(FULL, rf, src), mg = a.pair_mgf[NOISY ? 1 : 0];
+            lo2 = t > mg ? (t - mg) * (t - mg) : -1.f;
+            hi2 = (t + mg) * (t + mg);
+        }
+        const bool mine = part && oxf < 1e29f && !(k == G / 2 && m >= G / 2);
+        const float dx = xf - oxf, dy = yf - oyf;
+        const float d2 = dx * dx + dy * dy;
+        if (mine) {
+            if (d2 < lo2) hit = true;
+            else if (!(d2 > hi2)) unc = true;
+        }
+    }
+    if (__any_sync(FULL, unc)) hit = pair_circle<G, NOISY>(a, lane, m, part, x, y, r, safety, env_global, event, stream);
+    return hit;
 }
 
 // One observation row (plan:536-573) + the per-env reductions the reward needs.
@@ -206,7 +281,9 @@ __device__ __forceinline__ void sample_positions(const PlanArgs& a, const Tables
     const int mm = has_mover ? m : 0;
     const double cw0 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 0], cw1 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 1];
     const double cs0 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0], cs1 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
+    const float rf = (float)cs0, diagf = (float)cs0 + (float)cs1;  // box: |half diagonal| <= sx + sy
     const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
+    const unsigned base = ln.lane & ~(unsigned)(G - 1);
     unsigned todo = __ballot_sync(FULL, need && m == 0);
     while (todo) {
         const int leader = __ffs(todo) - 1;
@@ -218,50 +295,94 @@ __device__ __forceinline__ void sample_positions(const PlanArgs& a, const Tables
         for (int t0 = 0; t0 < cap && !found; t0 += 2 * S) {
             const uint32_t blk = (uint32_t)(t0 / 2 + slot);
             const gpr_u32x4 r = gpr_rng_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)KIND, (uint32_t)m);
+            // ---- phase 1, float32: ~99% of the attempts die on a pair that is far inside the rejection band
+            bool cand[2], needx[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = 2 * (int)blk + h;
+                const bool part = has_mover && t < cap;
+                const float xf = part ? fmaf(a.spanxf, (float)r.v[2 * h] * 2.3283064365386963e-10f, a.minxf) : 1e30f;
+                const float yf = part ? fmaf(a.spanyf, (float)r.v[2 * h + 1] * 2.3283064365386963e-10f, a.minyf) : 1e30f;
+                bool rej = false, unc = false;
+                if (G > 1) {
+#pragma unroll
+                    for (int k = 1; k <= G / 2; ++k) {
+                        const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
+                        const float oxf = __shfl_sync(FULL, xf, src), oyf = __shfl_sync(FULL, yf, src);
+                        float lo2, hi2;
+                        if (KIND == 1) {
+                            lo2 = a.goal_lo2f;
+                            hi2 = a.goal_hi2f;
+                        } else if (BOX) {
+                            const float td = diagf + __shfl_sync(FULL, diagf, src) + a.pair_mgf[0];
+                            lo2 = -1.f;  // boxes: the float test can only prove a miss (centres farther than the diagonals)
+                            hi2 = td * td;
+                        } else if (a.uniform_pairs) {
+                            lo2 = a.pair_lo2f[1][0];
+                            hi2 = a.pair_hi2f[1][0];
+                        } else {
+                            const float tt = rf + __shfl_sync(FULL, rf, src), mg = a.pair_mgf[0];
+                            lo2 = tt > mg ? (tt - mg) * (tt - mg) : -1.f;
+                            hi2 = (tt + mg) * (tt + mg);
+                        }
+                        const bool mine = part && oxf < 1e29f;  // (pairs seen from both ends agree; no need to dedupe)
+                        const float dx = xf - oxf, dy = yf - oyf;
+                        const float d2 = dx * dx + dy * dy;
+                        if (mine) {
+                            if (d2 < lo2) rej = true;
+                            else if (!(d2 > hi2)) unc = true;
+                        }
+                    }
+                }
+                const unsigned rejm = __ballot_sync(FULL, rej), uncm = __ballot_sync(FULL, unc);
+                cand[h] = (rejm & ln.gmask) == 0u && t < cap;
+                needx[h] = cand[h] && (uncm & ln.gmask) != 0u;
+            }
+            // ---- phase 2, float64 (exact), only when some group of the warp still has a candidate
+            if (!__any_sync(FULL, cand[0] || cand[1])) continue;
             double xs[2], ys[2];
             unsigned okmask[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int t = 2 * (int)blk + h;
-                const double x = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform32(r.v[2 * h])));      // plan:377/405
+                const double x = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform32(r.v[2 * h])));  // plan:377/405
                 const double y = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform32(r.v[2 * h + 1])));
                 xs[h] = x;
                 ys[h] = y;
-                const bool part = has_mover && t < cap;
-                Rect rw, rm;
-                bool hit;
-                if (KIND == 0) {
-                    if (BOX) {
-                        rect_vertices_axis(x, y, cs0, cs1, rm);
-                        hit = pair_check<G, true>(ln.lane, m, part, x, y, cs0, cs1, rm, false, 0.0);
+                const bool part = has_mover && t < cap && cand[h];
+                bool hit = false;
+                if (G > 1 && __any_sync(FULL, needx[h])) {
+                    const bool px = part && needx[h];
+                    if (KIND == 0) {
+                        if (BOX) {
+                            Rect rm;
+                            rect_vertices_axis(x, y, cs0, cs1, rm);
+                            hit = pair_check<G, true>(ln.lane, m, px, x, y, cs0, cs1, rm, false, 0.0);
+                        } else {
+                            hit = pair_circle<G, false>(a, ln.lane, m, px, x, y, cs0, 1, eg, ev, 0u);  // plan:381
+                        }
                     } else {
-                        hit = pair_circle<G, false>(a, ln.lane, m, part, x, y, cs0, 1, eg, ev, 0u);  // plan:381
-                    }
-                } else {
-                    hit = false;  // plan:408-413: any pair closer than min_goal_dist (strict '<') rejects
-                    if (G > 1) {
-                        const unsigned base = ln.lane & ~(unsigned)(G - 1);
+                        // plan:408-413: any pair closer than min_goal_dist (strict '<') rejects
 #pragma unroll
                         for (int k = 1; k <= G / 2; ++k) {
                             const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
                             const double ox = __shfl_sync(FULL, x, src), oy = __shfl_sync(FULL, y, src);
-                            const bool opart = __shfl_sync(FULL, (int)part, src) != 0;
+                            const bool opart = __shfl_sync(FULL, (int)px, src) != 0;
                             const double dx = dsub(x, ox), dy = dsub(y, oy);
-                            if (part && opart && sqrt_lt(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_goal_dist)) hit = true;
+                            if (px && opart && sqrt_lt(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_goal_dist)) hit = true;
                         }
                     }
                 }
-                // the pair test rejects ~99% of the attempts: only survivors pay for the wall check (plan:379 / 406)
-                const bool alive_grp = (__ballot_sync(FULL, hit) & ln.gmask) == 0u;
+                const unsigned hitm = __ballot_sync(FULL, hit);
+                const bool alive_grp = cand[h] && (hitm & ln.gmask) == 0u;
                 bool bad = false;
-                if (alive_grp && part) {
+                if (alive_grp && part) {  // plan:379 / 406 wall check with safety offset
+                    Rect rw;
                     if (BOX) rect_vertices_axis(x, y, cw0, cw1, rw);
                     bad = !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);
                 }
-                // NB: every ballot is evaluated unconditionally (no short-circuit in front of a collective)
-                const unsigned badmask = __ballot_sync(FULL, bad);
-                const bool ok_grp = alive_grp && (badmask & ln.gmask) == 0u && t < cap;
-                okmask[h] = __ballot_sync(FULL, ok_grp && m == 0);
+                const unsigned badm = __ballot_sync(FULL, bad);
+                okmask[h] = __ballot_sync(FULL, alive_grp && (badm & ln.gmask) == 0u && m == 0);
             }
             if (okmask[0] | okmask[1]) {
                 // sequential order is t = t0, t0+1, ...: slot-major, half-minor
@@ -312,15 +433,14 @@ __device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb,
     const bool part = need && ln.active;
     bool bad, hit;
     if (!BOX) {
-        double wx = p.x, wy = p.y;
-        if (NOISE && part && wall_close(a, tb, p.x, p.y, (float)cw0)) {
+        {
+            int gi, gj;
+            guess_cell(a, p.x, p.y, gi, gj);
             float n4[4];
-            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, n4);
-            wx = noisy(p.x, n4[0], a.sigma_p);
-            wy = noisy(p.y, n4[1], a.sigma_p);
+            bool have = false;
+            bad = wall_bad_circle<NOISE>(a, tb, part, p.x, p.y, cw0, (float)cw0, gi, gj, ln.env_global, event,
+                                         GPR_RNG_RESET_CHECK, ln.m, 0, n4, have);
         }
-        Rect dummy;
-        bad = part && !wall_valid<false>(tb, a.L, wx, wy, cw0, dummy);
         // the mover-check noise of reset() lives in words 2,3 of the same block
         hit = false;
         if (G > 1) {
@@ -437,6 +557,8 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
     // ------------------------------------------------------------------ the 40-cycle loop (basic:1879-1905)
     bool alive = ln.env_ok && !pending_reset;
     bool mc = false, wc = false;
+    int gi = 0, gj = 0;  // tile cell under the mover, tracked across cycles (movement per cycle is ~mm)
+    if (!BOX) guess_cell(a, p.x, p.y, gi, gj);
     for (int cyc = 0; cyc < a.num_cycles; ++cyc) {
         if (!__any_sync(FULL, alive)) break;
         const uint32_t s0 = (uint32_t)cyc * 4u;
@@ -486,17 +608,12 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
         }
         bool bad, hit;
         if (!BOX) {
-            // basic:1888-1894 wall check on noisy qpos: noise-free unless a comparison is within the noise bound
-            double wx = p.x, wy = p.y;
-            if (NOISE && part && wall_close(a, tb, p.x, p.y, cw0f)) {
-                if (!have0) gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
-                wx = noisy(p.x, n4[2], a.sigma_p);
-                wy = noisy(p.y, n4[3], a.sigma_p);
-            }
-            Rect dummy;
-            bad = part && !wall_valid<false>(tb, a.L, wx, wy, cw0, dummy);
+            // basic:1888-1894 wall check on noisy qpos: float32 for the tracked cell, exact (with noise) when too close
+            bad = wall_bad_circle<NOISE>(a, tb, part, p.x, p.y, cw0, cw0f, gi, gj, ln.env_global, event,
+                                         s0 + GPR_RNG_BLOCK_VEL_WALL, ln.m, 2, n4, have0);
             // basic:1895-1901 mover check on an independently noisy qpos
-            hit = pair_circle<G, NOISE>(a, ln.lane, ln.m, part, p.x, p.y, cm0, 0, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER);
+            hit = pair_circle_fast<G, NOISE>(a, ln.lane, ln.m, part, p.x, p.y, cm0, 0, ln.env_global, event,
+                                             s0 + GPR_RNG_BLOCK_MOVER);
         } else {
             double wx = p.x, wy = p.y, mx = p.x, my = p.y;
             Rect rw, rm;
