@@ -57,6 +57,10 @@ struct gpr_handle {
     float* ep_return = nullptr;
     double* stats = nullptr;
     uint32_t* fail_count = nullptr;
+    int32_t* reset_list = nullptr;    // auto-reset work list (see planning_autoreset_kernel)
+    uint32_t* reset_count = nullptr;  // [2] count, [2] cursor
+    int parity = 0;
+    int num_sms = 148;
     // pushing state
     double2* act = nullptr;        // [B] jerk integrator state
     double2* mover_yaw = nullptr;  // [B] (yaw, yaw rate)
@@ -168,7 +172,7 @@ extern "C" void gpr_destroy(gpr_handle* h) {
     cudaGetDevice(&prev);
     cudaSetDevice(h->device);
     void* ptrs[] = {h->pos, h->vel, h->acc, h->goal, h->elapsed, h->rng, h->needs_reset, h->ep_return, h->stats,
-                    h->fail_count, h->act, h->mover_yaw, h->obj_pos, h->obj_vel, h->cx, h->cy, h->c_wall, h->c_mover,
+                    h->fail_count, h->reset_list, h->reset_count, h->act, h->mover_yaw, h->obj_pos, h->obj_vel, h->cx, h->cy, h->c_wall, h->c_mover,
                     h->cell, h->d_stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -225,6 +229,9 @@ extern "C" int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_ha
     TRY(dalloc(&h->ep_return, B));
     TRY(dalloc(&h->stats, 6));
     TRY(dalloc(&h->fail_count, 1));
+    TRY(dalloc(&h->reset_list, B));
+    TRY(dalloc(&h->reset_count, 4));
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (cfg->env_kind == GPR_ENV_PUSHING) {
         TRY(dalloc(&h->act, B));
         TRY(dalloc(&h->mover_yaw, B));
@@ -358,43 +365,48 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     a.ep_return = h->ep_return;
     a.stats = h->stats;
     a.fail_count = h->fail_count;
+    a.reset_list = h->reset_list;
+    a.reset_count = h->reset_count;
+    a.reset_cursor = h->reset_count + 2;
+    a.parity = h->parity;
     if (out) a.out = *out;
     return a;
 }
 
-template <int G, bool BOX>
-static cudaError_t launch_plan_gb(bool reset, bool noise, const PlanArgs& a, cudaStream_t s) {
+enum PlanKernel { PLAN_STEP = 0, PLAN_RESET = 1, PLAN_AUTORESET = 2 };
+
+template <int G, bool BOX, bool NOISE>
+static cudaError_t launch_plan_gbn(PlanKernel which, const PlanArgs& a, int num_sms, cudaStream_t s) {
     const int threads = 256;
     const long long lanes = (long long)a.B * G;
     const unsigned blocks = (unsigned)((lanes + threads - 1) / threads);
-    if (reset) {
-        if (noise)
-            planning_reset_kernel<G, BOX, true><<<blocks, threads, 0, s>>>(a);
-        else
-            planning_reset_kernel<G, BOX, false><<<blocks, threads, 0, s>>>(a);
+    if (which == PLAN_RESET) {
+        planning_reset_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
+    } else if (which == PLAN_STEP) {
+        planning_step_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
     } else {
-        if (noise)
-            planning_step_kernel<G, BOX, true><<<blocks, threads, 0, s>>>(a);
-        else
-            planning_step_kernel<G, BOX, false><<<blocks, threads, 0, s>>>(a);
+        // one warp per finished env, pulled through an atomic cursor: a fixed grid of 8 CTAs (4 warps each) per SM
+        const unsigned ab = (unsigned)std::min<long long>(((long long)a.B + 3) / 4, (long long)num_sms * 8);
+        planning_autoreset_kernel<G, BOX, NOISE><<<ab, 128, 0, s>>>(a);
     }
     return cudaGetLastError();
 }
 
 template <int G>
-static cudaError_t launch_plan_g(bool reset, bool box, bool noise, const PlanArgs& a, cudaStream_t s) {
-    return box ? launch_plan_gb<G, true>(reset, noise, a, s) : launch_plan_gb<G, false>(reset, noise, a, s);
+static cudaError_t launch_plan_g(PlanKernel which, bool box, bool noise, const PlanArgs& a, int num_sms, cudaStream_t s) {
+    if (box) return noise ? launch_plan_gbn<G, true, true>(which, a, num_sms, s) : launch_plan_gbn<G, true, false>(which, a, num_sms, s);
+    return noise ? launch_plan_gbn<G, false, true>(which, a, num_sms, s) : launch_plan_gbn<G, false, false>(which, a, num_sms, s);
 }
 
-static cudaError_t launch_plan(const gpr_handle* h, bool reset, const PlanArgs& a, cudaStream_t s) {
+static cudaError_t launch_plan(const gpr_handle* h, PlanKernel which, const PlanArgs& a, cudaStream_t s) {
     const bool box = h->cfg.c_shape == GPR_SHAPE_BOX;
     switch (h->G) {
-        case 1: return launch_plan_g<1>(reset, box, h->noise, a, s);
-        case 2: return launch_plan_g<2>(reset, box, h->noise, a, s);
-        case 4: return launch_plan_g<4>(reset, box, h->noise, a, s);
-        case 8: return launch_plan_g<8>(reset, box, h->noise, a, s);
-        case 16: return launch_plan_g<16>(reset, box, h->noise, a, s);
-        default: return launch_plan_g<32>(reset, box, h->noise, a, s);
+        case 1: return launch_plan_g<1>(which, box, h->noise, a, h->num_sms, s);
+        case 2: return launch_plan_g<2>(which, box, h->noise, a, h->num_sms, s);
+        case 4: return launch_plan_g<4>(which, box, h->noise, a, h->num_sms, s);
+        case 8: return launch_plan_g<8>(which, box, h->noise, a, h->num_sms, s);
+        case 16: return launch_plan_g<16>(which, box, h->noise, a, h->num_sms, s);
+        default: return launch_plan_g<32>(which, box, h->noise, a, h->num_sms, s);
     }
 }
 
@@ -438,7 +450,7 @@ extern "C" int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, u
         a.reset_mask = reset_mask;
         a.inject_start = reinterpret_cast<const double2*>(inject_start);
         a.inject_goal = reinterpret_cast<const double2*>(inject_goal);
-        CU(launch_plan(h, true, a, s));
+        CU(launch_plan(h, PLAN_RESET, a, s));
     } else {
         PushArgs a = push_args(h, out);
         a.reset_mask = reset_mask;
@@ -460,7 +472,12 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
     if (h->cfg.env_kind == GPR_ENV_PLANNING) {
         PlanArgs a = plan_args(h, out);
         a.action = reinterpret_cast<const float2*>(action);
-        CU(launch_plan(h, false, a, s));
+        CU(launch_plan(h, PLAN_STEP, a, s));
+        if (h->cfg.autoreset_mode != GPR_AUTORESET_OFF) {
+            CU(launch_plan(h, PLAN_AUTORESET, a, s));
+            h->parity ^= 1;
+            h->launches += 1;
+        }
     } else {
         PushArgs a = push_args(h, out);
         a.action = reinterpret_cast<const float2*>(action);

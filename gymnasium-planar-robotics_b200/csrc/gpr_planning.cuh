@@ -61,6 +61,11 @@ struct PlanArgs {
     float* ep_return;
     double* stats;         // 6 accumulators, see gpr_episode_stats
     uint32_t* fail_count;  // number of resets whose rejection loop hit max_reset_attempts
+    // auto-reset work list: the step kernel appends finished envs, the auto-reset kernel consumes them (one warp per env)
+    int32_t* reset_list;     // [B]
+    uint32_t* reset_count;   // [2] double-buffered by step parity
+    uint32_t* reset_cursor;  // [2]
+    int parity;
     // per-call I/O
     const float2* action;
     gpr_outputs out;
@@ -271,165 +276,163 @@ __device__ __forceinline__ void store_obs(const PlanArgs& a, const Lane<G>& ln, 
 // the reference's sequential while-loop would, but with all 32/G groups of the warp testing different attempts of the
 // same environment concurrently.  KIND 0: wall check with safety offset + mover collision with safety offset;
 // KIND 1: wall check with safety offset + pairwise distance >= min_goal_dist.
+// One environment (global index eg, RNG event ev), whole warp: on return EVERY lane holds, for mover m = lane % G, the
+// position of the first accepted attempt (or of the last attempt, with failed = true, if the cap was hit).
 template <int G, bool BOX, int KIND>
-__device__ __forceinline__ void sample_positions(const PlanArgs& a, const Tables& tb, const Lane<G>& ln, bool need,
-                                                 uint32_t event, double2& out, bool& failed) {
+__device__ __forceinline__ void sample_env(const PlanArgs& a, const Tables& tb, unsigned lane, unsigned gmask_, uint32_t eg,
+                                           uint32_t ev, double2& out, bool& failed) {
     constexpr int S = 32 / G;  // attempts tested per half-iteration
-    const int slot = (int)(ln.lane / G);
-    const int m = ln.m;  // == lane % G
+    struct { unsigned lane, gmask; } ln = {lane, gmask_};
+    const int slot = (int)(lane / G);
+    const int m = (int)(lane % G);
     const bool has_mover = m < a.N;
     const int mm = has_mover ? m : 0;
     const double cw0 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 0], cw1 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 1];
     const double cs0 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0], cs1 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
     const float rf = (float)cs0, diagf = (float)cs0 + (float)cs1;  // box: |half diagonal| <= sx + sy
     const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
-    const unsigned base = ln.lane & ~(unsigned)(G - 1);
-    unsigned todo = __ballot_sync(FULL, need && m == 0);
+    const unsigned base = lane & ~(unsigned)(G - 1);
+    bool found = false;
+    for (int t0 = 0; t0 < cap && !found; t0 += 2 * S) {
+        const uint32_t blk = (uint32_t)(t0 / 2 + slot);
+        const gpr_u32x4 r = gpr_rng_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)KIND, (uint32_t)m);
+        // ---- phase 1, float32: ~99% of the attempts die on a pair that is far inside the rejection band
+        bool cand[2], needx[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = 2 * (int)blk + h;
+            const bool part = has_mover && t < cap;
+            const float xf = part ? fmaf(a.spanxf, (float)r.v[2 * h] * 2.3283064365386963e-10f, a.minxf) : 1e30f;
+            const float yf = part ? fmaf(a.spanyf, (float)r.v[2 * h + 1] * 2.3283064365386963e-10f, a.minyf) : 1e30f;
+            bool rej = false, unc = false;
+            if (G > 1) {
+#pragma unroll
+                for (int k = 1; k <= G / 2; ++k) {
+                    const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
+                    const float oxf = __shfl_sync(FULL, xf, src), oyf = __shfl_sync(FULL, yf, src);
+                    float lo2, hi2;
+                    if (KIND == 1) {
+                        lo2 = a.goal_lo2f;
+                        hi2 = a.goal_hi2f;
+                    } else if (BOX) {
+                        const float td = diagf + __shfl_sync(FULL, diagf, src) + a.pair_mgf[0];
+                        lo2 = -1.f;  // boxes: the float test can only prove a miss (centres farther than the diagonals)
+                        hi2 = td * td;
+                    } else if (a.uniform_pairs) {
+                        lo2 = a.pair_lo2f[1][0];
+                        hi2 = a.pair_hi2f[1][0];
+                    } else {
+                        const float tt = rf + __shfl_sync(FULL, rf, src), mg = a.pair_mgf[0];
+                        lo2 = tt > mg ? (tt - mg) * (tt - mg) : -1.f;
+                        hi2 = (tt + mg) * (tt + mg);
+                    }
+                    const bool mine = part && oxf < 1e29f;  // (pairs seen from both ends agree; no need to dedupe)
+                    const float dx = xf - oxf, dy = yf - oyf;
+                    const float d2 = dx * dx + dy * dy;
+                    if (mine) {
+                        if (d2 < lo2) rej = true;
+                        else if (!(d2 > hi2)) unc = true;
+                    }
+                }
+            }
+            const unsigned rejm = __ballot_sync(FULL, rej), uncm = __ballot_sync(FULL, unc);
+            cand[h] = (rejm & ln.gmask) == 0u && t < cap;
+            needx[h] = cand[h] && (uncm & ln.gmask) != 0u;
+        }
+        // ---- phase 2, float64 (exact), only when some group of the warp still has a candidate
+        if (!__any_sync(FULL, cand[0] || cand[1])) continue;
+        double xs[2], ys[2];
+        unsigned okmask[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = 2 * (int)blk + h;
+            const double x = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform32(r.v[2 * h])));  // plan:377/405
+            const double y = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform32(r.v[2 * h + 1])));
+            xs[h] = x;
+            ys[h] = y;
+            const bool part = has_mover && t < cap && cand[h];
+            bool hit = false;
+            if (G > 1 && __any_sync(FULL, needx[h])) {
+                const bool px = part && needx[h];
+                if (KIND == 0) {
+                    if (BOX) {
+                        Rect rm;
+                        rect_vertices_axis(x, y, cs0, cs1, rm);
+                        hit = pair_check<G, true>(ln.lane, m, px, x, y, cs0, cs1, rm, false, 0.0);
+                    } else {
+                        hit = pair_circle<G, false>(a, ln.lane, m, px, x, y, cs0, 1, eg, ev, 0u);  // plan:381
+                    }
+                } else {
+                    // plan:408-413: any pair closer than min_goal_dist (strict '<') rejects
+#pragma unroll
+                    for (int k = 1; k <= G / 2; ++k) {
+                        const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
+                        const double ox = __shfl_sync(FULL, x, src), oy = __shfl_sync(FULL, y, src);
+                        const bool opart = __shfl_sync(FULL, (int)px, src) != 0;
+                        const double dx = dsub(x, ox), dy = dsub(y, oy);
+                        if (px && opart && sqrt_lt(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_goal_dist)) hit = true;
+                    }
+                }
+            }
+            const unsigned hitm = __ballot_sync(FULL, hit);
+            const bool alive_grp = cand[h] && (hitm & ln.gmask) == 0u;
+            bool bad = false;
+            if (alive_grp && part) {  // plan:379 / 406 wall check with safety offset
+                Rect rw;
+                if (BOX) rect_vertices_axis(x, y, cw0, cw1, rw);
+                bad = !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);
+            }
+            const unsigned badm = __ballot_sync(FULL, bad);
+            okmask[h] = __ballot_sync(FULL, alive_grp && (badm & ln.gmask) == 0u && m == 0);
+        }
+        if (okmask[0] | okmask[1]) {
+            // sequential order is t = t0, t0+1, ...: slot-major, half-minor
+            const int s0 = okmask[0] ? (__ffs(okmask[0]) - 1) / G : 1 << 20;
+            const int s1 = okmask[1] ? (__ffs(okmask[1]) - 1) / G : 1 << 20;
+            const int hw = (2 * s0 <= 2 * s1 + 1) ? 0 : 1;
+            const int sw = hw == 0 ? s0 : s1;
+            const double wx = __shfl_sync(FULL, hw == 0 ? xs[0] : xs[1], sw * G + m);
+            const double wy = __shfl_sync(FULL, hw == 0 ? ys[0] : ys[1], sw * G + m);
+            out = make_double2(wx, wy);
+            found = true;
+        }
+    }
+    if (!found) {
+        // the reference would loop forever (plan:369); keep the last attempt's sample and report the failure
+        double ux, uy;
+        gpr_sample_xy(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE, (uint32_t)KIND, (uint32_t)(cap - 1), (uint32_t)m, &ux, &uy);
+        out = make_double2(dadd(a.min_xy[0], dmul(a.span_xy[0], ux)), dadd(a.min_xy[1], dmul(a.span_xy[1], uy)));
+        failed = true;
+    }
+}
+
+template <int G, bool BOX, int KIND>
+__device__ __forceinline__ void sample_positions(const PlanArgs& a, const Tables& tb, const Lane<G>& ln, bool need,
+                                                 uint32_t event, double2& out, bool& failed) {
+    unsigned todo = __ballot_sync(FULL, need && ln.m == 0);
     while (todo) {
         const int leader = __ffs(todo) - 1;
         todo &= todo - 1;
         const uint32_t eg = __shfl_sync(FULL, ln.env_global, leader);
         const uint32_t ev = __shfl_sync(FULL, event, leader);
         const bool target = (ln.lane / G) == (unsigned)(leader / G);
-        bool found = false;
-        for (int t0 = 0; t0 < cap && !found; t0 += 2 * S) {
-            const uint32_t blk = (uint32_t)(t0 / 2 + slot);
-            const gpr_u32x4 r = gpr_rng_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)KIND, (uint32_t)m);
-            // ---- phase 1, float32: ~99% of the attempts die on a pair that is far inside the rejection band
-            bool cand[2], needx[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int t = 2 * (int)blk + h;
-                const bool part = has_mover && t < cap;
-                const float xf = part ? fmaf(a.spanxf, (float)r.v[2 * h] * 2.3283064365386963e-10f, a.minxf) : 1e30f;
-                const float yf = part ? fmaf(a.spanyf, (float)r.v[2 * h + 1] * 2.3283064365386963e-10f, a.minyf) : 1e30f;
-                bool rej = false, unc = false;
-                if (G > 1) {
-#pragma unroll
-                    for (int k = 1; k <= G / 2; ++k) {
-                        const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
-                        const float oxf = __shfl_sync(FULL, xf, src), oyf = __shfl_sync(FULL, yf, src);
-                        float lo2, hi2;
-                        if (KIND == 1) {
-                            lo2 = a.goal_lo2f;
-                            hi2 = a.goal_hi2f;
-                        } else if (BOX) {
-                            const float td = diagf + __shfl_sync(FULL, diagf, src) + a.pair_mgf[0];
-                            lo2 = -1.f;  // boxes: the float test can only prove a miss (centres farther than the diagonals)
-                            hi2 = td * td;
-                        } else if (a.uniform_pairs) {
-                            lo2 = a.pair_lo2f[1][0];
-                            hi2 = a.pair_hi2f[1][0];
-                        } else {
-                            const float tt = rf + __shfl_sync(FULL, rf, src), mg = a.pair_mgf[0];
-                            lo2 = tt > mg ? (tt - mg) * (tt - mg) : -1.f;
-                            hi2 = (tt + mg) * (tt + mg);
-                        }
-                        const bool mine = part && oxf < 1e29f;  // (pairs seen from both ends agree; no need to dedupe)
-                        const float dx = xf - oxf, dy = yf - oyf;
-                        const float d2 = dx * dx + dy * dy;
-                        if (mine) {
-                            if (d2 < lo2) rej = true;
-                            else if (!(d2 > hi2)) unc = true;
-                        }
-                    }
-                }
-                const unsigned rejm = __ballot_sync(FULL, rej), uncm = __ballot_sync(FULL, unc);
-                cand[h] = (rejm & ln.gmask) == 0u && t < cap;
-                needx[h] = cand[h] && (uncm & ln.gmask) != 0u;
-            }
-            // ---- phase 2, float64 (exact), only when some group of the warp still has a candidate
-            if (!__any_sync(FULL, cand[0] || cand[1])) continue;
-            double xs[2], ys[2];
-            unsigned okmask[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int t = 2 * (int)blk + h;
-                const double x = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform32(r.v[2 * h])));  // plan:377/405
-                const double y = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform32(r.v[2 * h + 1])));
-                xs[h] = x;
-                ys[h] = y;
-                const bool part = has_mover && t < cap && cand[h];
-                bool hit = false;
-                if (G > 1 && __any_sync(FULL, needx[h])) {
-                    const bool px = part && needx[h];
-                    if (KIND == 0) {
-                        if (BOX) {
-                            Rect rm;
-                            rect_vertices_axis(x, y, cs0, cs1, rm);
-                            hit = pair_check<G, true>(ln.lane, m, px, x, y, cs0, cs1, rm, false, 0.0);
-                        } else {
-                            hit = pair_circle<G, false>(a, ln.lane, m, px, x, y, cs0, 1, eg, ev, 0u);  // plan:381
-                        }
-                    } else {
-                        // plan:408-413: any pair closer than min_goal_dist (strict '<') rejects
-#pragma unroll
-                        for (int k = 1; k <= G / 2; ++k) {
-                            const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
-                            const double ox = __shfl_sync(FULL, x, src), oy = __shfl_sync(FULL, y, src);
-                            const bool opart = __shfl_sync(FULL, (int)px, src) != 0;
-                            const double dx = dsub(x, ox), dy = dsub(y, oy);
-                            if (px && opart && sqrt_lt(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_goal_dist)) hit = true;
-                        }
-                    }
-                }
-                const unsigned hitm = __ballot_sync(FULL, hit);
-                const bool alive_grp = cand[h] && (hitm & ln.gmask) == 0u;
-                bool bad = false;
-                if (alive_grp && part) {  // plan:379 / 406 wall check with safety offset
-                    Rect rw;
-                    if (BOX) rect_vertices_axis(x, y, cw0, cw1, rw);
-                    bad = !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);
-                }
-                const unsigned badm = __ballot_sync(FULL, bad);
-                okmask[h] = __ballot_sync(FULL, alive_grp && (badm & ln.gmask) == 0u && m == 0);
-            }
-            if (okmask[0] | okmask[1]) {
-                // sequential order is t = t0, t0+1, ...: slot-major, half-minor
-                const int s0 = okmask[0] ? (__ffs(okmask[0]) - 1) / G : 1 << 20;
-                const int s1 = okmask[1] ? (__ffs(okmask[1]) - 1) / G : 1 << 20;
-                const int hw = (2 * s0 <= 2 * s1 + 1) ? 0 : 1;
-                const int sw = hw == 0 ? s0 : s1;
-                const double wx = __shfl_sync(FULL, hw == 0 ? xs[0] : xs[1], sw * G + m);
-                const double wy = __shfl_sync(FULL, hw == 0 ? ys[0] : ys[1], sw * G + m);
-                if (target) out = make_double2(wx, wy);
-                found = true;
-            }
-        }
-        if (!found) {
-            // the reference would loop forever (plan:369); keep the last attempt's sample and report the failure
-            double ux, uy;
-            gpr_sample_xy(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE, (uint32_t)KIND, (uint32_t)(cap - 1), (uint32_t)m, &ux, &uy);
-            if (target) {
-                out = make_double2(dadd(a.min_xy[0], dmul(a.span_xy[0], ux)), dadd(a.min_xy[1], dmul(a.span_xy[1], uy)));
-                failed = true;
-            }
+        double2 res;
+        bool f = false;
+        sample_env<G, BOX, KIND>(a, tb, ln.lane, ln.gmask, eg, ev, res, f);
+        if (target) {
+            out = res;
+            failed = failed || f;
         }
     }
 }
 
-// plan:355-418 + basic:1797-1805 for the envs with `need` set; warp-collective (every lane of the warp calls it).
+// basic:1799-1805: wall check WITH the safety offset, mover check WITHOUT, on independently noisy qpos (warp-collective)
 template <int G, bool BOX, bool NOISE>
-__device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb, const Lane<G>& ln, bool need,
-                                            uint32_t event, const double2* inj_start, const double2* inj_goal,
-                                            double2& p, double2& v, double2& acc, double2& goal, bool& mc, bool& wc,
-                                            bool& failed) {
+__device__ __forceinline__ void reset_checks(const PlanArgs& a, const Tables& tb, const Lane<G>& ln, bool need,
+                                             uint32_t event, double2 p, bool& mc, bool& wc) {
     const int mm = ln.active ? ln.m : 0;
     const double cw0 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 0], cw1 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 1];
     const double cm0 = a.c_mover[mm * 2 + 0], cm1 = a.c_mover[mm * 2 + 1];
-    failed = false;
-    if (need && inj_start != nullptr && ln.active) p = inj_start[ln.idx];
-    if (need && inj_goal != nullptr && ln.active) goal = inj_goal[ln.idx];
-    sample_positions<G, BOX, 0>(a, tb, ln, need && inj_start == nullptr, event, p, failed);
-    sample_positions<G, BOX, 1>(a, tb, ln, need && inj_goal == nullptr, event, goal, failed);
-    failed = (__ballot_sync(FULL, failed) & ln.gmask) != 0u;
-
-    // ---- fresh MjData (plan:336-353): qvel = act = qacc = 0
-    if (need) {
-        v = make_double2(0.0, 0.0);
-        acc = make_double2(0.0, 0.0);
-    }
-    // ---- basic:1799-1805: wall check WITH the safety offset, mover check WITHOUT, on independently noisy qpos
     const bool part = need && ln.active;
     bool bad, hit;
     if (!BOX) {
@@ -512,6 +515,27 @@ __device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb,
     }
 }
 
+// plan:355-418 + basic:1797-1805 for the envs with `need` set; warp-collective (every lane of the warp calls it).
+template <int G, bool BOX, bool NOISE>
+__device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb, const Lane<G>& ln, bool need,
+                                            uint32_t event, const double2* inj_start, const double2* inj_goal,
+                                            double2& p, double2& v, double2& acc, double2& goal, bool& mc, bool& wc,
+                                            bool& failed) {
+    failed = false;
+    if (need && inj_start != nullptr && ln.active) p = inj_start[ln.idx];
+    if (need && inj_goal != nullptr && ln.active) goal = inj_goal[ln.idx];
+    sample_positions<G, BOX, 0>(a, tb, ln, need && inj_start == nullptr, event, p, failed);
+    sample_positions<G, BOX, 1>(a, tb, ln, need && inj_goal == nullptr, event, goal, failed);
+    failed = (__ballot_sync(FULL, failed) & ln.gmask) != 0u;
+
+    // ---- fresh MjData (plan:336-353): qvel = act = qacc = 0
+    if (need) {
+        v = make_double2(0.0, 0.0);
+        acc = make_double2(0.0, 0.0);
+    }
+    reset_checks<G, BOX, NOISE>(a, tb, ln, need, event, p, mc, wc);
+}
+
 // reward / terminated / is_success for one env from the group reductions (plan:502-534, 459-479, 596-601)
 __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, bool wc, float& reward, bool& term,
                                                 bool& succ) {
@@ -523,7 +547,7 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
 }
 
 template <int G, bool BOX, bool NOISE>
-__global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
+__global__ void __launch_bounds__(256) planning_step_kernel(const __grid_constant__ PlanArgs a) {
     __shared__ Tables tb;
     load_tables(tb, a.L);
     __syncthreads();
@@ -704,56 +728,106 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const PlanArgs a) {
         if (a.out.wall_collision) a.out.wall_collision[ln.env] = wc;
     }
 
-    // ------------------------------------------------------------------ auto-reset
+    // ------------------------------------------------------------------ auto-reset: hand finished envs to the reset kernel
     bool need = false;
     if (a.autoreset == GPR_AUTORESET_SAME_STEP) need = done;
     if (a.autoreset == GPR_AUTORESET_NEXT_STEP) need = ln.env_ok && pending_reset;
-    if (__any_sync(FULL, need)) {
-        if (need && a.autoreset == GPR_AUTORESET_SAME_STEP)
-            store_obs<G>(a, ln, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, ov, acc, ag, goal);
-        bool rmc = false, rwc = false, failed = false;
-        reset_group<G, BOX, NOISE>(a, tb, ln, need, event, nullptr, nullptr, p, v, acc, goal, rmc, rwc, failed);
-        double2 ag2, ov2;
-        int reached2;
-        observe<G, NOISE>(a, ln, event, p, v, goal, ag2, ov2, reached2);
-        if (need) {
-            ag = ag2;
-            ov = ov2;
-            event += 1u;
-            elapsed = 0;
-            if (failed && ln.m == 0) atomicAdd(a.fail_count, 1u);
-            if (a.autoreset == GPR_AUTORESET_NEXT_STEP && ln.m == 0) {
+    {
+        const unsigned leaders = __ballot_sync(FULL, need && ln.m == 0);
+        if (leaders) {
+            unsigned slot0 = 0;
+            if (ln.lane == 0) slot0 = atomicAdd(a.reset_count + a.parity, (unsigned)__popc(leaders));
+            slot0 = __shfl_sync(FULL, slot0, 0);
+            if (need && ln.m == 0) a.reset_list[slot0 + __popc(leaders & ((1u << ln.lane) - 1u))] = ln.env;
+        }
+    }
+    if (need && a.autoreset == GPR_AUTORESET_SAME_STEP)
+        store_obs<G>(a, ln, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, ov, acc, ag, goal);
+    // (rows of envs on the reset list are overwritten by planning_autoreset_kernel)
+    if (stepped) store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, a.out.desired_goal, ov, acc, ag, goal);
+
+    // ------------------------------------------------------------------ state write-back
+    if (ln.active && stepped) {
+        a.pos[ln.idx] = p;
+        a.vel[ln.idx] = v;
+        a.acc[ln.idx] = acc;
+    }
+    if (ln.env_ok && ln.m == 0 && stepped) {
+        a.rng[ln.env] = event;
+        a.elapsed[ln.env] = elapsed;
+        if (a.autoreset == GPR_AUTORESET_NEXT_STEP) a.needs_reset[ln.env] = done ? 1 : 0;
+    }
+}
+
+// plan:355-418 + basic:1770-1833 for the envs on the reset list: ONE WARP PER ENVIRONMENT.  All 32/G lane groups test
+// different rejection-sampling attempts; lane group 0 then acts as the env's movers for the reset-time checks, the first
+// observation and the state write.  Warps pull list entries through an atomic cursor (attempt counts are geometric).
+template <int G, bool BOX, bool NOISE>
+__global__ void __launch_bounds__(128) planning_autoreset_kernel(const __grid_constant__ PlanArgs a) {
+    __shared__ Tables tb;
+    load_tables(tb, a.L);
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t count = a.reset_count[a.parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the other buffer belongs to the next step: clear it now
+        a.reset_count[a.parity ^ 1] = 0u;
+        a.reset_cursor[a.parity ^ 1] = 0u;
+    }
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(a.reset_cursor + a.parity, 1u);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= count) break;
+        Lane<G> ln;
+        ln.lane = lane;
+        ln.gmask = group_mask<G>(lane);
+        ln.env = a.reset_list[i];
+        ln.m = (int)(lane % G);
+        ln.env_ok = true;
+        ln.active = lane < (unsigned)G && ln.m < a.N;  // lane group 0 carries the env
+        ln.idx = (size_t)ln.env * (size_t)a.N + (size_t)ln.m;
+        ln.env_global = a.env_base + (uint32_t)ln.env;
+        const uint32_t event = a.rng[ln.env];
+        double2 p = make_double2(0, 0), v = p, acc = p, goal = p;
+        bool failed = false, f2 = false;
+        sample_env<G, BOX, 0>(a, tb, lane, ln.gmask, ln.env_global, event, p, failed);
+        sample_env<G, BOX, 1>(a, tb, lane, ln.gmask, ln.env_global, event, goal, f2);
+        failed = failed || f2;
+        bool mc = false, wc = false;
+        reset_checks<G, BOX, NOISE>(a, tb, ln, lane < (unsigned)G, event, p, mc, wc);
+        double2 ag, ov;
+        int reached;
+        observe<G, NOISE>(a, ln, event, p, v, goal, ag, ov, reached);
+        store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, a.out.desired_goal, ov, acc, ag, goal);
+        if (ln.active) {
+            a.pos[ln.idx] = p;
+            a.vel[ln.idx] = v;
+            a.acc[ln.idx] = acc;
+            a.goal[ln.idx] = goal;
+        }
+        if (lane == 0) {
+            a.rng[ln.env] = event + 1u;
+            a.elapsed[ln.env] = 0;
+            if (failed) atomicAdd(a.fail_count, 1u);
+            if (a.autoreset == GPR_AUTORESET_NEXT_STEP) {
                 // gymnasium NEXT_STEP: this call only resets; reward 0, not done; info of the fresh episode
                 float r2;
                 bool t2, s2;
-                planning_reward(a.N, reached2, rmc, rwc, r2, t2, s2);
+                planning_reward(a.N, reached, mc, wc, r2, t2, s2);
+                a.needs_reset[ln.env] = 0;
                 if (a.out.reward) a.out.reward[ln.env] = 0.f;
                 if (a.out.terminated) a.out.terminated[ln.env] = 0;
                 if (a.out.truncated) a.out.truncated[ln.env] = 0;
                 if (a.out.is_success) a.out.is_success[ln.env] = s2;
-                if (a.out.mover_collision) a.out.mover_collision[ln.env] = rmc;
-                if (a.out.wall_collision) a.out.wall_collision[ln.env] = rwc;
+                if (a.out.mover_collision) a.out.mover_collision[ln.env] = mc;
+                if (a.out.wall_collision) a.out.wall_collision[ln.env] = wc;
             }
         }
-    }
-    store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, a.out.desired_goal, ov, acc, ag, goal);
-
-    // ------------------------------------------------------------------ state write-back
-    if (ln.active) {
-        a.pos[ln.idx] = p;
-        a.vel[ln.idx] = v;
-        a.acc[ln.idx] = acc;
-        if (need) a.goal[ln.idx] = goal;
-    }
-    if (ln.env_ok && ln.m == 0) {
-        a.rng[ln.env] = event;
-        a.elapsed[ln.env] = elapsed;
-        if (a.autoreset == GPR_AUTORESET_NEXT_STEP) a.needs_reset[ln.env] = (done && !need) ? 1 : 0;
     }
 }
 
 template <int G, bool BOX, bool NOISE>
-__global__ void __launch_bounds__(256) planning_reset_kernel(const PlanArgs a) {
+__global__ void __launch_bounds__(256) planning_reset_kernel(const __grid_constant__ PlanArgs a) {
     __shared__ Tables tb;
     load_tables(tb, a.L);
     __syncthreads();
