@@ -13,8 +13,7 @@
 #include <new>
 #include <vector>
 
-#include "gpr_planning.cuh"
-#include "gpr_pushing.cuh"
+#include "gpr_launch.h"
 
 using namespace gpr;
 
@@ -63,8 +62,8 @@ struct gpr_handle {
     int num_sms = 148;
     // pushing state
     double2* act = nullptr;        // [B] jerk integrator state
-    double2* mover_yaw = nullptr;  // [B] (yaw, yaw rate)
-    double* obj_pos = nullptr;     // [B,3]
+    double* mover_rot = nullptr;   // [B,3] cos yaw, sin yaw, yaw rate
+    double* obj_pos = nullptr;     // [B,4] x, y, cos yaw, sin yaw
     double* obj_vel = nullptr;     // [B,3]
     // tables
     double *cx = nullptr, *cy = nullptr, *c_wall = nullptr, *c_mover = nullptr;
@@ -172,7 +171,7 @@ extern "C" void gpr_destroy(gpr_handle* h) {
     cudaGetDevice(&prev);
     cudaSetDevice(h->device);
     void* ptrs[] = {h->pos, h->vel, h->acc, h->goal, h->elapsed, h->rng, h->needs_reset, h->ep_return, h->stats,
-                    h->fail_count, h->reset_list, h->reset_count, h->act, h->mover_yaw, h->obj_pos, h->obj_vel, h->cx, h->cy, h->c_wall, h->c_mover,
+                    h->fail_count, h->reset_list, h->reset_count, h->act, h->mover_rot, h->obj_pos, h->obj_vel, h->cx, h->cy, h->c_wall, h->c_mover,
                     h->cell, h->d_stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -234,8 +233,8 @@ extern "C" int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_ha
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (cfg->env_kind == GPR_ENV_PUSHING) {
         TRY(dalloc(&h->act, B));
-        TRY(dalloc(&h->mover_yaw, B));
-        TRY(dalloc(&h->obj_pos, 3 * B));
+        TRY(dalloc(&h->mover_rot, 3 * B));
+        TRY(dalloc(&h->obj_pos, 4 * B));
         TRY(dalloc(&h->obj_vel, 3 * B));
     }
     TRY(dalloc(&h->cx, GPR_MAX_TILES_1D));
@@ -373,31 +372,6 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     return a;
 }
 
-enum PlanKernel { PLAN_STEP = 0, PLAN_RESET = 1, PLAN_AUTORESET = 2 };
-
-template <int G, bool BOX, bool NOISE>
-static cudaError_t launch_plan_gbn(PlanKernel which, const PlanArgs& a, int num_sms, cudaStream_t s) {
-    const int threads = 256;
-    const long long lanes = (long long)a.B * G;
-    const unsigned blocks = (unsigned)((lanes + threads - 1) / threads);
-    if (which == PLAN_RESET) {
-        planning_reset_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
-    } else if (which == PLAN_STEP) {
-        planning_step_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
-    } else {
-        // one warp per finished env, pulled through an atomic cursor: a fixed grid of 8 CTAs (4 warps each) per SM
-        const unsigned ab = (unsigned)std::min<long long>(((long long)a.B + 3) / 4, (long long)num_sms * 8);
-        planning_autoreset_kernel<G, BOX, NOISE><<<ab, 128, 0, s>>>(a);
-    }
-    return cudaGetLastError();
-}
-
-template <int G>
-static cudaError_t launch_plan_g(PlanKernel which, bool box, bool noise, const PlanArgs& a, int num_sms, cudaStream_t s) {
-    if (box) return noise ? launch_plan_gbn<G, true, true>(which, a, num_sms, s) : launch_plan_gbn<G, true, false>(which, a, num_sms, s);
-    return noise ? launch_plan_gbn<G, false, true>(which, a, num_sms, s) : launch_plan_gbn<G, false, false>(which, a, num_sms, s);
-}
-
 static cudaError_t launch_plan(const gpr_handle* h, PlanKernel which, const PlanArgs& a, cudaStream_t s) {
     const bool box = h->cfg.c_shape == GPR_SHAPE_BOX;
     switch (h->G) {
@@ -411,13 +385,77 @@ static cudaError_t launch_plan(const gpr_handle* h, PlanKernel which, const Plan
 }
 
 static PushArgs push_args(const gpr_handle* h, const gpr_outputs* out) {
+    const gpr_config& c = h->cfg;
     PushArgs a;
     memset(&a, 0, sizeof(a));
-    a.B = h->cfg.num_envs;
+    a.B = c.num_envs;
+    a.learn_jerk = c.learn_jerk != 0;
+    a.num_cycles = c.num_cycles;
+    a.max_episode_steps = c.max_episode_steps;
+    a.autoreset = c.autoreset_mode;
+    a.max_reset_attempts = c.max_reset_attempts;
+    a.env_base = (uint32_t)c.env_index_base;
+    a.seed = h->seed;
+    a.dt = c.cycle_time;
+    a.v_max = c.v_max;
+    a.a_max = c.a_max;
+    a.j_max = c.j_max;
+    a.act_lim = c.learn_jerk ? c.j_max : c.a_max;  // push:243-245
+    a.v_max2_lo = c.v_max * c.v_max * (1.0 - 1e-14);
+    a.a_max2_lo = c.a_max * c.a_max * (1.0 - 1e-14);
+    a.threshold = c.threshold_pos;
+    for (int k = 0; k < 2; ++k) {
+        a.min_xy[k] = c.min_xy_pos[k];
+        a.span_xy[k] = c.max_xy_pos[k] - c.min_xy_pos[k];
+        a.obj_min[k] = c.object_min_xy_pos[k];
+        a.obj_span[k] = c.object_max_xy_pos[k] - c.object_min_xy_pos[k];
+        for (int sft = 0; sft < 2; ++sft) a.c_wall[sft][k] = c.c_wall[sft][0][k];
+    }
+    a.min_mo_dist = c.min_mo_dist;
+    a.sigma_p = c.std_noise[0];
+    a.sigma_v = c.std_noise[1];
+    a.sigma_obj = c.object_noise_xy;
+    a.L = layout_args(h);
+    // planar physics parameters (include/gpr_push_physics.h)
+    gpr_push_params& P = a.P;
+    P.dt = c.cycle_time;
+    P.mover_mass = c.mover_mass;
+    P.mover_hx = c.mover_half[0];
+    P.mover_hy = c.mover_half[1];
+    P.mover_inertia = c.mover_mass * ((2 * c.mover_half[0]) * (2 * c.mover_half[0]) + (2 * c.mover_half[1]) * (2 * c.mover_half[1])) / 12.0;
+    P.obj_mass = c.object_mass;
+    P.obj_h = c.object_half_xy;
+    P.obj_inertia = c.object_mass * (2 * (2 * c.object_half_xy) * (2 * c.object_half_xy)) / 12.0;
+    P.obj_damping = c.object_damping;
+    P.mu = c.friction;
+    P.gravity = c.gravity;
+    P.k_rot = c.imp_k_rot;
+    P.d_rot = 2.0 * std::sqrt(c.imp_k_rot * c.mover_mass);  // impedance_control.py:46-47
+    P.sol_B = 2.0 / (c.solimp[1] * c.solref[0]);
+    P.sol_K = 1.0 / (c.solimp[1] * c.solimp[1] * c.solref[0] * c.solref[0] * c.solref[1] * c.solref[1]);
+    P.imp_d0 = c.solimp[0];
+    P.imp_dw = c.solimp[1];
+    P.imp_width = c.solimp[2];
+    P.imp_mid = c.solimp[3];
+    P.imp_power = c.solimp[4];
+    P.iterations = c.contact_iterations;
+    a.pos = h->pos;
+    a.vel = h->vel;
+    a.acc = h->acc;
+    a.act = h->act;
+    a.mover_rot = h->mover_rot;
+    a.obj_pos = h->obj_pos;
+    a.obj_vel = h->obj_vel;
+    a.goal = h->goal;
+    a.elapsed = h->elapsed;
+    a.rng = h->rng;
+    a.needs_reset = h->needs_reset;
+    a.ep_return = h->ep_return;
+    a.stats = h->stats;
+    a.fail_count = h->fail_count;
     if (out) a.out = *out;
     return a;
 }
-static cudaError_t launch_push(const gpr_handle*, bool, const PushArgs&, cudaStream_t) { return cudaErrorNotSupported; }
 
 struct DeviceGuard {
     int prev = 0;
@@ -457,7 +495,7 @@ extern "C" int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, u
         a.inject_start = reinterpret_cast<const double2*>(inject_start);
         a.inject_goal = reinterpret_cast<const double2*>(inject_goal);
         a.inject_object = reinterpret_cast<const double2*>(inject_object);
-        CU(launch_push(h, true, a, s));
+        CU(launch_push(true, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, s));
     }
     h->launches += 1;
     return GPR_OK;
@@ -481,7 +519,7 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
     } else {
         PushArgs a = push_args(h, out);
         a.action = reinterpret_cast<const float2*>(action);
-        CU(launch_push(h, false, a, s));
+        CU(launch_push(false, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, s));
     }
     h->launches += 1;
     return GPR_OK;
@@ -534,15 +572,31 @@ static void** out_slot(gpr_outputs* o, int k) {
     return slots[k];
 }
 
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// device staging -> host results.  Page-locked destinations (e.g. torch pinned tensors / cudaHostRegister'ed arrays) are
+// written by the copy engine directly; pageable ones go through the handle's pinned mirror and one memcpy.
 static int copy_back(gpr_handle* h, const StageLayout& L, const gpr_outputs* host_out) {
     gpr_outputs ho = *host_out;
     char* hs = (char*)h->h_stage;
     char* ds = (char*)h->d_stage;
-    for (int k = 0; k < 12; ++k)
-        if (*out_slot(&ho, k)) CU(cudaMemcpyAsync(hs + L.off[k], ds + L.off[k], L.bytes[k], cudaMemcpyDeviceToHost, h->host_stream));
+    bool direct[12];
+    for (int k = 0; k < 12; ++k) {
+        void* dst = *out_slot(&ho, k);
+        if (!dst) continue;
+        direct[k] = is_pinned(dst);
+        CU(cudaMemcpyAsync(direct[k] ? dst : (void*)(hs + L.off[k]), ds + L.off[k], L.bytes[k], cudaMemcpyDeviceToHost, h->host_stream));
+    }
     CU(cudaStreamSynchronize(h->host_stream));
     for (int k = 0; k < 12; ++k)
-        if (*out_slot(&ho, k)) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
+        if (*out_slot(&ho, k) && !direct[k]) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
     return GPR_OK;
 }
 
@@ -561,9 +615,12 @@ extern "C" int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_
     if (rc != GPR_OK) return rc;
     const StageLayout L = stage_layout(h);
     const size_t abytes = (size_t)h->cfg.num_envs * h->action_dim * sizeof(float);
-    memcpy((char*)h->h_stage + L.off_action, host_action, abytes);
-    CU(cudaMemcpyAsync((char*)h->d_stage + L.off_action, (char*)h->h_stage + L.off_action, abytes, cudaMemcpyHostToDevice,
-                       h->host_stream));
+    const void* src = host_action;
+    if (!is_pinned(host_action)) {  // pageable caller buffer: stage through the pinned mirror
+        memcpy((char*)h->h_stage + L.off_action, host_action, abytes);
+        src = (char*)h->h_stage + L.off_action;
+    }
+    CU(cudaMemcpyAsync((char*)h->d_stage + L.off_action, src, abytes, cudaMemcpyHostToDevice, h->host_stream));
     gpr_outputs dv = device_outputs(h, L, host_out);
     rc = gpr_step(h, (const float*)((char*)h->d_stage + L.off_action), &dv, h->host_stream);
     if (rc != GPR_OK) return rc;
@@ -600,8 +657,8 @@ static int copy_state(gpr_handle* h, const gpr_state* st, bool to_handle, cudaSt
         {h->elapsed, st->elapsed_steps, B * sizeof(int32_t)},
         {h->rng, st->rng_counter, B * sizeof(uint32_t)},
         {h->act, st->act, B * sizeof(double2)},
-        {h->mover_yaw, st->mover_yaw, B * sizeof(double2)},
-        {h->obj_pos, st->object_pos, 3 * B * sizeof(double)},
+        {h->mover_rot, st->mover_yaw, 3 * B * sizeof(double)},
+        {h->obj_pos, st->object_pos, 4 * B * sizeof(double)},
         {h->obj_vel, st->object_vel, 3 * B * sizeof(double)},
     };
     for (const Item& it : items) {
@@ -631,11 +688,8 @@ extern "C" int gpr_compute_reward(gpr_handle* h, int batch, const float* achieve
     if (batch < 0) return fail(GPR_ERR_INVALID_ARG, "batch < 0");
     if (batch == 0) return GPR_OK;
     DeviceGuard g(h->device);
-    const int threads = 256;
-    compute_reward_kernel<<<(batch + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
-        h->cfg.env_kind, h->cfg.num_movers, batch, h->cfg.threshold_pos, achieved, desired, mover_collision, wall_collision,
-        reward, terminated);
-    CU(cudaGetLastError());
+    CU(launch_compute_reward(h->cfg.env_kind, h->cfg.num_movers, batch, h->cfg.threshold_pos, achieved, desired, mover_collision,
+                             wall_collision, reward, terminated, (cudaStream_t)stream));
     h->launches += 1;
     return GPR_OK;
 }

@@ -137,7 +137,7 @@ __device__ __forceinline__ bool segments_intersect(double p1x, double p1y, doubl
     const double pb = dmul(orient(q1x, q1y, q2x, q2y, p1x, p1y), orient(q1x, q1y, q2x, q2y, p2x, p2y));
     return ((pa <= 0.0) || (fabs(pa) < 1e-7)) && ((pb <= 0.0) || (fabs(pb) < 1e-7));  // geom:62-64
 }
-__device__ __noinline__ bool rects_intersect(const Rect& a, const Rect& b) {
+static __device__ __noinline__ bool rects_intersect(const Rect& a, const Rect& b) {
     bool any = false;  // geom:132-138: 4 x 4 edge pairs
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {

@@ -1,0 +1,37 @@
+// gpr_planning_g.cu — planning kernels for ONE lane-group width (compile with -DGPR_G=<1|2|4|8|16|32>).
+#include <algorithm>
+
+#include "gpr_launch.h"
+
+#ifndef GPR_G
+#error "compile with -DGPR_G=<lane group width>"
+#endif
+
+namespace gpr {
+
+template <int G, bool BOX, bool NOISE>
+static cudaError_t launch_plan_gbn(PlanKernel which, const PlanArgs& a, int num_sms, cudaStream_t s) {
+    const int threads = 256;
+    const long long lanes = (long long)a.B * G;
+    const unsigned blocks = (unsigned)((lanes + threads - 1) / threads);
+    if (which == PLAN_RESET) {
+        planning_reset_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
+    } else if (which == PLAN_STEP) {
+        planning_step_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
+    } else {
+        // one warp per finished env, pulled through an atomic cursor: a fixed grid of 8 CTAs (4 warps each) per SM
+        const unsigned ab = (unsigned)std::min<long long>(((long long)a.B + 3) / 4, (long long)num_sms * 8);
+        planning_autoreset_kernel<G, BOX, NOISE><<<ab, 128, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+template <int G>
+cudaError_t launch_plan_g(PlanKernel which, bool box, bool noise, const PlanArgs& a, int num_sms, cudaStream_t s) {
+    if (box) return noise ? launch_plan_gbn<G, true, true>(which, a, num_sms, s) : launch_plan_gbn<G, true, false>(which, a, num_sms, s);
+    return noise ? launch_plan_gbn<G, false, true>(which, a, num_sms, s) : launch_plan_gbn<G, false, false>(which, a, num_sms, s);
+}
+
+template cudaError_t launch_plan_g<GPR_G>(PlanKernel, bool, bool, const PlanArgs&, int, cudaStream_t);
+
+}  // namespace gpr

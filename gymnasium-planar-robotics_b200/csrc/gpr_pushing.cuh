@@ -1,12 +1,52 @@
-// gpr_pushing.cuh — fused kernels of BenchmarkPushingEnv's step path (placeholder until the planar contact model lands).
+// gpr_pushing.cuh — fused kernels of BenchmarkPushingEnv's step path: one lane per environment (one mover + one object).
+//
+//   pushing_step_kernel : basic:1835-1950 — action clip, num_cycles x { push:419-455 limit control + yaw impedance,
+//                         planar mj_step substitute with mover-object box contact and object-ground friction
+//                         (include/gpr_push_physics.h), basic:459-788 wall check, break on wall collision },
+//                         push:529-576 observation, push:578-608 info, push:499-527 reward, push:457-476 terminated,
+//                         TimeLimit, episode statistics, auto-reset (push:373-417).
+//   pushing_reset_kernel: basic:1770-1833 for a masked subset with optional injected positions.
+//
+// This translation unit is compiled with -fmad=false: the shared physics header uses plain float64 expressions and must
+// round exactly like the CPU oracle (gcc -ffp-contract=off).
 #pragma once
 
+#include "../../include/gpr_push_physics.h"
 #include "gpr_device.cuh"
 
 namespace gpr {
 
 struct PushArgs {
     int B;
+    int learn_jerk, num_cycles, max_episode_steps, autoreset, max_reset_attempts;
+    uint32_t env_base;
+    uint64_t seed;
+    double dt, v_max, a_max, j_max, act_lim;
+    double v_max2_lo, a_max2_lo;
+    double threshold;
+    double min_xy[2], span_xy[2];          // mover spawn box (push:250-255)
+    double obj_min[2], obj_span[2];        // object / goal box (push:257-258)
+    double min_mo_dist;                    // push:279-288, strict '>' accepts
+    double sigma_p, sigma_v, sigma_obj;    // sensor noise; object position noise 1e-5 (push:178)
+    double c_wall[2][2];                   // [safety][xy] mover collision size incl. offsets (basic:487)
+    LayoutArgs L;
+    gpr_push_params P;
+    // state (SoA, float64)
+    double2* pos;      // mover x, y
+    double2* vel;
+    double2* acc;      // MuJoCo qacc of the mover (differs from `act` under contact)
+    double2* act;      // jerk-mode integrator state
+    double* mover_rot;  // [B,3] cos yaw, sin yaw, yaw rate
+    double* obj_pos;    // [B,4] x, y, cos yaw, sin yaw
+    double* obj_vel;    // [B,3] vx, vy, yaw rate
+    double2* goal;     // object goal
+    int32_t* elapsed;
+    uint32_t* rng;
+    uint8_t* needs_reset;
+    float* ep_return;
+    double* stats;
+    uint32_t* fail_count;
+    // per-call I/O
     const float2* action;
     gpr_outputs out;
     const uint8_t* reset_mask;
@@ -14,5 +54,322 @@ struct PushArgs {
     const double2* inject_goal;
     const double2* inject_object;
 };
+
+struct PushState {
+    gpr_body2 M, O;
+    double2 acc, act, goal;
+};
+
+__device__ __forceinline__ void push_load(const PushArgs& a, int e, PushState& s) {
+    const double2 p = a.pos[e], v = a.vel[e];
+    s.M.x = p.x;
+    s.M.y = p.y;
+    s.M.vx = v.x;
+    s.M.vy = v.y;
+    s.M.c = a.mover_rot[3 * e + 0];
+    s.M.s = a.mover_rot[3 * e + 1];
+    s.M.w = a.mover_rot[3 * e + 2];
+    s.O.x = a.obj_pos[4 * e + 0];
+    s.O.y = a.obj_pos[4 * e + 1];
+    s.O.c = a.obj_pos[4 * e + 2];
+    s.O.s = a.obj_pos[4 * e + 3];
+    s.O.vx = a.obj_vel[3 * e + 0];
+    s.O.vy = a.obj_vel[3 * e + 1];
+    s.O.w = a.obj_vel[3 * e + 2];
+    s.acc = a.acc[e];
+    s.act = a.act[e];
+    s.goal = a.goal[e];
+}
+
+__device__ __forceinline__ void push_store(const PushArgs& a, int e, const PushState& s) {
+    a.pos[e] = make_double2(s.M.x, s.M.y);
+    a.vel[e] = make_double2(s.M.vx, s.M.vy);
+    a.mover_rot[3 * e + 0] = s.M.c;
+    a.mover_rot[3 * e + 1] = s.M.s;
+    a.mover_rot[3 * e + 2] = s.M.w;
+    a.obj_pos[4 * e + 0] = s.O.x;
+    a.obj_pos[4 * e + 1] = s.O.y;
+    a.obj_pos[4 * e + 2] = s.O.c;
+    a.obj_pos[4 * e + 3] = s.O.s;
+    a.obj_vel[3 * e + 0] = s.O.vx;
+    a.obj_vel[3 * e + 1] = s.O.vy;
+    a.obj_vel[3 * e + 2] = s.O.w;
+    a.acc[e] = s.acc;
+    a.act[e] = s.act;
+    a.goal[e] = s.goal;
+}
+
+// basic:1888-1894 / 1799-1801 for the single mover: noisy qpos (position and, for the box shape, the yaw quaternion)
+template <bool BOX, bool NOISE>
+__device__ __forceinline__ bool push_wall_bad(const PushArgs& a, const Tables& tb, const gpr_body2& M, int safety,
+                                              float nx, float ny, uint32_t env_global, uint32_t event, uint32_t qstream) {
+    double wx = M.x, wy = M.y;
+    if (NOISE) {
+        wx = dadd(M.x, dmul((double)nx, a.sigma_p));
+        wy = dadd(M.y, dmul((double)ny, a.sigma_p));
+    }
+    const double c0 = a.c_wall[safety][0], c1 = a.c_wall[safety][1];
+    Rect r;
+    if (BOX) {
+        // yaw quaternion (cos(yaw/2), 0, 0, sin(yaw/2)) from (cos yaw, sin yaw) by the half-angle identities
+        const double ch = dsqrt(dmul(0.5, dadd(1.0, M.c)));
+        const double sh = ddiv(M.s, dmul(2.0, ch));
+        double qw = ch, qx = 0.0, qy = 0.0, qz = sh;
+        if (NOISE) {
+            float q[4];
+            gpr_normal4(a.seed, env_global, event, qstream, 0u, q);
+            qw = dadd(qw, dmul((double)q[0], a.sigma_p));
+            qx = dmul((double)q[1], a.sigma_p);
+            qy = dmul((double)q[2], a.sigma_p);
+            qz = dadd(qz, dmul((double)q[3], a.sigma_p));
+        }
+        rect_vertices(wx, wy, qw, qx, qy, qz, c0, c1, r);
+    }
+    return !wall_valid<BOX>(tb, a.L, wx, wy, c0, r);
+}
+
+// push:529-576 observation + push:499-527 / 457-476 / 578-608 reward, terminated, is_success
+template <bool NOISE>
+__device__ __forceinline__ void push_observe(const PushArgs& a, const PushState& s, uint32_t env_global, uint32_t event,
+                                             double (&obs)[6], double2& ag, bool& reached) {
+    double px = s.M.x, py = s.M.y, vx = s.M.vx, vy = s.M.vy;
+    if (NOISE) {
+        float n4[4];
+        gpr_normal4(a.seed, env_global, event, GPR_RNG_OBS, 0u, n4);
+        px = dadd(px, dmul((double)n4[0], a.sigma_p));
+        py = dadd(py, dmul((double)n4[1], a.sigma_p));
+        vx = dadd(vx, dmul((double)n4[2], a.sigma_v));
+        vy = dadd(vy, dmul((double)n4[3], a.sigma_v));
+    }
+    obs[0] = px;
+    obs[1] = py;
+    obs[2] = vx;
+    obs[3] = vy;
+    obs[4] = s.acc.x;  // qacc, no noise (push:556)
+    obs[5] = s.acc.y;
+    ag = make_double2(s.O.x, s.O.y);
+    if (a.sigma_obj != 0.0) {  // push:565: always-on object position noise
+        float k4[4];
+        gpr_normal4(a.seed, env_global, event, GPR_RNG_OBJECT, 0u, k4);
+        ag.x = dadd(ag.x, dmul((double)k4[0], a.sigma_obj));
+        ag.y = dadd(ag.y, dmul((double)k4[1], a.sigma_obj));
+    }
+    const double dx = dsub(ag.x, s.goal.x), dy = dsub(ag.y, s.goal.y);
+    reached = sqrt_le(dadd(dmul(dx, dx), dmul(dy, dy)), a.threshold);  // push:519
+}
+
+__device__ __forceinline__ void push_store_obs(const PushArgs& a, int e, float* O, float* AG, float* DG, const double (&obs)[6],
+                                               double2 ag, double2 goal) {
+    if (O) {
+        const int od = 2 * (2 + a.learn_jerk);
+        float* row = O + (size_t)e * od;
+        reinterpret_cast<float2*>(row)[0] = make_float2((float)obs[0], (float)obs[1]);
+        reinterpret_cast<float2*>(row)[1] = make_float2((float)obs[2], (float)obs[3]);
+        if (a.learn_jerk) reinterpret_cast<float2*>(row)[2] = make_float2((float)obs[4], (float)obs[5]);
+    }
+    if (AG) reinterpret_cast<float2*>(AG)[e] = make_float2((float)ag.x, (float)ag.y);
+    if (DG) reinterpret_cast<float2*>(DG)[e] = make_float2((float)goal.x, (float)goal.y);
+}
+
+// push:373-417 + basic:1797-1805 for one env. Returns true if the object rejection loop hit the cap.
+template <bool BOX, bool NOISE>
+__device__ __forceinline__ bool push_reset_one(const PushArgs& a, const Tables& tb, PushState& s, uint32_t env_global,
+                                               uint32_t event, const double2* inj_start, const double2* inj_goal,
+                                               const double2* inj_object, int e, bool& wc) {
+    double ux, uy;
+    if (inj_start) {
+        s.M.x = inj_start[e].x;
+        s.M.y = inj_start[e].y;
+    } else {  // push:387-389
+        gpr_sample_xy(a.seed, env_global, event, GPR_RNG_RESET_SAMPLE, 0u, 0u, 0u, &ux, &uy);
+        s.M.x = dadd(a.min_xy[0], dmul(a.span_xy[0], ux));
+        s.M.y = dadd(a.min_xy[1], dmul(a.span_xy[1], uy));
+    }
+    bool failed = false;
+    if (inj_object) {
+        s.O.x = inj_object[e].x;
+        s.O.y = inj_object[e].y;
+    } else {  // push:392-404: redraw until the object is farther than min_mo_dist from the mover (strict '>')
+        const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
+        bool ok = false;
+        for (int t = 0; t < cap && !ok; ++t) {
+            gpr_sample_xy(a.seed, env_global, event, GPR_RNG_RESET_OBJECT, 0u, (uint32_t)t, 0u, &ux, &uy);
+            s.O.x = dadd(a.obj_min[0], dmul(a.obj_span[0], ux));
+            s.O.y = dadd(a.obj_min[1], dmul(a.obj_span[1], uy));
+            const double dx = dsub(s.O.x, s.M.x), dy = dsub(s.O.y, s.M.y);
+            ok = !sqrt_le(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_mo_dist);
+        }
+        failed = !ok;
+    }
+    if (inj_goal) {
+        s.goal = inj_goal[e];
+    } else {  // push:409-411
+        gpr_sample_xy(a.seed, env_global, event, GPR_RNG_RESET_OBJECT, 1u, 0u, 0u, &ux, &uy);
+        s.goal.x = dadd(a.obj_min[0], dmul(a.obj_span[0], ux));
+        s.goal.y = dadd(a.obj_min[1], dmul(a.obj_span[1], uy));
+    }
+    // reload_model (push:353-371): fresh MjData, everything at rest, identity orientations
+    s.M.vx = s.M.vy = s.M.w = 0.0;
+    s.M.c = 1.0;
+    s.M.s = 0.0;
+    s.O.vx = s.O.vy = s.O.w = 0.0;
+    s.O.c = 1.0;
+    s.O.s = 0.0;
+    s.acc = make_double2(0.0, 0.0);
+    s.act = make_double2(0.0, 0.0);
+    // basic:1799-1801 wall check with the safety offset on noisy qpos
+    float n4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (NOISE) gpr_normal4(a.seed, env_global, event, GPR_RNG_RESET_CHECK, 0u, n4);
+    wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 1, n4[0], n4[1], env_global, event, GPR_RNG_RESET_CHECK_WQUAT);
+    return failed;
+}
+
+__device__ __forceinline__ void push_reward(bool reached, bool wc, float& reward, bool& term, bool& succ) {
+    reward = wc ? -50.f : (reached ? 0.f : -1.f);  // push:521-523
+    term = wc;                                      // push:475
+    succ = reached && !wc;                          // push:602
+}
+
+template <bool BOX, bool NOISE>
+__global__ void __launch_bounds__(128) pushing_step_kernel(const __grid_constant__ PushArgs a) {
+    __shared__ Tables tb;
+    load_tables(tb, a.L);
+    __syncthreads();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.B) return;
+    const uint32_t env_global = a.env_base + (uint32_t)e;
+    PushState s;
+    push_load(a, e, s);
+    uint32_t event = a.rng[e];
+    int elapsed = a.elapsed[e];
+    const bool pending = a.autoreset == GPR_AUTORESET_NEXT_STEP && a.needs_reset[e] != 0;
+    double obs[6] = {0, 0, 0, 0, 0, 0};
+    double2 ag = make_double2(0, 0);
+    bool reached = false;
+    float reward = 0.f;
+    bool term = false, succ = false, wc = false;
+    if (!pending) {
+        const float2 af = a.action[e];
+        const double ux = fmin(fmax((double)af.x, -a.act_lim), a.act_lim);  // basic:1869-1873
+        const double uy = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
+        for (int cyc = 0; cyc < a.num_cycles; ++cyc) {  // basic:1879
+            float n4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (NOISE) gpr_normal4(a.seed, env_global, event, (uint32_t)cyc * 4u + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
+            // push:419-455 _mujoco_step_callback
+            double velx = s.M.vx, vely = s.M.vy;
+            if (NOISE) {
+                velx = dadd(velx, dmul((double)n4[0], a.sigma_v));
+                vely = dadd(vely, dmul((double)n4[1], a.sigma_v));
+            }
+            double cx, cy, t0, t1;
+            if (a.learn_jerk) {
+                double atx, aty, jx, jy, ax, ay;
+                ensure_max(s.acc.x, s.acc.y, a.a_max, a.a_max2_lo, ux, uy, a.dt, atx, aty, jx, jy);  // push:432 (acc = real qacc)
+                ensure_max(velx, vely, a.v_max, a.v_max2_lo, atx, aty, a.dt, t0, t1, ax, ay);        // push:435
+                if (atx != ax || aty != ay) {                                                        // push:436
+                    jx = ddiv(dsub(ax, s.acc.x), a.dt);
+                    jy = ddiv(dsub(ay, s.acc.y), a.dt);
+                }
+                // integrator actuator with actearly (push:305-311): act += dt*ctrl, force uses the new act
+                s.act.x = dadd(s.act.x, dmul(a.dt, jx));
+                s.act.y = dadd(s.act.y, dmul(a.dt, jy));
+                cx = s.act.x;
+                cy = s.act.y;
+            } else {
+                ensure_max(velx, vely, a.v_max, a.v_max2_lo, ux, uy, a.dt, t0, t1, cx, cy);  // push:440
+            }
+            double qax, qay;
+            gpr_push_substep(&a.P, &s.M, &s.O, cx, cy, &qax, &qay);  // mj_step (basic:1882)
+            s.acc = make_double2(qax, qay);
+            // basic:1888-1894 wall check; no mover-mover check with one mover; push:607 asserts no mover collision
+            wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 0, n4[2], n4[3], env_global, event,
+                                           (uint32_t)cyc * 4u + GPR_RNG_BLOCK_WALL_QUAT);
+            if (wc) break;  // basic:1904
+        }
+        push_observe<NOISE>(a, s, env_global, event, obs, ag, reached);
+        push_reward(reached, wc, reward, term, succ);
+        event += 1u;
+        elapsed += 1;
+    }
+    const bool stepped = !pending;
+    const bool trunc = stepped && a.max_episode_steps > 0 && elapsed >= a.max_episode_steps;
+    const bool done = stepped && (term || trunc);
+    if (stepped) {
+        const float ret = a.ep_return[e] + reward;
+        if (done) {
+            atomicAdd(a.stats + 0, 1.0);
+            atomicAdd(a.stats + 1, (double)ret);
+            atomicAdd(a.stats + 2, (double)elapsed);
+            if (succ) atomicAdd(a.stats + 3, 1.0);
+            if (wc) atomicAdd(a.stats + 5, 1.0);
+        }
+        a.ep_return[e] = done ? 0.f : ret;
+        if (a.out.reward) a.out.reward[e] = reward;
+        if (a.out.terminated) a.out.terminated[e] = term;
+        if (a.out.truncated) a.out.truncated[e] = trunc;
+        if (a.out.is_success) a.out.is_success[e] = succ;
+        if (a.out.mover_collision) a.out.mover_collision[e] = 0;
+        if (a.out.wall_collision) a.out.wall_collision[e] = wc;
+    }
+    const bool need = (a.autoreset == GPR_AUTORESET_SAME_STEP && done) || pending;
+    if (need) {
+        if (a.autoreset == GPR_AUTORESET_SAME_STEP)
+            push_store_obs(a, e, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, obs, ag, s.goal);
+        bool rwc;
+        const bool failed = push_reset_one<BOX, NOISE>(a, tb, s, env_global, event, nullptr, nullptr, nullptr, e, rwc);
+        push_observe<NOISE>(a, s, env_global, event, obs, ag, reached);
+        event += 1u;
+        elapsed = 0;
+        if (failed) atomicAdd(a.fail_count, 1u);
+        if (pending) {  // gymnasium NEXT_STEP: this call only resets
+            float r2;
+            bool t2, s2;
+            push_reward(reached, rwc, r2, t2, s2);
+            if (a.out.reward) a.out.reward[e] = 0.f;
+            if (a.out.terminated) a.out.terminated[e] = 0;
+            if (a.out.truncated) a.out.truncated[e] = 0;
+            if (a.out.is_success) a.out.is_success[e] = s2;
+            if (a.out.mover_collision) a.out.mover_collision[e] = 0;
+            if (a.out.wall_collision) a.out.wall_collision[e] = rwc;
+        }
+    }
+    push_store_obs(a, e, a.out.observation, a.out.achieved_goal, a.out.desired_goal, obs, ag, s.goal);
+    push_store(a, e, s);
+    a.rng[e] = event;
+    a.elapsed[e] = elapsed;
+    if (a.autoreset == GPR_AUTORESET_NEXT_STEP) a.needs_reset[e] = (done && !need) ? 1 : 0;
+}
+
+template <bool BOX, bool NOISE>
+__global__ void __launch_bounds__(128) pushing_reset_kernel(const __grid_constant__ PushArgs a) {
+    __shared__ Tables tb;
+    load_tables(tb, a.L);
+    __syncthreads();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.B) return;
+    if (a.reset_mask && !a.reset_mask[e]) return;
+    const uint32_t env_global = a.env_base + (uint32_t)e;
+    PushState s;
+    const uint32_t event = a.rng[e];
+    bool wc;
+    const bool failed = push_reset_one<BOX, NOISE>(a, tb, s, env_global, event, a.inject_start, a.inject_goal, a.inject_object, e, wc);
+    double obs[6];
+    double2 ag;
+    bool reached;
+    push_observe<NOISE>(a, s, env_global, event, obs, ag, reached);
+    push_store_obs(a, e, a.out.observation, a.out.achieved_goal, a.out.desired_goal, obs, ag, s.goal);
+    push_store(a, e, s);
+    float r;
+    bool t, succ;
+    push_reward(reached, wc, r, t, succ);
+    if (a.out.is_success) a.out.is_success[e] = succ;
+    if (a.out.mover_collision) a.out.mover_collision[e] = 0;
+    if (a.out.wall_collision) a.out.wall_collision[e] = wc;
+    a.rng[e] = event + 1u;
+    a.elapsed[e] = 0;
+    a.ep_return[e] = 0.f;
+    if (a.needs_reset) a.needs_reset[e] = 0;
+    if (failed) atomicAdd(a.fail_count, 1u);
+}
 
 }  // namespace gpr

@@ -161,7 +161,9 @@ class BatchedCore:
         """The same step called with HOST buffers (``gpr_step_host``): NumPy action in, NumPy results out."""
         a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.num_envs, self.action_dim)
         if self._host is None:
-            self._host = {k: np.zeros(tuple(v.shape), dtype=np.float32 if v.dtype == torch.float32 else np.uint8) for k, v in self.buf.items()}
+            # page-locked result arrays (torch owns the memory, NumPy views it): the copy engine writes them directly
+            self._host_pin = {k: torch.zeros(tuple(v.shape), dtype=v.dtype, pin_memory=True) for k, v in self.buf.items()}
+            self._host = {k: t.numpy() for k, t in self._host_pin.items()}
             self._host_out = GprOutputs()
             for name in _OUT_FIELDS:
                 setattr(self._host_out, name, self._host[name].ctypes.data if name in self._host else None)
