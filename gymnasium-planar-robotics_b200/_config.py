@@ -115,7 +115,7 @@ class GprState(ctypes.Structure):
         ('elapsed_steps', ctypes.c_void_p),
         ('rng_counter', ctypes.c_void_p),
         ('act', ctypes.c_void_p),
-        ('mover_yaw', ctypes.c_void_p),
+        ('mover_rot', ctypes.c_void_p),
         ('object_pos', ctypes.c_void_p),
         ('object_vel', ctypes.c_void_p),
     ]
@@ -422,12 +422,17 @@ def pushing_config(
     cycle_time: float = 0.001,
     max_episode_steps: int = 50,
     autoreset_mode='same_step',
-    max_reset_attempts: int = 100000,
+    max_reset_attempts: int = 4096,
     env_index_base: int = 0,
     seed: int = 0,
     contact_iterations: int = 8,
 ) -> tuple[GprConfig, dict[str, Any]]:
-    """kwargs of ``BenchmarkPushingEnv`` (pushing:154-169) -> ``gpr_config``."""
+    """kwargs of ``BenchmarkPushingEnv`` (pushing:154-169) -> ``gpr_config``.
+
+    ``max_reset_attempts`` caps the object-placement loop of pushing:392-407.  The reference loops without bound, and
+    NEVER terminates when the mover is drawn within a few millimetres of the layout centre (every point of the object box
+    [0.22, 0.44]^2 is then closer than ``min_mo_dist`` = 0.159 m; probability ~2e-4 per reset).  Here such a reset keeps
+    its last draw and is counted in ``gpr_reset_failures``."""
     del render_every_cycle, initial_mover_zpos
     _reject_out_of_scope({} if mover_params is None else mover_params, render_mode, False, use_mj_passive_viewer)
     cfg = GprConfig()

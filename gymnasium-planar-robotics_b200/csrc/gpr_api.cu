@@ -197,8 +197,7 @@ extern "C" int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_ha
     h->device = device;
     h->seed = cfg->seed;
     h->G = next_pow2(cfg->num_movers);
-    h->noise = cfg->std_noise[0] != 0.0 || cfg->std_noise[1] != 0.0 ||
-               (cfg->env_kind == GPR_ENV_PUSHING && cfg->object_noise_xy != 0.0);
+    h->noise = cfg->std_noise[0] != 0.0 || cfg->std_noise[1] != 0.0;  // (the object noise of push:565 has its own switch)
     const int N = cfg->num_movers, J = cfg->learn_jerk != 0;
     if (cfg->env_kind == GPR_ENV_PLANNING) {
         h->obs_dim = 2 * N * (1 + J);
@@ -416,29 +415,7 @@ static PushArgs push_args(const gpr_handle* h, const gpr_outputs* out) {
     a.sigma_v = c.std_noise[1];
     a.sigma_obj = c.object_noise_xy;
     a.L = layout_args(h);
-    // planar physics parameters (include/gpr_push_physics.h)
-    gpr_push_params& P = a.P;
-    P.dt = c.cycle_time;
-    P.mover_mass = c.mover_mass;
-    P.mover_hx = c.mover_half[0];
-    P.mover_hy = c.mover_half[1];
-    P.mover_inertia = c.mover_mass * ((2 * c.mover_half[0]) * (2 * c.mover_half[0]) + (2 * c.mover_half[1]) * (2 * c.mover_half[1])) / 12.0;
-    P.obj_mass = c.object_mass;
-    P.obj_h = c.object_half_xy;
-    P.obj_inertia = c.object_mass * (2 * (2 * c.object_half_xy) * (2 * c.object_half_xy)) / 12.0;
-    P.obj_damping = c.object_damping;
-    P.mu = c.friction;
-    P.gravity = c.gravity;
-    P.k_rot = c.imp_k_rot;
-    P.d_rot = 2.0 * std::sqrt(c.imp_k_rot * c.mover_mass);  // impedance_control.py:46-47
-    P.sol_B = 2.0 / (c.solimp[1] * c.solref[0]);
-    P.sol_K = 1.0 / (c.solimp[1] * c.solimp[1] * c.solref[0] * c.solref[0] * c.solref[1] * c.solref[1]);
-    P.imp_d0 = c.solimp[0];
-    P.imp_dw = c.solimp[1];
-    P.imp_width = c.solimp[2];
-    P.imp_mid = c.solimp[3];
-    P.imp_power = c.solimp[4];
-    P.iterations = c.contact_iterations;
+    gpr_push_params_from_config(&c, &a.P);  // planar physics parameters (include/gpr_push_physics.h)
     a.pos = h->pos;
     a.vel = h->vel;
     a.acc = h->acc;
@@ -657,7 +634,7 @@ static int copy_state(gpr_handle* h, const gpr_state* st, bool to_handle, cudaSt
         {h->elapsed, st->elapsed_steps, B * sizeof(int32_t)},
         {h->rng, st->rng_counter, B * sizeof(uint32_t)},
         {h->act, st->act, B * sizeof(double2)},
-        {h->mover_rot, st->mover_yaw, 3 * B * sizeof(double)},
+        {h->mover_rot, st->mover_rot, 3 * B * sizeof(double)},
         {h->obj_pos, st->object_pos, 4 * B * sizeof(double)},
         {h->obj_vel, st->object_vel, 3 * B * sizeof(double)},
     };

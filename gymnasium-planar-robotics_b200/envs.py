@@ -187,7 +187,7 @@ class BatchedCore:
             'rng_counter': z((B,), torch.int32),  # uint32 bit pattern
         }
         if self.kind != ENV_PLANNING:
-            st.update(act=z((B, 2)), mover_yaw=z((B, 2)), object_pos=z((B, 3)), object_vel=z((B, 3)))
+            st.update(act=z((B, 2)), mover_rot=z((B, 3)), object_pos=z((B, 4)), object_vel=z((B, 3)))
         return st
 
     def get_state(self) -> dict[str, torch.Tensor]:

@@ -164,9 +164,9 @@ typedef struct gpr_state {
     uint32_t* rng_counter;  /* [num_envs] number of step/reset events consumed so far (Philox counter word) */
     /* pushing only */
     double* act;         /* [num_envs, 2] jerk-mode integrator state (differs from qacc under contact) */
-    double* mover_yaw;   /* [num_envs, 2] yaw, yaw rate */
-    double* object_pos;  /* [num_envs, 3] x, y, yaw */
-    double* object_vel;  /* [num_envs, 3] */
+    double* mover_rot;   /* [num_envs, 3] cos(yaw), sin(yaw), yaw rate (orientation kept on the unit circle) */
+    double* object_pos;  /* [num_envs, 4] x, y, cos(yaw), sin(yaw) */
+    double* object_vel;  /* [num_envs, 3] vx, vy, yaw rate */
 } gpr_state;
 
 typedef struct gpr_handle gpr_handle;

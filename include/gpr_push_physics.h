@@ -32,6 +32,8 @@
 
 #include <math.h>
 
+#include "gpr.h"
+
 #if defined(__CUDACC__)
 #define GPR_PHD __host__ __device__ __forceinline__
 #else
@@ -48,6 +50,33 @@ typedef struct gpr_push_params {
     double imp_d0, imp_dw, imp_width, imp_mid, imp_power;
     int iterations;
 } gpr_push_params;
+
+/* Derived physics parameters from the config — ONE definition shared by the CUDA host code and the CPU oracle so both
+ * sides see bit-identical constants. */
+static inline void gpr_push_params_from_config(const gpr_config* c, gpr_push_params* P) {
+    const double lx = 2.0 * c->mover_half[0], ly = 2.0 * c->mover_half[1], lo = 2.0 * c->object_half_xy;
+    P->dt = c->cycle_time;
+    P->mover_mass = c->mover_mass;
+    P->mover_hx = c->mover_half[0];
+    P->mover_hy = c->mover_half[1];
+    P->mover_inertia = c->mover_mass * (lx * lx + ly * ly) / 12.0; /* box about its vertical axis */
+    P->obj_mass = c->object_mass;
+    P->obj_h = c->object_half_xy;
+    P->obj_inertia = c->object_mass * (lo * lo + lo * lo) / 12.0;
+    P->obj_damping = c->object_damping;
+    P->mu = c->friction;
+    P->gravity = c->gravity;
+    P->k_rot = c->imp_k_rot;
+    P->d_rot = 2.0 * sqrt(c->imp_k_rot * c->mover_mass); /* utils/impedance_control.py:46-47 */
+    P->sol_B = 2.0 / (c->solimp[1] * c->solref[0]);
+    P->sol_K = 1.0 / (c->solimp[1] * c->solimp[1] * c->solref[0] * c->solref[0] * c->solref[1] * c->solref[1]);
+    P->imp_d0 = c->solimp[0];
+    P->imp_dw = c->solimp[1];
+    P->imp_width = c->solimp[2];
+    P->imp_mid = c->solimp[3];
+    P->imp_power = c->solimp[4];
+    P->iterations = c->contact_iterations;
+}
 
 typedef struct gpr_body2 {
     double x, y, c, s;  /* position, (cos yaw, sin yaw) */

@@ -30,6 +30,7 @@
 
 #include "../include/gpr.h"
 #include "../include/gpr_rng.h"
+#include "../include/gpr_push_physics.h"
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -376,9 +377,9 @@ typedef struct gpro_state {
     uint8_t* needs_reset; /* NEXT_STEP autoreset bookkeeping */
     /* pushing only */
     double* act;        /* [B, 2] jerk integrator state */
-    double* mover_yaw;  /* [B, 2] yaw, yaw rate */
-    double* object_pos; /* [B, 3] x, y, yaw */
-    double* object_vel; /* [B, 3] */
+    double* mover_rot;  /* [B, 3] cos yaw, sin yaw, yaw rate */
+    double* object_pos; /* [B, 4] x, y, cos yaw, sin yaw */
+    double* object_vel; /* [B, 3] vx, vy, yaw rate */
 } gpro_state;
 
 typedef struct gpro_outputs {
@@ -753,6 +754,354 @@ void gpro_planning_step(const gpr_config* c, uint64_t seed, gpro_state* s, const
         write_obs(c, obs_dim, goal_dim, o, ag, dg, e, out->observation, out->achieved_goal, out->desired_goal);
     }
     (void)nthreads;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* BenchmarkPushingEnv (push = envs/manipulation/benchmark_pushing_env.py)                                              */
+/*                                                                                                                      */
+/* Everything AROUND mj_step is a restatement of the reference (control limiting push:419-455, wall check                */
+/* basic:1888-1894, observation push:529-576, reward / terminated / info push:457-527, 578-608, reset push:373-417).      */
+/* mj_step itself (mover-object contact, object-ground friction, yaw impedance) is the planar specification in          */
+/* include/gpr_push_physics.h — MuJoCo is not available, PARITY UNPINNED for that part.                 */
+/* ------------------------------------------------------------------------------------------------------------------ */
+typedef struct push_env {
+    gpr_body2 M, O;
+    double acc[2], act[2], goal[2];
+} push_env;
+
+static void push_env_load(const gpro_state* s, int64_t e, push_env* x) {
+    x->M.x = s->pos[2 * e];
+    x->M.y = s->pos[2 * e + 1];
+    x->M.vx = s->vel[2 * e];
+    x->M.vy = s->vel[2 * e + 1];
+    x->M.c = s->mover_rot[3 * e];
+    x->M.s = s->mover_rot[3 * e + 1];
+    x->M.w = s->mover_rot[3 * e + 2];
+    x->O.x = s->object_pos[4 * e];
+    x->O.y = s->object_pos[4 * e + 1];
+    x->O.c = s->object_pos[4 * e + 2];
+    x->O.s = s->object_pos[4 * e + 3];
+    x->O.vx = s->object_vel[3 * e];
+    x->O.vy = s->object_vel[3 * e + 1];
+    x->O.w = s->object_vel[3 * e + 2];
+    for (int k = 0; k < 2; ++k) {
+        x->acc[k] = s->acc[2 * e + k];
+        x->act[k] = s->act[2 * e + k];
+        x->goal[k] = s->goal[2 * e + k];
+    }
+}
+
+static void push_env_store(gpro_state* s, int64_t e, const push_env* x) {
+    s->pos[2 * e] = x->M.x;
+    s->pos[2 * e + 1] = x->M.y;
+    s->vel[2 * e] = x->M.vx;
+    s->vel[2 * e + 1] = x->M.vy;
+    s->mover_rot[3 * e] = x->M.c;
+    s->mover_rot[3 * e + 1] = x->M.s;
+    s->mover_rot[3 * e + 2] = x->M.w;
+    s->object_pos[4 * e] = x->O.x;
+    s->object_pos[4 * e + 1] = x->O.y;
+    s->object_pos[4 * e + 2] = x->O.c;
+    s->object_pos[4 * e + 3] = x->O.s;
+    s->object_vel[3 * e] = x->O.vx;
+    s->object_vel[3 * e + 1] = x->O.vy;
+    s->object_vel[3 * e + 2] = x->O.w;
+    for (int k = 0; k < 2; ++k) {
+        s->acc[2 * e + k] = x->acc[k];
+        s->act[2 * e + k] = x->act[k];
+        s->goal[2 * e + k] = x->goal[k];
+    }
+}
+
+/* basic:1888-1894 / 1799-1801: check_wall_collision on the noisy qpos of the single mover.
+ * nxy: position noise (2 normals) or NULL; qstream: RNG stream of the quaternion noise (box shape only). */
+static int push_wall_collision(const gpr_config* c, const gpr_body2* M, int safety, const float* nxy, uint64_t seed,
+                               uint32_t env_global, uint32_t event, uint32_t qstream) {
+    const double sp = c->std_noise[0];
+    const int noisy = (sp != 0.0 || c->std_noise[1] != 0.0) && nxy != NULL;
+    double qpos[7] = {M->x, M->y, 0.0, 1.0, 0.0, 0.0, 0.0};
+    if (noisy) {
+        qpos[0] = M->x + (double)nxy[0] * sp;
+        qpos[1] = M->y + (double)nxy[1] * sp;
+    }
+    if (c->c_shape == GPR_SHAPE_BOX) {
+        /* the mover's yaw as MuJoCo's quaternion (cos(yaw/2), 0, 0, sin(yaw/2)), by the half-angle identities */
+        const double ch = sqrt(0.5 * (1.0 + M->c));
+        const double sh = M->s / (2.0 * ch);
+        qpos[3] = ch;
+        qpos[6] = sh;
+        if (noisy) { /* basic:828: noise on all quaternion components */
+            float q[4];
+            gpr_normal4(seed, env_global, event, qstream, 0u, q);
+            qpos[3] = qpos[3] + (double)q[0] * sp;
+            qpos[4] = (double)q[1] * sp;
+            qpos[5] = (double)q[2] * sp;
+            qpos[6] = qpos[6] + (double)q[3] * sp;
+        }
+    }
+    double cw[2] = {c->c_wall[safety][0][0], c->c_wall[safety][0][1]};
+    int32_t valid;
+    gpro_qpos_is_valid(c, 1, qpos, cw, &valid);
+    return !valid;
+}
+
+/* push:529-576 _get_obs: [pos, vel, (acc)] of the mover; achieved = object xy + N(0, 1e-5) (push:565) */
+static void pushing_obs(const gpr_config* c, const push_env* x, uint64_t seed, uint32_t env_global, uint32_t event,
+                        double* observation, double* achieved, double* desired) {
+    double px = x->M.x, py = x->M.y, vx = x->M.vx, vy = x->M.vy;
+    if (c->std_noise[0] != 0.0 || c->std_noise[1] != 0.0) {
+        float n4[4];
+        gpr_normal4(seed, env_global, event, GPR_RNG_OBS, 0u, n4);
+        px = px + (double)n4[0] * c->std_noise[0];
+        py = py + (double)n4[1] * c->std_noise[0];
+        vx = vx + (double)n4[2] * c->std_noise[1];
+        vy = vy + (double)n4[3] * c->std_noise[1];
+    }
+    observation[0] = px;
+    observation[1] = py;
+    observation[2] = vx;
+    observation[3] = vy;
+    if (c->learn_jerk) { /* push:556: qacc without noise */
+        observation[4] = x->acc[0];
+        observation[5] = x->acc[1];
+    }
+    achieved[0] = x->O.x;
+    achieved[1] = x->O.y;
+    if (c->object_noise_xy != 0.0) {
+        float k4[4];
+        gpr_normal4(seed, env_global, event, GPR_RNG_OBJECT, 0u, k4);
+        achieved[0] = achieved[0] + (double)k4[0] * c->object_noise_xy;
+        achieved[1] = achieved[1] + (double)k4[1] * c->object_noise_xy;
+    }
+    desired[0] = x->goal[0];
+    desired[1] = x->goal[1];
+}
+
+/* push:373-417 _reset_callback + push:353-371 reload_model + basic:1797-1801.  Returns 1 if the object loop ran out. */
+static int pushing_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_global, uint32_t event, push_env* x,
+                             const double* inj_start, const double* inj_goal, const double* inj_object,
+                             int* wall_collision) {
+    double ux, uy;
+    int failed = 0;
+    if (inj_start) {
+        x->M.x = inj_start[0];
+        x->M.y = inj_start[1];
+    } else { /* push:387-389 */
+        gpr_sample_xy(seed, env_global, event, GPR_RNG_RESET_SAMPLE, 0u, 0u, 0u, &ux, &uy);
+        x->M.x = c->min_xy_pos[0] + (c->max_xy_pos[0] - c->min_xy_pos[0]) * ux;
+        x->M.y = c->min_xy_pos[1] + (c->max_xy_pos[1] - c->min_xy_pos[1]) * uy;
+    }
+    if (inj_object) {
+        x->O.x = inj_object[0];
+        x->O.y = inj_object[1];
+    } else { /* push:392-407: redraw the object until it is farther than min_mo_dist from the mover (strict '>') */
+        const int cap = c->max_reset_attempts > 0 ? c->max_reset_attempts : 1;
+        int ok = 0;
+        for (int t = 0; t < cap && !ok; ++t) {
+            gpr_sample_xy(seed, env_global, event, GPR_RNG_RESET_OBJECT, 0u, (uint32_t)t, 0u, &ux, &uy);
+            x->O.x = c->object_min_xy_pos[0] + (c->object_max_xy_pos[0] - c->object_min_xy_pos[0]) * ux;
+            x->O.y = c->object_min_xy_pos[1] + (c->object_max_xy_pos[1] - c->object_min_xy_pos[1]) * uy;
+            double dx = x->O.x - x->M.x, dy = x->O.y - x->M.y;
+            ok = sqrt(dx * dx + dy * dy) > c->min_mo_dist; /* push:407 */
+        }
+        failed = !ok;
+    }
+    if (inj_goal) {
+        x->goal[0] = inj_goal[0];
+        x->goal[1] = inj_goal[1];
+    } else { /* push:411-413 */
+        gpr_sample_xy(seed, env_global, event, GPR_RNG_RESET_OBJECT, 1u, 0u, 0u, &ux, &uy);
+        x->goal[0] = c->object_min_xy_pos[0] + (c->object_max_xy_pos[0] - c->object_min_xy_pos[0]) * ux;
+        x->goal[1] = c->object_min_xy_pos[1] + (c->object_max_xy_pos[1] - c->object_min_xy_pos[1]) * uy;
+    }
+    /* reload_model (push:353-371): fresh MjData — everything at rest, identity orientations */
+    x->M.vx = x->M.vy = x->M.w = 0.0;
+    x->M.c = 1.0;
+    x->M.s = 0.0;
+    x->O.vx = x->O.vy = x->O.w = 0.0;
+    x->O.c = 1.0;
+    x->O.s = 0.0;
+    x->acc[0] = x->acc[1] = x->act[0] = x->act[1] = 0.0;
+    /* basic:1799-1801: wall check WITH the safety offset on noisy qpos */
+    float n4[4] = {0.f, 0.f, 0.f, 0.f};
+    const int noisy = c->std_noise[0] != 0.0 || c->std_noise[1] != 0.0;
+    if (noisy) gpr_normal4(seed, env_global, event, GPR_RNG_RESET_CHECK, 0u, n4);
+    *wall_collision = push_wall_collision(c, &x->M, 1, noisy ? n4 : NULL, seed, env_global, event, GPR_RNG_RESET_CHECK_WQUAT);
+    return failed;
+}
+
+/* basic:1835-1950 step for one pushing env. */
+static void pushing_step_one(const gpr_config* c, const gpr_push_params* P, uint64_t seed, uint32_t env_global,
+                             uint32_t event, push_env* x, const float* action, int* wall_collision) {
+    const double dt = c->cycle_time;
+    const double lim = c->learn_jerk ? c->j_max : c->a_max;
+    const int noisy = c->std_noise[0] != 0.0 || c->std_noise[1] != 0.0;
+    double u[2];
+    for (int k = 0; k < 2; ++k) { /* basic:1869-1873 */
+        double a = (double)action[k];
+        u[k] = a < -lim ? -lim : (a > lim ? lim : a);
+    }
+    int wc = 0;
+    for (int cyc = 0; cyc < c->num_cycles; ++cyc) { /* basic:1879 */
+        float n4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (noisy) gpr_normal4(seed, env_global, event, (uint32_t)cyc * 4u + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
+        /* push:419-455 _mujoco_step_callback */
+        double vel[2] = {x->M.vx, x->M.vy};
+        if (noisy) { /* push:428 get_mover_qvel(add_noise=True) */
+            vel[0] = vel[0] + (double)n4[0] * c->std_noise[1];
+            vel[1] = vel[1] + (double)n4[1] * c->std_noise[1];
+        }
+        double ctrl[2];
+        if (c->learn_jerk) {
+            double next_acc_tmp[2], next_jerk[2], tmpv[2], next_acc[2];
+            gpro_ensure_max_dyn_val(x->acc, c->a_max, u, dt, next_acc_tmp, next_jerk); /* push:432, acc = the real qacc */
+            gpro_ensure_max_dyn_val(vel, c->v_max, next_acc_tmp, dt, tmpv, next_acc);  /* push:435 */
+            if (next_acc_tmp[0] != next_acc[0] || next_acc_tmp[1] != next_acc[1]) {    /* push:436 */
+                next_jerk[0] = (next_acc[0] - x->acc[0]) / dt;
+                next_jerk[1] = (next_acc[1] - x->acc[1]) / dt;
+            }
+            /* integrator actuator, actearly (push:305-311): act += dt*ctrl; the actuator force uses the new act */
+            x->act[0] = x->act[0] + dt * next_jerk[0];
+            x->act[1] = x->act[1] + dt * next_jerk[1];
+            ctrl[0] = x->act[0];
+            ctrl[1] = x->act[1];
+        } else {
+            double tmpv[2];
+            gpro_ensure_max_dyn_val(vel, c->v_max, u, dt, tmpv, ctrl); /* push:440 */
+        }
+        /* mj_step (basic:1882): planar substitute, see include/gpr_push_physics.h */
+        double qax, qay;
+        gpr_push_substep(P, &x->M, &x->O, ctrl[0], ctrl[1], &qax, &qay);
+        x->acc[0] = qax;
+        x->acc[1] = qay;
+        /* basic:1888-1894 wall check; a single mover has no mover-mover check (push:592 asserts no mover collision) */
+        wc = push_wall_collision(c, &x->M, 0, noisy ? n4 + 2 : NULL, seed, env_global, event,
+                                 (uint32_t)cyc * 4u + GPR_RNG_BLOCK_WALL_QUAT);
+        if (wc) break; /* basic:1904 */
+    }
+    *wall_collision = wc;
+}
+
+void gpro_pushing_reset(const gpr_config* c, uint64_t seed, gpro_state* s, const uint8_t* mask,
+                        const double* inject_start, const double* inject_goal, const double* inject_object,
+                        gpro_outputs* out, int nthreads) {
+    const int B = c->num_envs;
+    const int obs_dim = 2 * (2 + (c->learn_jerk != 0)), goal_dim = 2;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1) schedule(static)
+#endif
+    for (int64_t e = 0; e < B; ++e) {
+        if (mask && !mask[e]) continue;
+        push_env x;
+        memset(&x, 0, sizeof(x));
+        uint32_t env_global = (uint32_t)(c->env_index_base + e);
+        uint32_t event = s->rng_counter[e];
+        int wc;
+        int failed = pushing_reset_one(c, seed, env_global, event, &x, inject_start ? inject_start + 2 * e : NULL,
+                                       inject_goal ? inject_goal + 2 * e : NULL,
+                                       inject_object ? inject_object + 2 * e : NULL, &wc);
+        double o[6], ag[2], dg[2];
+        pushing_obs(c, &x, seed, env_global, event, o, ag, dg);
+        push_env_store(s, e, &x);
+        s->rng_counter[e] = event + 1u;
+        s->elapsed_steps[e] = 0;
+        if (s->needs_reset) s->needs_reset[e] = 0;
+        if (out) {
+            write_obs(c, obs_dim, goal_dim, o, ag, dg, e, out->observation, out->achieved_goal, out->desired_goal);
+            double r;
+            int term, succ;
+            gpro_pushing_reward(c, ag, dg, wc, &r, &term, &succ);
+            if (out->is_success) out->is_success[e] = (uint8_t)succ;
+            if (out->mover_collision) out->mover_collision[e] = 0;
+            if (out->wall_collision) out->wall_collision[e] = (uint8_t)wc;
+            if (out->reset_failed) out->reset_failed[e] = (uint8_t)failed;
+        }
+    }
+    (void)nthreads;
+}
+
+void gpro_pushing_step(const gpr_config* c, uint64_t seed, gpro_state* s, const float* action, gpro_outputs* out,
+                       int nthreads) {
+    const int B = c->num_envs;
+    const int obs_dim = 2 * (2 + (c->learn_jerk != 0)), goal_dim = 2;
+    gpr_push_params P;
+    gpr_push_params_from_config(c, &P);
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1) schedule(static)
+#endif
+    for (int64_t e = 0; e < B; ++e) {
+        push_env x;
+        push_env_load(s, e, &x);
+        uint32_t env_global = (uint32_t)(c->env_index_base + e);
+        double o[6] = {0, 0, 0, 0, 0, 0}, ag[2], dg[2];
+        int wc = 0;
+        if (c->autoreset_mode == GPR_AUTORESET_NEXT_STEP && s->needs_reset && s->needs_reset[e]) {
+            uint32_t event = s->rng_counter[e];
+            pushing_reset_one(c, seed, env_global, event, &x, NULL, NULL, NULL, &wc);
+            pushing_obs(c, &x, seed, env_global, event, o, ag, dg);
+            push_env_store(s, e, &x);
+            s->rng_counter[e] = event + 1u;
+            s->elapsed_steps[e] = 0;
+            s->needs_reset[e] = 0;
+            write_obs(c, obs_dim, goal_dim, o, ag, dg, e, out->observation, out->achieved_goal, out->desired_goal);
+            double r;
+            int term, succ;
+            gpro_pushing_reward(c, ag, dg, wc, &r, &term, &succ);
+            if (out->reward) out->reward[e] = 0.0;
+            if (out->terminated) out->terminated[e] = 0;
+            if (out->truncated) out->truncated[e] = 0;
+            if (out->is_success) out->is_success[e] = (uint8_t)succ;
+            if (out->mover_collision) out->mover_collision[e] = 0;
+            if (out->wall_collision) out->wall_collision[e] = (uint8_t)wc;
+            continue;
+        }
+        uint32_t event = s->rng_counter[e];
+        pushing_step_one(c, &P, seed, env_global, event, &x, action + 2 * e, &wc);
+        pushing_obs(c, &x, seed, env_global, event, o, ag, dg);
+        s->rng_counter[e] = event + 1u;
+        double r;
+        int term, succ;
+        gpro_pushing_reward(c, ag, dg, wc, &r, &term, &succ);
+        int steps = s->elapsed_steps[e] + 1;
+        s->elapsed_steps[e] = steps;
+        int trunc = (c->max_episode_steps > 0) && (steps >= c->max_episode_steps);
+        if (out->reward) out->reward[e] = r;
+        if (out->terminated) out->terminated[e] = (uint8_t)term;
+        if (out->truncated) out->truncated[e] = (uint8_t)trunc;
+        if (out->is_success) out->is_success[e] = (uint8_t)succ;
+        if (out->mover_collision) out->mover_collision[e] = 0;
+        if (out->wall_collision) out->wall_collision[e] = (uint8_t)wc;
+        const int done = term || trunc;
+        if (done && c->autoreset_mode == GPR_AUTORESET_SAME_STEP) {
+            write_obs(c, obs_dim, goal_dim, o, ag, dg, e, out->final_observation, out->final_achieved_goal,
+                      out->final_desired_goal);
+            uint32_t ev2 = s->rng_counter[e];
+            int wc2;
+            int failed = pushing_reset_one(c, seed, env_global, ev2, &x, NULL, NULL, NULL, &wc2);
+            pushing_obs(c, &x, seed, env_global, ev2, o, ag, dg);
+            s->rng_counter[e] = ev2 + 1u;
+            s->elapsed_steps[e] = 0;
+            if (out->reset_failed) out->reset_failed[e] = (uint8_t)failed;
+        } else if (done && c->autoreset_mode == GPR_AUTORESET_NEXT_STEP && s->needs_reset) {
+            s->needs_reset[e] = 1;
+        }
+        push_env_store(s, e, &x);
+        write_obs(c, obs_dim, goal_dim, o, ag, dg, e, out->observation, out->achieved_goal, out->desired_goal);
+    }
+    (void)nthreads;
+}
+
+/* one substep of the planar push physics on explicit bodies (property tests of the specification) */
+int gpro_push_substep(const gpr_config* c, double* mover7, double* object7, double ux, double uy, double* qacc) {
+    gpr_push_params P;
+    gpr_push_params_from_config(c, &P);
+    gpr_body2 M = {mover7[0], mover7[1], mover7[2], mover7[3], mover7[4], mover7[5], mover7[6]};
+    gpr_body2 O = {object7[0], object7[1], object7[2], object7[3], object7[4], object7[5], object7[6]};
+    int nc = gpr_push_substep(&P, &M, &O, ux, uy, &qacc[0], &qacc[1]);
+    double m[7] = {M.x, M.y, M.c, M.s, M.vx, M.vy, M.w}, o[7] = {O.x, O.y, O.c, O.s, O.vx, O.vy, O.w};
+    memcpy(mover7, m, sizeof(m));
+    memcpy(object7, o, sizeof(o));
+    return nc;
 }
 
 /* HER relabelling on float32 goals (what gpr_compute_reward sees): goals are promoted to float64 first. */

@@ -21,7 +21,7 @@ def build(force: bool = False) -> str:
     """Compile the C restatement (oracle/Makefile). Building the checker is not using it."""
     if force or not os.path.exists(_SO) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
-        for f in ('gpr_oracle.c', '../include/gpr.h', '../include/gpr_rng.h')
+        for f in ('gpr_oracle.c', '../include/gpr.h', '../include/gpr_rng.h', '../include/gpr_push_physics.h')
     ):
         subprocess.run(['make', '-C', _HERE, '-s'] + (['-B'] if force else []), check=True)
     return _SO
@@ -57,7 +57,7 @@ class OState(ctypes.Structure):
         ('rng_counter', ctypes.c_void_p),
         ('needs_reset', ctypes.c_void_p),
         ('act', ctypes.c_void_p),
-        ('mover_yaw', ctypes.c_void_p),
+        ('mover_rot', ctypes.c_void_p),
         ('object_pos', ctypes.c_void_p),
         ('object_vel', ctypes.c_void_p),
     ]
@@ -178,8 +178,8 @@ class OracleEnv:
         self.rng_counter = np.zeros(B, dtype=np.uint32)
         self.needs_reset = np.zeros(B, dtype=np.uint8)
         self.act = np.zeros((B, 2))
-        self.mover_yaw = np.zeros((B, 2))
-        self.object_pos = np.zeros((B, 3))
+        self.mover_rot = np.zeros((B, 3))
+        self.object_pos = np.zeros((B, 4))
         self.object_vel = np.zeros((B, 3))
         self._alloc_out()
 
