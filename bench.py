@@ -121,6 +121,14 @@ def make_cfg(wl, num_envs, env_index_base=0, **over):
     return fn(num_envs=num_envs, env_index_base=env_index_base, **kw)
 
 
+def host_threads() -> int:
+    """Host cores available to this process (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU baseline)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def time_oracle(wl, num_envs: int, steps: int, warmup: int, threads: int, seed: int = 0) -> float:
     """env-steps/s of the CPU oracle (float64 C restatement of the reference's algorithm) on `threads` host threads."""
     import gpr_oracle
@@ -145,9 +153,7 @@ def run_reference(args, wl):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    import gpr_oracle
-
-    threads = gpr_oracle.max_threads()
+    threads = host_threads()
     sample_envs = 4096  # bounded sample of the same workload: the per-env cost does not depend on the batch size
     v = time_oracle(wl, sample_envs, args.steps, max(args.warmup, 1), threads)
     cfg, d = make_cfg(wl, sample_envs)
@@ -231,7 +237,11 @@ def run_b200(args, wl):
     # ---- end to end through the host-buffer API (NumPy in / NumPy out), H2D + D2H inside the timed region
     lim = env.j_max if env.learn_jerk else env.a_max
     rng = np.random.default_rng(5 + rank)
-    hacts = [rng.uniform(-lim, lim, (B, env.core.action_dim)).astype(np.float32) for _ in range(4)]
+    hacts = []
+    for _ in range(4):  # page-locked host arrays (the contract's "pinned host memory"); filled on the host
+        buf = env.core.pinned_action_buffer()
+        buf[:] = rng.uniform(-lim, lim, (B, env.core.action_dim)).astype(np.float32)
+        hacts.append(buf)
     for i in range(3):
         env.step_host(hacts[i % 4])
     e2e_steps = max(10, args.steps // 4)
@@ -249,6 +259,19 @@ def run_b200(args, wl):
     d2h = int(sum(v.nbytes for v in env.core._host.values()))
     env.close()
 
+    # context number: the same workload without sensor noise (the reference tests' parity setting).  EVERY rank runs it:
+    # timed() holds barriers, so it must never sit inside rank-conditional code.
+    extra = {}
+    if not args.quick:
+        e0 = build(std_noise=0.0)
+        n0 = max(20, args.steps // 2)
+        ms0, _, _ = timed(e0, n0, 3)
+        t0 = torch.tensor([ms0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t0, op=dist.ReduceOp.MAX)
+        extra['value_no_noise'] = world * B * n0 / (float(t0.item()) * 1e-3)
+        e0.close()
+
     if rank == 0:
         N, J = int(env.cfg.num_movers), int(env.cfg.learn_jerk)
         abytes = algorithmic_bytes_per_env_step(wl['kind'], N, J)
@@ -263,19 +286,10 @@ def run_b200(args, wl):
                     traffic = json.load(f).get(args.workload)
             except Exception:
                 traffic = None
-        extra = {}
-        if not args.quick:
-            # context numbers: the same workload without sensor noise (the reference tests' parity setting)
-            e0 = build(std_noise=0.0)
-            ms0, _, _ = timed(e0, max(20, args.steps // 2), 3)
-            extra['value_no_noise'] = B * max(20, args.steps // 2) / (ms0 * 1e-3) * world
-            e0.close()
         # CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
         cpu = None
         if world == 1 and not args.no_cpu:
-            import gpr_oracle
-
-            threads = gpr_oracle.max_threads()
+            threads = host_threads()
             cb, cs = 2048, 10
             v1 = time_oracle(wl, cb, cs, 2, threads)
             cpu = {'value': v1, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
@@ -293,7 +307,7 @@ def run_b200(args, wl):
                          'note': 'issue-bound kernel (40-cycle float64 loop per env): see profiles/ for issue-slot and stall breakdown'},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-                    'api': 'BenchmarkPlanningVecEnv.step_host -> gpr_step_host (pinned staging, NumPy in/out)'},
+                    'api': f'{type(env).__name__}.step_host -> gpr_step_host: NumPy views of page-locked host arrays in/out, read and written in place by the kernels over PCIe (zero-copy), stream sync before returning'},
             'gpu_launches': int(launches), 'clocks': clocks,
             'episode_stats': stats, 'reset_failures': fails, 'wall_s_timed_region': wall,
         }

@@ -23,6 +23,8 @@ _ENV_NAMES = (
     'BenchmarkPlanningParallelEnv',
     'register_gymnasium_envs',
     'shard_range',
+    'all_reduce_stats',
+    'stats_dict',
 )
 
 

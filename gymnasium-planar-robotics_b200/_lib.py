@@ -12,7 +12,8 @@ import os
 from ._config import GPR_ABI_VERSION, GprConfig, GprOutputs, GprState
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libgpr_b200.so')
+# GPR_B200_LIB: path of an alternative build of the same library (kernel tuning experiments); never a fallback
+LIB_PATH = os.environ.get('GPR_B200_LIB') or os.path.join(_HERE, 'csrc', 'libgpr_b200.so')
 
 # every symbol include/gpr.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = (

@@ -346,8 +346,14 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
             const double mf = a.pair_mgf[nz];
             a.pair_lo2f[s][nz] = (t - mf) > 0.0 ? (float)((t - mf) * (t - mf)) : -1.f;
             a.pair_hi2f[s][nz] = (float)((t + mf) * (t + mf));
+            a.pair_thif[s][nz] = (float)((t + mf) * 1.000001);
         }
     }
+    // box shape: the quaternion noise (1 + n0*s, n1*s, n2*s, n3*s), |n| <= 5.77, rotates the rectangle by at most
+    // |sin| <= 2*|qz|/|q|^2 < 14*s; the float32 wall screen widens its bounding rectangle by that much (s >= 5e-3 is
+    // too large for the bound: a huge extent then makes the screen defer to the exact test every time)
+    a.rot_extf = !h->noise ? 0.f : (c.std_noise[0] < 5e-3 ? (float)(14.0 * c.std_noise[0]) : 1e3f);
+    a.inv_dtf = (float)((1.0 / c.cycle_time) * (1.0 - 1e-6));
     a.sigma_p = c.std_noise[0];
     a.sigma_v = c.std_noise[1];
     a.L = layout_args(h);
@@ -549,40 +555,50 @@ static void** out_slot(gpr_outputs* o, int k) {
     return slots[k];
 }
 
-static bool is_pinned(const void* p) {
+// Page-locked host memory (torch pinned tensors, cudaHostAlloc / cudaHostRegister'ed arrays) is mapped into the device's
+// address space under unified addressing: returns the device alias of `p`, or NULL for pageable memory.
+static void* device_alias(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
-        return false;
+        return nullptr;
     }
-    return at.type == cudaMemoryTypeHost;
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
-// device staging -> host results.  Page-locked destinations (e.g. torch pinned tensors / cudaHostRegister'ed arrays) are
-// written by the copy engine directly; pageable ones go through the handle's pinned mirror and one memcpy.
-static int copy_back(gpr_handle* h, const StageLayout& L, const gpr_outputs* host_out) {
+// Where the kernels write each result of a *_host call:
+//   page-locked destination -> the kernels store straight into it through its device alias (zero-copy: the stores of
+//                              finished CTAs cross PCIe while other CTAs still compute; no copy is enqueued at all)
+//   pageable destination    -> device staging, then one async copy into the handle's pinned mirror and a memcpy
+struct HostRoute {
+    gpr_outputs dev;   // pointers handed to the kernels
+    bool staged[12];   // field k goes through d_stage / h_stage
+};
+
+static HostRoute route_outputs(gpr_handle* h, const StageLayout& L, const gpr_outputs* host_out) {
+    HostRoute r;
     gpr_outputs ho = *host_out;
-    char* hs = (char*)h->h_stage;
-    char* ds = (char*)h->d_stage;
-    bool direct[12];
+    memset(&r, 0, sizeof(r));
     for (int k = 0; k < 12; ++k) {
         void* dst = *out_slot(&ho, k);
         if (!dst) continue;
-        direct[k] = is_pinned(dst);
-        CU(cudaMemcpyAsync(direct[k] ? dst : (void*)(hs + L.off[k]), ds + L.off[k], L.bytes[k], cudaMemcpyDeviceToHost, h->host_stream));
+        void* alias = device_alias(dst);
+        r.staged[k] = alias == nullptr;
+        *out_slot(&r.dev, k) = alias ? alias : (void*)((char*)h->d_stage + L.off[k]);
     }
-    CU(cudaStreamSynchronize(h->host_stream));
-    for (int k = 0; k < 12; ++k)
-        if (*out_slot(&ho, k) && !direct[k]) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
-    return GPR_OK;
+    return r;
 }
 
-static gpr_outputs device_outputs(gpr_handle* h, const StageLayout& L, const gpr_outputs* host_out) {
-    gpr_outputs ho = *host_out, dv;
-    memset(&dv, 0, sizeof(dv));
+static int finish_host_call(gpr_handle* h, const StageLayout& L, const HostRoute& r, const gpr_outputs* host_out) {
+    gpr_outputs ho = *host_out;
+    char* hs = (char*)h->h_stage;
+    char* ds = (char*)h->d_stage;
     for (int k = 0; k < 12; ++k)
-        if (*out_slot(&ho, k)) *out_slot(&dv, k) = (char*)h->d_stage + L.off[k];
-    return dv;
+        if (r.staged[k]) CU(cudaMemcpyAsync(hs + L.off[k], ds + L.off[k], L.bytes[k], cudaMemcpyDeviceToHost, h->host_stream));
+    CU(cudaStreamSynchronize(h->host_stream));  // results (zero-copy stores included) are visible to the host after this
+    for (int k = 0; k < 12; ++k)
+        if (r.staged[k]) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
+    return GPR_OK;
 }
 
 extern "C" int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out) {
@@ -592,16 +608,18 @@ extern "C" int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_
     if (rc != GPR_OK) return rc;
     const StageLayout L = stage_layout(h);
     const size_t abytes = (size_t)h->cfg.num_envs * h->action_dim * sizeof(float);
-    const void* src = host_action;
-    if (!is_pinned(host_action)) {  // pageable caller buffer: stage through the pinned mirror
+    // action: a page-locked caller buffer is read by the kernel in place (each lane loads its float2 once, coalesced);
+    // a pageable one is first copied into the pinned mirror, which the kernel then reads the same way
+    const float* dev_action = (const float*)device_alias(host_action);
+    if (!dev_action) {
         memcpy((char*)h->h_stage + L.off_action, host_action, abytes);
-        src = (char*)h->h_stage + L.off_action;
+        dev_action = (const float*)device_alias((char*)h->h_stage + L.off_action);
+        if (!dev_action) return fail(GPR_ERR_CUDA, "pinned staging buffer has no device alias");
     }
-    CU(cudaMemcpyAsync((char*)h->d_stage + L.off_action, src, abytes, cudaMemcpyHostToDevice, h->host_stream));
-    gpr_outputs dv = device_outputs(h, L, host_out);
-    rc = gpr_step(h, (const float*)((char*)h->d_stage + L.off_action), &dv, h->host_stream);
+    const HostRoute r = route_outputs(h, L, host_out);
+    rc = gpr_step(h, dev_action, &r.dev, h->host_stream);
     if (rc != GPR_OK) return rc;
-    return copy_back(h, L, host_out);
+    return finish_host_call(h, L, r, host_out);
 }
 
 extern "C" int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_outputs* host_out) {
@@ -610,10 +628,10 @@ extern "C" int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gp
     int rc = ensure_stage(h);
     if (rc != GPR_OK) return rc;
     const StageLayout L = stage_layout(h);
-    gpr_outputs dv = device_outputs(h, L, host_out);
-    rc = gpr_reset(h, nullptr, reseed, seed, nullptr, nullptr, nullptr, &dv, h->host_stream);
+    const HostRoute r = route_outputs(h, L, host_out);
+    rc = gpr_reset(h, nullptr, reseed, seed, nullptr, nullptr, nullptr, &r.dev, h->host_stream);
     if (rc != GPR_OK) return rc;
-    return copy_back(h, L, host_out);
+    return finish_host_call(h, L, r, host_out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -199,9 +199,10 @@ __device__ __forceinline__ void rect_vertices_axis(double px, double py, double 
 // ---- wall / tile-layout check (basic:459-788, one mover) -------------------------------------------------------------
 // Containing cells are found exactly: the guessed index and its two neighbours are each tested with the reference's
 // inclusive comparisons against the reference's float64 bounds (basic:507-512); the guess never decides anything.
+// (out of line on purpose: it is the rare exact fallback of the float32 screens, called from many places)
 template <bool BOX>
-__device__ __forceinline__ bool wall_valid(const Tables& tb, const LayoutArgs& L, double x, double y, double cs0,
-                                           const Rect& rect) {
+static __device__ __noinline__ bool wall_valid(const Tables& tb, const LayoutArgs& L, double x, double y, double cs0,
+                                               const Rect& rect) {
     int gi = __double2int_rd(dmul(x, L.inv_wx));
     int gj = __double2int_rd(dmul(y, L.inv_wy));
     gi = min(max(gi, 0), L.nx - 1);

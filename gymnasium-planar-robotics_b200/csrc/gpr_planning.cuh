@@ -45,6 +45,9 @@ struct PlanArgs {
     // fall back to the exact float64 evaluation otherwise
     float pair_lo2f[2][2], pair_hi2f[2][2];  // [safety][noisy] squared-distance bands (uniform_pairs)
     float pair_mgf[2];                       // [noisy] distance margin for per-mover radii
+    float pair_thif[2][2];                   // [safety][noisy] upper edge of the band as a distance (uniform_pairs)
+    float rot_extf;                          // box shape: bound on |sin| of the noise-induced rotation (0 without noise)
+    float inv_dtf;                           // 1 / cycle_time, rounded down (travel budget in velocity units)
     float goal_lo2f, goal_hi2f;              // min_goal_dist bands
     float minxf, minyf, spanxf, spanyf;      // spawn box as float
     LayoutArgs L;
@@ -104,10 +107,17 @@ __device__ __forceinline__ Lane<G> make_lane(const PlanArgs& a) {
 
 __device__ __forceinline__ double noisy(double x, float n, double sigma) { return dadd(x, dmul((double)n, sigma)); }
 
+// gpr_normal4 for the lazily generated noise: those sites are cold (a check only needs its noise inside a ~1e-4 m band),
+// so one out-of-line copy keeps the hot loops small (instruction cache) instead of ~150 inlined instructions per site
+static __device__ __noinline__ void normal4_cold(uint64_t seed, uint32_t env_global, uint32_t event, uint32_t stream,
+                                                 uint32_t lane, float (&out)[4]) {
+    gpr_normal4(seed, env_global, event, stream, lane, out);
+}
+
 // ---- circle pair check with the lazy-noise band (basic:392-409), warp-collective --------------------------------------
 //   NOISY: the positions carry the mover-check noise of (event, stream) — generated only inside the uncertainty band.
 template <int G, bool NOISY>
-__device__ __forceinline__ bool pair_circle(const PlanArgs& a, unsigned lane, int m, bool part, double x, double y,
+static __device__ __noinline__ bool pair_circle(const PlanArgs& a, unsigned lane, int m, bool part, double x, double y,
                                             double r, int safety, uint32_t env_global, uint32_t event, uint32_t stream) {
     bool hit = false;
     if (G == 1) return false;
@@ -142,10 +152,10 @@ __device__ __forceinline__ bool pair_circle(const PlanArgs& a, unsigned lane, in
                 double xi = x, yi = y, xj = ox, yj = oy;
                 if (NOISY) {
                     float k4[4];
-                    gpr_normal4(a.seed, env_global, event, stream, (uint32_t)m, k4);
+                    normal4_cold(a.seed, env_global, event, stream, (uint32_t)m, k4);
                     xi = noisy(x, k4[0], a.sigma_p);
                     yi = noisy(y, k4[1], a.sigma_p);
-                    gpr_normal4(a.seed, env_global, event, stream, (uint32_t)pm, k4);
+                    normal4_cold(a.seed, env_global, event, stream, (uint32_t)pm, k4);
                     xj = noisy(ox, k4[0], a.sigma_p);
                     yj = noisy(oy, k4[1], a.sigma_p);
                 }
@@ -157,19 +167,39 @@ __device__ __forceinline__ bool pair_circle(const PlanArgs& a, unsigned lane, in
     return hit;
 }
 
-// Circle wall check in float32 for the tracked cell (gi, gj): returns 1 valid / 0 invalid when every comparison of
-// basic:507-558 has a margin larger than `wall_delta` (noise bound + float rounding slack) — the float32 signs are then
-// certain and equal the reference's float64 ones — and 2 when some comparison is too close to call (or the mover left
-// the tracked cell): the caller then runs the exact float64 check (with the noise, if any).
-__device__ __forceinline__ int wall_fast(const PlanArgs& a, const Tables& tb, double x, double y, float c, int gi, int gj) {
+// Wall check in float32 for the tracked cell (gi, gj) of an axis-aligned rectangle with half sizes (cx, cy) — the circle's
+// bounding square of basic:545-558, or a bounding rectangle of a box-shaped mover.  Returns 1 valid / 0 invalid when every
+// comparison of basic:507-558 has a margin larger than `wall_delta` (noise bound + float rounding slack) — the float32
+// signs are then certain and equal the reference's float64 ones — and 2 when some comparison is too close to call (or the
+// mover left the tracked cell): the caller then runs the exact float64 check (with the noise, if any).
+//
+// `clear` (>= 0): a certified L-infinity distance the centre may still travel without the check turning invalid.  The
+// check is "the rectangle [x-cx, x+cx] x [y-cy, y+cy] overlaps no missing cell" (sides_ok: an unsafe side needs that
+// neighbour, an unsafe corner also the diagonal one), so the clearance is the smallest L-infinity gap between the
+// rectangle and a missing cell of the 3x3 neighbourhood, capped by the gap to the ring beyond it (>= tile width - c),
+// minus wall_delta.  It does not depend on how close the verdict of THIS cycle was.
+__device__ __forceinline__ int wall_fast(const PlanArgs& a, const Tables& tb, double x, double y, float cx, float cy, int gi,
+                                         int gj, float& clear) {
     const float fx = (float)dsub(x, tb.xlo[gi]), fy = (float)dsub(y, tb.ylo[gj]);
-    const float wc = a.wxf - c, hc = a.wyf - c;
-    const float mx = fminf(fminf(fabsf(fx), fabsf(fx - c)), fminf(fabsf(fx - wc), fabsf(fx - a.wxf)));
-    const float my = fminf(fminf(fabsf(fy), fabsf(fy - c)), fminf(fabsf(fy - hc), fabsf(fy - a.wyf)));
+    const float wc = a.wxf - cx, hc = a.wyf - cy;
+    const float gw = fx - cx, ge = wc - fx, gs = fy - cy, gn = hc - fy;  // gaps to the W / E columns and S / N rows
     const bool inside = fx > 0.f && fx < a.wxf && fy > 0.f && fy < a.wyf;
-    if (!(fminf(mx, my) >= a.wall_delta) || !inside) return 2;
-    const uint32_t u = (fx < c ? 1u : 0u) | (fx > wc ? 2u : 0u) | (fy < c ? 4u : 0u) | (fy > hc ? 8u : 0u);
     const uint32_t code = tb.cell[gi * a.L.ny + gj];
+    float c = fminf(wc, hc);
+    c = (code & CELL_W) ? c : fminf(c, gw);
+    c = (code & CELL_E) ? c : fminf(c, ge);
+    c = (code & CELL_S) ? c : fminf(c, gs);
+    c = (code & CELL_N) ? c : fminf(c, gn);
+    c = (code & CELL_SW) ? c : fminf(c, fmaxf(gw, gs));
+    c = (code & CELL_NW) ? c : fminf(c, fmaxf(gw, gn));
+    c = (code & CELL_SE) ? c : fminf(c, fmaxf(ge, gs));
+    c = (code & CELL_NE) ? c : fminf(c, fmaxf(ge, gn));
+    clear = (inside && (code & CELL_T)) ? fmaxf(c - a.wall_delta, 0.f) : 0.f;
+    // certainty of this cycle's verdict: distance to the nearest comparison threshold of the tracked cell
+    const float mx = fminf(fminf(fabsf(fx), fabsf(gw)), fminf(fabsf(ge), fabsf(fx - a.wxf)));
+    const float my = fminf(fminf(fabsf(fy), fabsf(gs)), fminf(fabsf(gn), fabsf(fy - a.wyf)));
+    if (!(fminf(mx, my) >= a.wall_delta) || !inside) return 2;
+    const uint32_t u = (gw < 0.f ? 1u : 0u) | (ge < 0.f ? 2u : 0u) | (gs < 0.f ? 4u : 0u) | (gn < 0.f ? 8u : 0u);
     return ((code & CELL_3X3) || sides_ok(u, code)) ? 1 : 0;
 }
 
@@ -183,14 +213,17 @@ __device__ __forceinline__ void guess_cell(const PlanArgs& a, double x, double y
 template <bool NOISE>
 __device__ __forceinline__ bool wall_bad_circle(const PlanArgs& a, const Tables& tb, bool part, double x, double y,
                                                 double c, float cf, int& gi, int& gj, uint32_t env_global, uint32_t event,
-                                                uint32_t stream, int m, int w0, float (&n4)[4], bool& have) {
+                                                uint32_t stream, int m, int w0, float (&n4)[4], bool& have,
+                                                float& margin) {
+    margin = 3.0e38f;
     if (!part) return false;
-    const int f = wall_fast(a, tb, x, y, cf, gi, gj);
+    const int f = wall_fast(a, tb, x, y, cf, cf, gi, gj, margin);
     if (f != 2) return f == 0;
+    // (the clearance computed for the tracked cell stays valid: it is 0 whenever the mover is not strictly inside it)
     double wx = x, wy = y;
     if (NOISE) {
         if (!have) {
-            gpr_normal4(a.seed, env_global, event, stream, (uint32_t)m, n4);
+            normal4_cold(a.seed, env_global, event, stream, (uint32_t)m, n4);
             have = true;
         }
         wx = noisy(x, n4[w0], a.sigma_p);
@@ -204,10 +237,13 @@ __device__ __forceinline__ bool wall_bad_circle(const PlanArgs& a, const Tables&
 // Circle pair check with a float32 prefilter (warp-collective).  xf/yf are this lane's float coordinates (1e30f when the
 // lane does not take part); a pair is decided in float32 when its squared distance is outside the band, and only if some
 // lane of the warp meets an undecided pair does the whole warp run the exact float64 check.
+// `margin`: min over the pairs this lane looked at of (distance - upper band edge), 0 when a pair was hit or undecided —
+// as long as the two movers of every pair have together travelled less than that, no pair can start to collide.
 template <int G, bool NOISY>
 __device__ __forceinline__ bool pair_circle_fast(const PlanArgs& a, unsigned lane, int m, bool part, double x, double y,
                                                  double r, int safety, uint32_t env_global, uint32_t event,
-                                                 uint32_t stream) {
+                                                 uint32_t stream, float& margin) {
+    margin = 3.0e38f;
     if (G == 1) return false;
     const float xf = part ? (float)x : 1e30f, yf = part ? (float)y : 1e30f;
     const float rf = (float)r;
@@ -217,25 +253,56 @@ __device__ __forceinline__ bool pair_circle_fast(const PlanArgs& a, unsigned lan
     for (int k = 1; k <= G / 2; ++k) {
         const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
         const float oxf = __shfl_sync(FULL, xf, src), oyf = __shfl_sync(FULL, yf, src);
-        float lo2, hi2;
+        float lo2, hi2, thi;
         if (a.uniform_pairs) {
             lo2 = a.pair_lo2f[safety][NOISY ? 1 : 0];
             hi2 = a.pair_hi2f[safety][NOISY ? 1 : 0];
+            thi = a.pair_thif[safety][NOISY ? 1 : 0];
         } else {
             const float t = rf + __shfl_sync(FULL, rf, src), mg = a.pair_mgf[NOISY ? 1 : 0];
             lo2 = t > mg ? (t - mg) * (t - mg) : -1.f;
             hi2 = (t + mg) * (t + mg);
+            thi = (t + mg) * 1.000001f;
         }
-        const bool mine = part && oxf < 1e29f && !(k == G / 2 && m >= G / 2);
+        const bool both = part && oxf < 1e29f;
+        const bool mine = both && !(k == G / 2 && m >= G / 2);
         const float dx = xf - oxf, dy = yf - oyf;
         const float d2 = dx * dx + dy * dy;
         if (mine) {
             if (d2 < lo2) hit = true;
             else if (!(d2 > hi2)) unc = true;
         }
+        if (both) margin = fminf(margin, fmaxf(sqrtf(d2) * 0.999999f - thi, 0.f));
     }
     if (__any_sync(FULL, unc)) hit = pair_circle<G, NOISY>(a, lane, m, part, x, y, r, safety, env_global, event, stream);
     return hit;
+}
+
+// Box shape: float32 bounding-circle screen of the mover-mover check (warp-collective).  Two rectangles whose centres are
+// farther apart than the sum of their half diagonals (+ noise bound + float slack) cannot intersect (geom:107-138), so such
+// a pair is a certain miss and `margin` says how much the two movers may still travel; `near` marks lanes with a pair the
+// screen cannot clear (the caller then runs the exact rectangle test for the warp).
+template <int G>
+__device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part, double x, double y, float diagf, float mg,
+                                                bool& near, float& margin) {
+    near = false;
+    margin = 3.0e38f;
+    if (G == 1) return;
+    const float xf = part ? (float)x : 1e30f, yf = part ? (float)y : 1e30f;
+    const unsigned base = lane & ~(unsigned)(G - 1);
+#pragma unroll
+    for (int k = 1; k <= G / 2; ++k) {
+        const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
+        const float oxf = __shfl_sync(FULL, xf, src), oyf = __shfl_sync(FULL, yf, src);
+        const float thi = (diagf + __shfl_sync(FULL, diagf, src) + mg) * 1.000001f;
+        const bool both = part && oxf < 1e29f;
+        const float dx = xf - oxf, dy = yf - oyf;
+        const float mgn = sqrtf(dx * dx + dy * dy) * 0.999999f - thi;
+        if (both) {
+            near = near || !(mgn > 0.f);
+            margin = fminf(margin, fmaxf(mgn, 0.f));
+        }
+    }
 }
 
 // One observation row (plan:536-573) + the per-env reductions the reward needs.
@@ -278,26 +345,95 @@ __device__ __forceinline__ void store_obs(const PlanArgs& a, const Lane<G>& ln, 
 // KIND 1: wall check with safety offset + pairwise distance >= min_goal_dist.
 // One environment (global index eg, RNG event ev), whole warp: on return EVERY lane holds, for mover m = lane % G, the
 // position of the first accepted attempt (or of the last attempt, with failed = true, if the cap was hit).
+// Phase 2 of sample_env (exact float64 confirmation of the attempts that survived the float32 screen; ~1% of them):
+// out of line, so the hot screening loop stays small.  Warp-collective.  Returns true (in every lane) when an attempt of
+// this Philox block round was accepted; `out` then holds, for mover m = lane % G, the position of the first accepted one.
 template <int G, bool BOX, int KIND>
-__device__ __forceinline__ void sample_env(const PlanArgs& a, const Tables& tb, unsigned lane, unsigned gmask_, uint32_t eg,
-                                           uint32_t ev, double2& out, bool& failed) {
-    constexpr int S = 32 / G;  // attempts tested per half-iteration
-    struct { unsigned lane, gmask; } ln = {lane, gmask_};
-    const int slot = (int)(lane / G);
+static __device__ __noinline__ bool sample_confirm(const PlanArgs& a, const Tables& tb, unsigned lane, unsigned gmask,
+                                                   int cap, uint32_t blk, gpr_u32x4 r, unsigned cand_bits,
+                                                   unsigned needx_bits, uint32_t eg, uint32_t ev, double2& out) {
     const int m = (int)(lane % G);
     const bool has_mover = m < a.N;
     const int mm = has_mover ? m : 0;
     const double cw0 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 0], cw1 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 1];
     const double cs0 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0], cs1 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
-    const float rf = (float)cs0, diagf = (float)cs0 + (float)cs1;  // box: |half diagonal| <= sx + sy
+    const unsigned base = lane & ~(unsigned)(G - 1);
+    double xs[2], ys[2];
+    unsigned okmask[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = 2 * (int)blk + h;
+        const bool cand = (cand_bits >> h) & 1u, needx = (needx_bits >> h) & 1u;
+        const double x = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform32(r.v[2 * h])));  // plan:377/405
+        const double y = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform32(r.v[2 * h + 1])));
+        xs[h] = x;
+        ys[h] = y;
+        const bool part = has_mover && t < cap && cand;
+        bool hit = false;
+        if (G > 1 && __any_sync(FULL, needx)) {
+            const bool px = part && needx;
+            if (KIND == 0) {
+                if (BOX) {
+                    Rect rm;
+                    rect_vertices_axis(x, y, cs0, cs1, rm);
+                    hit = pair_check<G, true>(lane, m, px, x, y, cs0, cs1, rm, false, 0.0);
+                } else {
+                    hit = pair_circle<G, false>(a, lane, m, px, x, y, cs0, 1, eg, ev, 0u);  // plan:381
+                }
+            } else {
+                // plan:408-413: any pair closer than min_goal_dist (strict '<') rejects
+#pragma unroll
+                for (int k = 1; k <= G / 2; ++k) {
+                    const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
+                    const double ox = __shfl_sync(FULL, x, src), oy = __shfl_sync(FULL, y, src);
+                    const bool opart = __shfl_sync(FULL, (int)px, src) != 0;
+                    const double dx = dsub(x, ox), dy = dsub(y, oy);
+                    if (px && opart && sqrt_lt(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_goal_dist)) hit = true;
+                }
+            }
+        }
+        const unsigned hitm = __ballot_sync(FULL, hit);
+        const bool alive_grp = cand && (hitm & gmask) == 0u;
+        bool bad = false;
+        if (alive_grp && part) {  // plan:379 / 406 wall check with safety offset
+            Rect rw;
+            if (BOX) rect_vertices_axis(x, y, cw0, cw1, rw);
+            bad = !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);
+        }
+        const unsigned badm = __ballot_sync(FULL, bad);
+        okmask[h] = __ballot_sync(FULL, alive_grp && (badm & gmask) == 0u && m == 0);
+    }
+    if (!(okmask[0] | okmask[1])) return false;
+    // sequential order is t = t0, t0+1, ...: slot-major, half-minor
+    const int s0 = okmask[0] ? (__ffs(okmask[0]) - 1) / G : 1 << 20;
+    const int s1 = okmask[1] ? (__ffs(okmask[1]) - 1) / G : 1 << 20;
+    const int hw = (2 * s0 <= 2 * s1 + 1) ? 0 : 1;
+    const int sw = hw == 0 ? s0 : s1;
+    const double wx = __shfl_sync(FULL, hw == 0 ? xs[0] : xs[1], sw * G + m);
+    const double wy = __shfl_sync(FULL, hw == 0 ? ys[0] : ys[1], sw * G + m);
+    out = make_double2(wx, wy);
+    return true;
+}
+
+template <int G, bool BOX, int KIND>
+__device__ __forceinline__ void sample_env(const PlanArgs& a, const Tables& tb, unsigned lane, unsigned gmask_, uint32_t eg,
+                                           uint32_t ev, double2& out, bool& failed) {
+    constexpr int S = 32 / G;  // attempts tested per half-iteration
+    const int slot = (int)(lane / G);
+    const int m = (int)(lane % G);
+    const bool has_mover = m < a.N;
+    const int mm = has_mover ? m : 0;
+    const float rf = (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0];
+    const float diagf = rf + (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];  // box: |half diagonal| <= sx + sy
     const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
     const unsigned base = lane & ~(unsigned)(G - 1);
     bool found = false;
+#pragma unroll 1
     for (int t0 = 0; t0 < cap && !found; t0 += 2 * S) {
         const uint32_t blk = (uint32_t)(t0 / 2 + slot);
         const gpr_u32x4 r = gpr_rng_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)KIND, (uint32_t)m);
         // ---- phase 1, float32: ~99% of the attempts die on a pair that is far inside the rejection band
-        bool cand[2], needx[2];
+        unsigned cand_bits = 0u, needx_bits = 0u;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int t = 2 * (int)blk + h;
@@ -336,66 +472,13 @@ __device__ __forceinline__ void sample_env(const PlanArgs& a, const Tables& tb, 
                 }
             }
             const unsigned rejm = __ballot_sync(FULL, rej), uncm = __ballot_sync(FULL, unc);
-            cand[h] = (rejm & ln.gmask) == 0u && t < cap;
-            needx[h] = cand[h] && (uncm & ln.gmask) != 0u;
+            const bool cand = (rejm & gmask_) == 0u && t < cap;
+            cand_bits |= cand ? (1u << h) : 0u;
+            needx_bits |= (cand && (uncm & gmask_) != 0u) ? (1u << h) : 0u;
         }
         // ---- phase 2, float64 (exact), only when some group of the warp still has a candidate
-        if (!__any_sync(FULL, cand[0] || cand[1])) continue;
-        double xs[2], ys[2];
-        unsigned okmask[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int t = 2 * (int)blk + h;
-            const double x = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform32(r.v[2 * h])));  // plan:377/405
-            const double y = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform32(r.v[2 * h + 1])));
-            xs[h] = x;
-            ys[h] = y;
-            const bool part = has_mover && t < cap && cand[h];
-            bool hit = false;
-            if (G > 1 && __any_sync(FULL, needx[h])) {
-                const bool px = part && needx[h];
-                if (KIND == 0) {
-                    if (BOX) {
-                        Rect rm;
-                        rect_vertices_axis(x, y, cs0, cs1, rm);
-                        hit = pair_check<G, true>(ln.lane, m, px, x, y, cs0, cs1, rm, false, 0.0);
-                    } else {
-                        hit = pair_circle<G, false>(a, ln.lane, m, px, x, y, cs0, 1, eg, ev, 0u);  // plan:381
-                    }
-                } else {
-                    // plan:408-413: any pair closer than min_goal_dist (strict '<') rejects
-#pragma unroll
-                    for (int k = 1; k <= G / 2; ++k) {
-                        const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
-                        const double ox = __shfl_sync(FULL, x, src), oy = __shfl_sync(FULL, y, src);
-                        const bool opart = __shfl_sync(FULL, (int)px, src) != 0;
-                        const double dx = dsub(x, ox), dy = dsub(y, oy);
-                        if (px && opart && sqrt_lt(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_goal_dist)) hit = true;
-                    }
-                }
-            }
-            const unsigned hitm = __ballot_sync(FULL, hit);
-            const bool alive_grp = cand[h] && (hitm & ln.gmask) == 0u;
-            bool bad = false;
-            if (alive_grp && part) {  // plan:379 / 406 wall check with safety offset
-                Rect rw;
-                if (BOX) rect_vertices_axis(x, y, cw0, cw1, rw);
-                bad = !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);
-            }
-            const unsigned badm = __ballot_sync(FULL, bad);
-            okmask[h] = __ballot_sync(FULL, alive_grp && (badm & ln.gmask) == 0u && m == 0);
-        }
-        if (okmask[0] | okmask[1]) {
-            // sequential order is t = t0, t0+1, ...: slot-major, half-minor
-            const int s0 = okmask[0] ? (__ffs(okmask[0]) - 1) / G : 1 << 20;
-            const int s1 = okmask[1] ? (__ffs(okmask[1]) - 1) / G : 1 << 20;
-            const int hw = (2 * s0 <= 2 * s1 + 1) ? 0 : 1;
-            const int sw = hw == 0 ? s0 : s1;
-            const double wx = __shfl_sync(FULL, hw == 0 ? xs[0] : xs[1], sw * G + m);
-            const double wy = __shfl_sync(FULL, hw == 0 ? ys[0] : ys[1], sw * G + m);
-            out = make_double2(wx, wy);
-            found = true;
-        }
+        if (!__any_sync(FULL, cand_bits != 0u)) continue;
+        found = sample_confirm<G, BOX, KIND>(a, tb, lane, gmask_, cap, blk, r, cand_bits, needx_bits, eg, ev, out);
     }
     if (!found) {
         // the reference would loop forever (plan:369); keep the last attempt's sample and report the failure
@@ -441,8 +524,9 @@ __device__ __forceinline__ void reset_checks(const PlanArgs& a, const Tables& tb
             guess_cell(a, p.x, p.y, gi, gj);
             float n4[4];
             bool have = false;
+            float mg_unused;
             bad = wall_bad_circle<NOISE>(a, tb, part, p.x, p.y, cw0, (float)cw0, gi, gj, ln.env_global, event,
-                                         GPR_RNG_RESET_CHECK, ln.m, 0, n4, have);
+                                         GPR_RNG_RESET_CHECK, ln.m, 0, n4, have, mg_unused);
         }
         // the mover-check noise of reset() lives in words 2,3 of the same block
         hit = false;
@@ -468,10 +552,10 @@ __device__ __forceinline__ void reset_checks(const PlanArgs& a, const Tables& tb
                         double xi = p.x, yi = p.y, xj = ox, yj = oy;
                         if (NOISE) {
                             float k4[4];
-                            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, k4);
+                            normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, k4);
                             xi = noisy(p.x, k4[2], a.sigma_p);
                             yi = noisy(p.y, k4[3], a.sigma_p);
-                            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)pm, k4);
+                            normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)pm, k4);
                             xj = noisy(ox, k4[2], a.sigma_p);
                             yj = noisy(oy, k4[3], a.sigma_p);
                         }
@@ -486,17 +570,17 @@ __device__ __forceinline__ void reset_checks(const PlanArgs& a, const Tables& tb
         Rect rw, rm;
         if (NOISE) {
             float n4[4];
-            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, n4);
+            normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, n4);
             wx = noisy(p.x, n4[0], a.sigma_p);
             wy = noisy(p.y, n4[1], a.sigma_p);
             mx = noisy(p.x, n4[2], a.sigma_p);
             my = noisy(p.y, n4[3], a.sigma_p);
             float q[4];
-            gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_WQUAT, (uint32_t)ln.m, q);
+            normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_WQUAT, (uint32_t)ln.m, q);
             rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
                           dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
             if (G > 1) {
-                gpr_normal4(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_MQUAT, (uint32_t)ln.m, q);
+                normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_MQUAT, (uint32_t)ln.m, q);
                 rect_vertices(mx, my, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
                               dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
             }
@@ -546,8 +630,15 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
     succ = all && !coll;
 }
 
+#ifndef GPR_STEP_MINB
+#define GPR_STEP_MINB 2
+#endif
+#ifndef GPR_AR_MINB
+#define GPR_AR_MINB 4
+#endif
+
 template <int G, bool BOX, bool NOISE>
-__global__ void __launch_bounds__(256) planning_step_kernel(const __grid_constant__ PlanArgs a) {
+__global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const __grid_constant__ PlanArgs a) {
     __shared__ Tables tb;
     load_tables(tb, a.L);
     __syncthreads();
@@ -579,97 +670,155 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const __grid_constan
     }
 
     // ------------------------------------------------------------------ the 40-cycle loop (basic:1879-1905)
+    // TEMPORAL COHERENCE.  A collision check leaves every mover with a certified clearance: the distance it may still
+    // travel before the wall check can turn invalid (wall_fast), and the distance the movers of its env may still travel
+    // before a pair can start to collide, noise included.  A mover moves dt*|v| <= 2 mm per cycle, so while its accumulated
+    // travel stays below a budget, the reference's check is known to report "no collision" and is not evaluated.  The wall
+    // check is lane-local and runs for the lanes whose wall budget is used up; the pair check is warp-collective and
+    // runs for the warp as soon as one of its envs has used up its pair budget.
     bool alive = ln.env_ok && !pending_reset;
     bool mc = false, wc = false;
     int gi = 0, gj = 0;  // tile cell under the mover, tracked across cycles (movement per cycle is ~mm)
-    if (!BOX) guess_cell(a, p.x, p.y, gi, gj);
-    for (int cyc = 0; cyc < a.num_cycles; ++cyc) {
-        if (!__any_sync(FULL, alive)) break;
+    guess_cell(a, p.x, p.y, gi, gj);
+    // bounding rectangle / circle used by the float32 screens of the box shape (planning movers never rotate: the only
+    // rotation is the sensor noise on the quaternion)
+    const float bxf = BOX ? (float)cw0 + a.rot_extf * (float)(cw0 + cw1) : cw0f;
+    const float byf = BOX ? (float)cw1 + a.rot_extf * (float)(cw0 + cw1) : cw0f;
+    const float diagf = BOX ? sqrtf((float)cm0 * (float)cm0 + (float)cm1 * (float)cm1) * 1.000001f : 0.f;
+    float travel = 0.f;                  // sum over cycles of an upper bound of |v|  (distance / dt)
+    float lim_w = -1.f, lim_p = -1.f;    // `travel` values up to which the wall / pair check is certified negative
+    bool any_alive = __any_sync(FULL, alive);
+    for (int cyc = 0; cyc < a.num_cycles && any_alive; ++cyc) {
         const uint32_t s0 = (uint32_t)cyc * 4u;
         const bool part = alive && ln.active;
         float n4[4] = {0.f, 0.f, 0.f, 0.f};
         bool have0 = false;  // block 0 of this cycle generated?
-        if (NOISE && BOX) {
-            gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
-            have0 = true;
-        }
         if (part) {
             // plan:420-450 _mujoco_step_callback; d = derivative entering the velocity clip (action or limited acc)
             double dxv = u.x, dyv = u.y, jx = 0.0, jy = 0.0;
             if (a.learn_jerk) ensure_max(acc.x, acc.y, a.a_max, a.a_max2_lo, u.x, u.y, a.dt, dxv, dyv, jx, jy);  // plan:434
-            double velx = v.x, vely = v.y;
-            if (NOISE) {
-                // the velocity noise (plan:430) can only matter if the un-noised |dt*d + v| is within its bound of v_max
-                const double tx = dadd(dmul(a.dt, dxv), v.x), ty = dadd(dmul(a.dt, dyv), v.y);
-                if (!(dadd(dmul(tx, tx), dmul(ty, ty)) < a.v_lazy2)) {
-                    if (!have0) {
-                        gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
+            // plan:437 / 442 on the noise-free velocity first: below v_lazy2 neither the clip nor the velocity noise
+            // (plan:430) can change anything and ensure_max_dyn_val passes its inputs through
+            const double tx = dadd(dmul(a.dt, dxv), v.x), ty = dadd(dmul(a.dt, dyv), v.y);
+            const bool free_run = dadd(dmul(tx, tx), dmul(ty, ty)) < (NOISE ? a.v_lazy2 : a.v_max2_lo);
+            if (free_run && !a.learn_jerk) {
+                acc.x = dxv;  // dyntype none, gain = mass (plan:314-320): qacc = ctrl
+                acc.y = dyv;
+                v.x = tx;     // == v + dt*qacc (the same two roundings)
+                v.y = ty;
+            } else {
+                double ax = dxv, ay = dyv;
+                if (!free_run) {
+                    double velx = v.x, vely = v.y;
+                    if (NOISE) {
+                        normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
                         have0 = true;
+                        velx = noisy(v.x, n4[0], a.sigma_v);
+                        vely = noisy(v.y, n4[1], a.sigma_v);
                     }
-                    velx = noisy(v.x, n4[0], a.sigma_v);
-                    vely = noisy(v.y, n4[1], a.sigma_v);
+                    double t0, t1;
+                    ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);
                 }
-            }
-            double t0, t1, ax, ay;
-            ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);  // plan:437 / 442
-            if (a.learn_jerk) {
-                if (dxv != ax || dyv != ay) {  // plan:438
-                    jx = ddiv(dsub(ax, acc.x), a.dt);
-                    jy = ddiv(dsub(ay, acc.y), a.dt);
+                if (a.learn_jerk) {
+                    if (dxv != ax || dyv != ay) {  // plan:438
+                        jx = ddiv(dsub(ax, acc.x), a.dt);
+                        jy = ddiv(dsub(ay, acc.y), a.dt);
+                    }
+                    // mj_step, integrator actuator with actearly (plan:305-311): act += dt*ctrl; qacc = act
+                    acc.x = dadd(acc.x, dmul(a.dt, jx));
+                    acc.y = dadd(acc.y, dmul(a.dt, jy));
+                } else {
+                    acc.x = ax;
+                    acc.y = ay;
                 }
-                // mj_step, integrator actuator with actearly (plan:305-311): act += dt*ctrl; qacc = act
-                acc.x = dadd(acc.x, dmul(a.dt, jx));
-                acc.y = dadd(acc.y, dmul(a.dt, jy));
-            } else {
-                acc.x = ax;  // dyntype none, gain = mass (plan:314-320): qacc = ctrl
-                acc.y = ay;
+                // semi-implicit Euler (MuJoCo): qvel += dt*qacc
+                v.x = dadd(v.x, dmul(a.dt, acc.x));
+                v.y = dadd(v.y, dmul(a.dt, acc.y));
             }
-            // semi-implicit Euler (MuJoCo): qvel += dt*qacc; qpos += dt*qvel
-            v.x = dadd(v.x, dmul(a.dt, acc.x));
-            v.y = dadd(v.y, dmul(a.dt, acc.y));
-            p.x = dadd(p.x, dmul(a.dt, v.x));
+            p.x = dadd(p.x, dmul(a.dt, v.x));  // qpos += dt*qvel
             p.y = dadd(p.y, dmul(a.dt, v.y));
+            // |v| <= max + min/2 of the absolute components; 1e-4 covers the float roundings of the running sum
+            const float avx = fabsf((float)v.x), avy = fabsf((float)v.y);
+            travel += (fmaxf(avx, avy) + 0.5f * fminf(avx, avy)) * 1.0001f;
         }
-        bool bad, hit;
-        if (!BOX) {
-            // basic:1888-1894 wall check on noisy qpos: float32 for the tracked cell, exact (with noise) when too close
-            bad = wall_bad_circle<NOISE>(a, tb, part, p.x, p.y, cw0, cw0f, gi, gj, ln.env_global, event,
-                                         s0 + GPR_RNG_BLOCK_VEL_WALL, ln.m, 2, n4, have0);
-            // basic:1895-1901 mover check on an independently noisy qpos
-            hit = pair_circle_fast<G, NOISE>(a, ln.lane, ln.m, part, p.x, p.y, cm0, 0, ln.env_global, event,
-                                             s0 + GPR_RNG_BLOCK_MOVER);
-        } else {
-            double wx = p.x, wy = p.y, mx = p.x, my = p.y;
-            Rect rw, rm;
-            if (NOISE) {
-                wx = noisy(p.x, n4[2], a.sigma_p);
-                wy = noisy(p.y, n4[3], a.sigma_p);
-                float q[4];
-                gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT, (uint32_t)ln.m, q);
-                rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
-                              dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
-                if (G > 1) {
-                    float k4[4];
-                    gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER, (uint32_t)ln.m, k4);
-                    mx = noisy(p.x, k4[0], a.sigma_p);
-                    my = noisy(p.y, k4[1], a.sigma_p);
-                    gpr_normal4(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER_QUAT, (uint32_t)ln.m, q);
-                    rect_vertices(mx, my, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
-                                  dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
-                }
+        const bool due_w = part && !(travel < lim_w);
+        const bool due_p = G > 1 && part && !(travel < lim_p);
+        if (!__any_sync(FULL, due_w || due_p)) continue;  // every mover of this warp is certified clear
+
+        // ---- wall check (basic:1888-1894) of the lanes that are due: lane-local
+        bool bad = false;
+        if (due_w) {
+            float clear_w;
+            if (!BOX) {
+                // float32 for the tracked cell, exact float64 (with the lazily generated noise) when too close to call
+                bad = wall_bad_circle<NOISE>(a, tb, true, p.x, p.y, cw0, cw0f, gi, gj, ln.env_global, event,
+                                             s0 + GPR_RNG_BLOCK_VEL_WALL, ln.m, 2, n4, have0, clear_w);
             } else {
-                rect_vertices_axis(wx, wy, cw0, cw1, rw);
-                rect_vertices_axis(mx, my, cm0, cm1, rm);
+                // float32 screen with a bounding rectangle; the exact vertex / rectangle tests of basic:559-572, 657-783
+                // only where the screen cannot certify "valid" (0 is not a verdict: the rectangle is conservative)
+                if (wall_fast(a, tb, p.x, p.y, bxf, byf, gi, gj, clear_w) != 1) {
+                    double wx = p.x, wy = p.y;
+                    Rect rw;
+                    if (NOISE) {
+                        if (!have0) normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
+                        have0 = true;
+                        wx = noisy(p.x, n4[2], a.sigma_p);
+                        wy = noisy(p.y, n4[3], a.sigma_p);
+                        float q[4];
+                        normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT, (uint32_t)ln.m, q);
+                        rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                                      dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
+                    } else {
+                        rect_vertices_axis(wx, wy, cw0, cw1, rw);
+                    }
+                    bad = !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
+                    guess_cell(a, p.x, p.y, gi, gj);  // refresh the tracked cell
+                }
             }
-            bad = part && !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
-            hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0);
+            lim_w = (travel + clear_w * a.inv_dtf) * 0.999999f;
         }
-        const bool wnow = (__ballot_sync(FULL, bad) & ln.gmask) != 0u;
-        const bool mnow = (__ballot_sync(FULL, hit) & ln.gmask) != 0u;
-        if (alive) {
-            wc = wnow;
-            mc = mnow;
-            if (wc || mc) alive = false;  // basic:1904 break
+        // ---- mover check (basic:1895-1901) on an independently noisy qpos: warp-collective
+        bool hit = false;
+        if (G > 1 && __any_sync(FULL, due_p)) {
+            float clear_p;
+            if (!BOX) {
+                hit = pair_circle_fast<G, NOISE>(a, ln.lane, ln.m, part, p.x, p.y, cm0, 0, ln.env_global, event,
+                                                 s0 + GPR_RNG_BLOCK_MOVER, clear_p);
+            } else {
+                // bounding-circle screen; the exact rectangle test of geom:107-138 only for a warp with an uncleared pair
+                bool near;
+                pair_box_screen<G>(ln.lane, ln.m, part, p.x, p.y, diagf, a.pair_mgf[NOISE ? 1 : 0], near, clear_p);
+                if (__any_sync(FULL, near)) {
+                    double mx = p.x, my = p.y;
+                    Rect rm;
+                    if (NOISE) {
+                        float k4[4], q[4];
+                        normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER, (uint32_t)ln.m, k4);
+                        mx = noisy(p.x, k4[0], a.sigma_p);
+                        my = noisy(p.y, k4[1], a.sigma_p);
+                        normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER_QUAT, (uint32_t)ln.m, q);
+                        rect_vertices(mx, my, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                                      dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
+                    } else {
+                        rect_vertices_axis(mx, my, cm0, cm1, rm);
+                    }
+                    // decides every pair of the warp's envs (pairs the screen cleared are misses either way)
+                    hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0);
+                }
+            }
+            // an env's pair clearance is the smallest one any of its lanes saw; each mover may use up half of it
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) clear_p = fminf(clear_p, __shfl_xor_sync(FULL, clear_p, o));
+            lim_p = (travel + 0.5f * clear_p * a.inv_dtf) * 0.999999f;
+        }
+        const unsigned badm = __ballot_sync(FULL, bad), hitm = __ballot_sync(FULL, hit);
+        if (badm | hitm) {
+            if (alive) {
+                wc = (badm & ln.gmask) != 0u;
+                mc = (hitm & ln.gmask) != 0u;
+                if (wc || mc) alive = false;  // basic:1904 break
+            }
+            any_alive = __any_sync(FULL, alive);
         }
     }
 
@@ -743,8 +892,9 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const __grid_constan
     }
     if (need && a.autoreset == GPR_AUTORESET_SAME_STEP)
         store_obs<G>(a, ln, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, ov, acc, ag, goal);
-    // (rows of envs on the reset list are overwritten by planning_autoreset_kernel)
-    if (stepped) store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, a.out.desired_goal, ov, acc, ag, goal);
+    // (the rows of envs handed to planning_autoreset_kernel are written there: first observation of the new episode)
+    if (stepped && !(need && a.autoreset == GPR_AUTORESET_SAME_STEP))
+        store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, a.out.desired_goal, ov, acc, ag, goal);
 
     // ------------------------------------------------------------------ state write-back
     if (ln.active && stepped) {
@@ -763,7 +913,7 @@ __global__ void __launch_bounds__(256) planning_step_kernel(const __grid_constan
 // different rejection-sampling attempts; lane group 0 then acts as the env's movers for the reset-time checks, the first
 // observation and the state write.  Warps pull list entries through an atomic cursor (attempt counts are geometric).
 template <int G, bool BOX, bool NOISE>
-__global__ void __launch_bounds__(128) planning_autoreset_kernel(const __grid_constant__ PlanArgs a) {
+__global__ void __launch_bounds__(128, GPR_AR_MINB) planning_autoreset_kernel(const __grid_constant__ PlanArgs a) {
     __shared__ Tables tb;
     load_tables(tb, a.L);
     __syncthreads();

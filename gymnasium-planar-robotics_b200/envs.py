@@ -51,6 +51,28 @@ def shard_range(total_envs: int, rank: int, world_size: int) -> tuple[int, int]:
     return base, count
 
 
+def all_reduce_stats(counters: torch.Tensor) -> torch.Tensor:
+    """Sum the 6 episode counters over ranks — the ONLY collective of the framework (NCCL for CUDA tensors, gloo for CPU
+    tensors in the host-logic tests); a no-op without an initialised process group.  Never on the step path."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    return counters
+
+
+def stats_dict(v: list[float]) -> dict[str, float]:
+    n = max(v[0], 1.0)
+    return {
+        'episodes': v[0],
+        'mean_return': v[1] / n,
+        'mean_length': v[2] / n,
+        'success_rate': v[3] / n,
+        'mover_collision_rate': v[4] / n,
+        'wall_collision_rate': v[5] / n,
+    }
+
+
 class BatchedCore:
     """One ``gpr_handle`` on one device plus the caller-owned I/O tensors the C ABI writes into."""
 
@@ -102,6 +124,7 @@ class BatchedCore:
             setattr(self._out, name, _ptr(self.buf.get(name)))
         self._action = z((B, self.action_dim), f32)
         self._host: dict[str, np.ndarray] | None = None
+        self._pinned_actions: list[torch.Tensor] = []
 
     # ------------------------------------------------------------------------------------------------------------ util
     def _stream(self) -> int:
@@ -157,11 +180,19 @@ class BatchedCore:
             raise ValueError(f'action dim != action_space dim: expected {(self.num_envs, self.action_dim)}, got {tuple(action.shape)}')
         _lib.check(self.lib.gpr_step(self.handle, action.data_ptr(), ctypes.byref(self._out), self._stream()))
 
+    def pinned_action_buffer(self) -> np.ndarray:
+        """A page-locked float32 (num_envs, action_dim) array to fill with actions: ``step_host`` reads it in place."""
+        t = torch.zeros((self.num_envs, self.action_dim), dtype=torch.float32, pin_memory=True)
+        self._pinned_actions.append(t)  # torch owns the memory, NumPy views it
+        return t.numpy()
+
     def step_host(self, action: np.ndarray) -> dict[str, np.ndarray]:
-        """The same step called with HOST buffers (``gpr_step_host``): NumPy action in, NumPy results out."""
+        """The same step called with HOST buffers (``gpr_step_host``): NumPy action in, NumPy results out.  The result
+        arrays are page-locked, so the kernels write them in place over PCIe (no staging copy); an action array obtained
+        from ``pinned_action_buffer`` is likewise read in place, any other one is staged through pinned memory."""
         a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.num_envs, self.action_dim)
         if self._host is None:
-            # page-locked result arrays (torch owns the memory, NumPy views it): the copy engine writes them directly
+            # page-locked result arrays (torch owns the memory, NumPy views it)
             self._host_pin = {k: torch.zeros(tuple(v.shape), dtype=v.dtype, pin_memory=True) for k, v in self.buf.items()}
             self._host = {k: t.numpy() for k, t in self._host_pin.items()}
             self._host_out = GprOutputs()
@@ -232,20 +263,8 @@ class BatchedCore:
         out = torch.zeros(6, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.gpr_episode_stats(self.handle, out.data_ptr(), int(reset), self._stream()))
         if all_reduce:
-            import torch.distributed as dist
-
-            if dist.is_available() and dist.is_initialized():
-                dist.all_reduce(out)
-        v = out.tolist()
-        n = max(v[0], 1.0)
-        return {
-            'episodes': v[0],
-            'mean_return': v[1] / n,
-            'mean_length': v[2] / n,
-            'success_rate': v[3] / n,
-            'mover_collision_rate': v[4] / n,
-            'wall_collision_rate': v[5] / n,
-        }
+            all_reduce_stats(out)
+        return stats_dict(out.tolist())
 
     def reset_failures(self) -> int:
         c = ctypes.c_uint32()
@@ -376,10 +395,11 @@ class _VecEnvBase:
         """step() for callers that live on the host (NumPy in / NumPy out through ``gpr_step_host``)."""
         h = self.core.step_host(action)
         obs = {'observation': h['observation'], 'achieved_goal': h['achieved_goal'], 'desired_goal': h['desired_goal']}
-        info = {k: h[k].astype(bool) for k in ('is_success', 'mover_collision', 'wall_collision')}
+        # the flag arrays hold 0/1 bytes: view them as bool instead of converting (the arrays are reused every step)
+        info = {k: h[k].view(np.bool_) for k in ('is_success', 'mover_collision', 'wall_collision')}
         if 'final_observation' in h:
             info['final_obs'] = {k: h['final_' + k] for k in ('observation', 'achieved_goal', 'desired_goal')}
-        return obs, h['reward'], h['terminated'].astype(bool), h['truncated'].astype(bool), info
+        return obs, h['reward'], h['terminated'].view(np.bool_), h['truncated'].view(np.bool_), info
 
     def compute_reward(self, achieved_goal, desired_goal, info=None):
         mc, wc = self._split_info(info)

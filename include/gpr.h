@@ -206,9 +206,10 @@ GPR_API int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, uint
  * [num_envs, action_dim]. */
 GPR_API int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* out, void* stream);
 
-/* Same step, called the way a user of the reference calls it: HOST buffers in, HOST buffers out.  The action is staged
- * through pinned memory, copied to the device, stepped, and every non-NULL output is copied back; returns after the host
- * buffers are valid.  `host_out` holds host pointers. */
+/* Same step, called the way a user of the reference calls it: HOST buffers in, HOST buffers out; returns after the host
+ * buffers are valid.  `host_out` holds host pointers.  Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch
+ * pinned tensors) are read and written by the kernels IN PLACE through their device alias (zero-copy: result stores cross
+ * PCIe while the rest of the grid still computes); pageable buffers are staged through the handle's pinned mirror. */
 GPR_API int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out);
 GPR_API int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_outputs* host_out);
 
