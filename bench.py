@@ -210,6 +210,7 @@ def run_b200(args, wl):
             env.step(acts[i % 8])
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         n0 = env.core.launch_count
+        env.core.kernel_times(True)  # per-kernel CUDA events inside gpr_step, on the launching stream
         barrier()
         t0 = time.perf_counter()
         for i in range(steps):
@@ -220,11 +221,12 @@ def run_b200(args, wl):
         barrier()
         wall = time.perf_counter() - t0
         ms = sum(a.elapsed_time(b) for a, b in ev)
-        return ms, env.core.launch_count - n0, wall
+        kt = env.core.kernel_times(False)
+        return ms, env.core.launch_count - n0, wall, kt
 
     env = build()
     with ClockSampler(local) as clk:
-        ms, launches, wall = timed(env, args.steps, args.warmup)
+        ms, launches, wall, ktimes = timed(env, args.steps, args.warmup)
     clocks = clk.summary()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -265,7 +267,7 @@ def run_b200(args, wl):
     if not args.quick:
         e0 = build(std_noise=0.0)
         n0 = max(20, args.steps // 2)
-        ms0, _, _ = timed(e0, n0, 3)
+        ms0, _, _, _ = timed(e0, n0, 3)
         t0 = torch.tensor([ms0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t0, op=dist.ReduceOp.MAX)
@@ -276,8 +278,11 @@ def run_b200(args, wl):
         N, J = int(env.cfg.num_movers), int(env.cfg.learn_jerk)
         abytes = algorithmic_bytes_per_env_step(wl['kind'], N, J)
         peak, peak_src = measured_hbm_peak()
-        kernel_ms = ms_max / args.steps
-        achieved = abytes * B / (kernel_ms * 1e-3) / 1e9
+        kernel_ms = ms_max / args.steps  # whole step (all kernels of gpr_step), max over ranks
+        # roofline of the dominant kernel (the fused step kernel): its own average launch duration, CUDA events on the
+        # launching stream around that kernel alone (rank 0)
+        step_kernel_ms = ktimes['step_kernel_ms']
+        achieved = abytes * B / (step_kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tp):
@@ -303,7 +308,8 @@ def run_b200(args, wl):
                        'actions': 'uniform(-max,max), 8 pre-generated device tensors cycled',
                        'l2': 'flushed between timed steps (256 MiB memset, outside the event pairs)', 'parallelism': f'env-shard x{world}'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                         'peak_source': peak_src, 'algorithmic_bytes_per_env_step': abytes, 'kernel': 'planning_step_kernel' if wl['kind'] == 'planning' else 'pushing_step_kernel',
+                         'peak_source': peak_src, 'algorithmic_bytes_per_env_step': abytes, 'algorithmic_bytes_per_launch': abytes * B,
+                         'kernel_ms': step_kernel_ms, 'other_kernels_ms': {'autoreset': ktimes['autoreset_kernel_ms']}, 'kernel': 'planning_step_kernel' if wl['kind'] == 'planning' else 'pushing_step_kernel',
                          'note': 'issue-bound kernel (40-cycle float64 loop per env): see profiles/ for issue-slot and stall breakdown'},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,

@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     'gpr_compute_reward',
     'gpr_episode_stats',
     'gpr_reset_failures',
+    'gpr_kernel_times',
     'gpr_launch_count',
 )
 
@@ -73,6 +74,7 @@ def load():
     lib.gpr_compute_reward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.gpr_episode_stats.argtypes = [vp, vp, i32, vp]
     lib.gpr_reset_failures.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
+    lib.gpr_kernel_times.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
     lib.gpr_launch_count.argtypes = [vp]
     lib.gpr_launch_count.restype = u64
     if lib.gpr_abi_version() != GPR_ABI_VERSION or lib.gpr_config_bytes() != ctypes.sizeof(GprConfig):

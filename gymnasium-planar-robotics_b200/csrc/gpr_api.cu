@@ -69,6 +69,10 @@ struct gpr_handle {
     double *cx = nullptr, *cy = nullptr, *c_wall = nullptr, *c_mover = nullptr;
     uint16_t* cell = nullptr;
     double quirk_rsum[2] = {0, 0};
+    // per-kernel timing (gpr_kernel_times)
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;  // triples: before step kernel, between, after auto-reset kernel
+    size_t tev_used = 0;
     // staging for the *_host entry points
     cudaStream_t host_stream = nullptr;
     void* d_stage = nullptr;  // device: action + all outputs
@@ -175,6 +179,7 @@ extern "C" void gpr_destroy(gpr_handle* h) {
                     h->cell, h->d_stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (cudaEvent_t ev : h->tev) cudaEventDestroy(ev);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     cudaSetDevice(prev);
@@ -333,9 +338,11 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     // circle: one threshold for every pair when all radii are equal, or under the basic:409 broadcast quirk
     bool equal = true;
     for (int s = 0; s < 2; ++s)
-        for (int m = 1; m < c.num_movers; ++m) equal = equal && c.c_mover[s][m][0] == c.c_mover[s][0][0];
+        for (int m = 1; m < c.num_movers; ++m)
+            equal = equal && c.c_mover[s][m][0] == c.c_mover[s][0][0] &&
+                    (c.c_shape == GPR_SHAPE_CIRCLE || c.c_mover[s][m][1] == c.c_mover[s][0][1]);
     const bool quirk = c.reference_quirks != 0 && c.c_shape == GPR_SHAPE_CIRCLE;
-    a.uniform_pairs = c.c_shape == GPR_SHAPE_CIRCLE && (equal || quirk);
+    a.uniform_pairs = equal || quirk;  // box shape: all movers have one size
     for (int s = 0; s < 2; ++s) {
         const double t = (quirk && !equal) ? h->quirk_rsum[s] : c.c_mover[s][0][0] + c.c_mover[s][0][0];
         a.pair_t[s] = t;
@@ -354,6 +361,8 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     // too large for the bound: a huge extent then makes the screen defer to the exact test every time)
     a.rot_extf = !h->noise ? 0.f : (c.std_noise[0] < 5e-3 ? (float)(14.0 * c.std_noise[0]) : 1e3f);
     a.inv_dtf = (float)((1.0 / c.cycle_time) * (1.0 - 1e-6));
+    a.inv_wxf = (float)(1.0 / (2.0 * c.tile_half[0]));
+    a.inv_wyf = (float)(1.0 / (2.0 * c.tile_half[1]));
     a.sigma_p = c.std_noise[0];
     a.sigma_v = c.std_noise[1];
     a.L = layout_args(h);
@@ -490,10 +499,22 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
     if (!out) return fail(GPR_ERR_INVALID_ARG, "outputs struct is NULL");
     DeviceGuard g(h->device);
     cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t* te = nullptr;
+    if (h->timing) {
+        while (h->tev.size() < h->tev_used + 3) {
+            cudaEvent_t ev;
+            CU(cudaEventCreate(&ev));
+            h->tev.push_back(ev);
+        }
+        te = &h->tev[h->tev_used];
+        h->tev_used += 3;
+        CU(cudaEventRecord(te[0], s));
+    }
     if (h->cfg.env_kind == GPR_ENV_PLANNING) {
         PlanArgs a = plan_args(h, out);
         a.action = reinterpret_cast<const float2*>(action);
         CU(launch_plan(h, PLAN_STEP, a, s));
+        if (te) CU(cudaEventRecord(te[1], s));
         if (h->cfg.autoreset_mode != GPR_AUTORESET_OFF) {
             CU(launch_plan(h, PLAN_AUTORESET, a, s));
             h->parity ^= 1;
@@ -503,8 +524,32 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
         PushArgs a = push_args(h, out);
         a.action = reinterpret_cast<const float2*>(action);
         CU(launch_push(false, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, s));
+        if (te) CU(cudaEventRecord(te[1], s));
     }
+    if (te) CU(cudaEventRecord(te[2], s));
     h->launches += 1;
+    return GPR_OK;
+}
+
+extern "C" int gpr_kernel_times(gpr_handle* h, int enable, double* host_ms) {
+    if (!h) return fail(GPR_ERR_INVALID_ARG, "handle is NULL");
+    DeviceGuard g(h->device);
+    if (host_ms) {
+        double t_step = 0.0, t_reset = 0.0;
+        for (size_t k = 0; k + 2 < h->tev_used + 0 && k + 3 <= h->tev_used; k += 3) {
+            CU(cudaEventSynchronize(h->tev[k + 2]));
+            float a = 0.f, b = 0.f;
+            CU(cudaEventElapsedTime(&a, h->tev[k], h->tev[k + 1]));
+            CU(cudaEventElapsedTime(&b, h->tev[k + 1], h->tev[k + 2]));
+            t_step += a;
+            t_reset += b;
+        }
+        host_ms[0] = t_step;
+        host_ms[1] = t_reset;
+        host_ms[2] = (double)(h->tev_used / 3);
+    }
+    h->tev_used = 0;
+    h->timing = enable != 0;
     return GPR_OK;
 }
 

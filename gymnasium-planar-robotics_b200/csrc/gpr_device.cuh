@@ -19,6 +19,26 @@
 #include "../../include/gpr.h"
 #include "../../include/gpr_rng.h"
 
+// Inlining policy of the cold (rarely executed) helpers, overridable per helper for tuning experiments:
+//   -DGPR_INL_WALL=0 / GPR_INL_NORMAL=0 / GPR_INL_PAIR=0 / GPR_INL_CONFIRM=0 move a helper out of line.  Measured on B200
+//   (planning4, same box, +-0.1%): all inline 0.312 ms/step, all out of line 0.326, mixed 0.320-0.341 -> inline.
+#ifndef GPR_INL_WALL
+#define GPR_INL_WALL 1
+#endif
+#ifndef GPR_INL_NORMAL
+#define GPR_INL_NORMAL 1
+#endif
+#ifndef GPR_INL_PAIR
+#define GPR_INL_PAIR 1
+#endif
+#ifndef GPR_INL_CONFIRM
+#define GPR_INL_CONFIRM 1
+#endif
+#define GPR_COLD_1 __device__ __forceinline__
+#define GPR_COLD_0 static __device__ __noinline__
+#define GPR_COLD_CAT(x) GPR_COLD_##x
+#define GPR_COLD(flag) GPR_COLD_CAT(flag)
+
 namespace gpr {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -71,6 +91,7 @@ struct Tables {
     double xlo[kMaxTiles], xhi[kMaxTiles];  // tile_cx[i] -+ half  (basic:519-523)
     double ylo[kMaxTiles], yhi[kMaxTiles];
     uint16_t cell[kMaxTiles * kMaxTiles];   // [i * ny + j]
+    float xlof[kMaxTiles], ylof[kMaxTiles]; // float copies of xlo / ylo (float32 screens only, never decisive)
 };
 
 struct LayoutArgs {
@@ -87,11 +108,13 @@ __device__ __forceinline__ void load_tables(Tables& tb, const LayoutArgs& L) {
         const double c = L.cx[i];
         tb.xlo[i] = dsub(c, L.hx);
         tb.xhi[i] = dadd(c, L.hx);
+        tb.xlof[i] = (float)dsub(c, L.hx);
     }
     for (int j = threadIdx.x; j < L.ny; j += blockDim.x) {
         const double c = L.cy[j];
         tb.ylo[j] = dsub(c, L.hy);
         tb.yhi[j] = dadd(c, L.hy);
+        tb.ylof[j] = (float)dsub(c, L.hy);
     }
     for (int k = threadIdx.x; k < L.nx * L.ny; k += blockDim.x) tb.cell[k] = L.cell[k];
 }
@@ -201,7 +224,7 @@ __device__ __forceinline__ void rect_vertices_axis(double px, double py, double 
 // inclusive comparisons against the reference's float64 bounds (basic:507-512); the guess never decides anything.
 // (out of line on purpose: it is the rare exact fallback of the float32 screens, called from many places)
 template <bool BOX>
-static __device__ __noinline__ bool wall_valid(const Tables& tb, const LayoutArgs& L, double x, double y, double cs0,
+GPR_COLD(GPR_INL_WALL) bool wall_valid(const Tables& tb, const LayoutArgs& L, double x, double y, double cs0,
                                                const Rect& rect) {
     int gi = __double2int_rd(dmul(x, L.inv_wx));
     int gj = __double2int_rd(dmul(y, L.inv_wy));

@@ -48,6 +48,7 @@ struct PlanArgs {
     float pair_thif[2][2];                   // [safety][noisy] upper edge of the band as a distance (uniform_pairs)
     float rot_extf;                          // box shape: bound on |sin| of the noise-induced rotation (0 without noise)
     float inv_dtf;                           // 1 / cycle_time, rounded down (travel budget in velocity units)
+    float inv_wxf, inv_wyf;                  // 1 / tile width (cell guess of the float32 screens)
     float goal_lo2f, goal_hi2f;              // min_goal_dist bands
     float minxf, minyf, spanxf, spanyf;      // spawn box as float
     LayoutArgs L;
@@ -109,7 +110,7 @@ __device__ __forceinline__ double noisy(double x, float n, double sigma) { retur
 
 // gpr_normal4 for the lazily generated noise: those sites are cold (a check only needs its noise inside a ~1e-4 m band),
 // so one out-of-line copy keeps the hot loops small (instruction cache) instead of ~150 inlined instructions per site
-static __device__ __noinline__ void normal4_cold(uint64_t seed, uint32_t env_global, uint32_t event, uint32_t stream,
+GPR_COLD(GPR_INL_NORMAL) void normal4_cold(uint64_t seed, uint32_t env_global, uint32_t event, uint32_t stream,
                                                  uint32_t lane, float (&out)[4]) {
     gpr_normal4(seed, env_global, event, stream, lane, out);
 }
@@ -117,7 +118,7 @@ static __device__ __noinline__ void normal4_cold(uint64_t seed, uint32_t env_glo
 // ---- circle pair check with the lazy-noise band (basic:392-409), warp-collective --------------------------------------
 //   NOISY: the positions carry the mover-check noise of (event, stream) — generated only inside the uncertainty band.
 template <int G, bool NOISY>
-static __device__ __noinline__ bool pair_circle(const PlanArgs& a, unsigned lane, int m, bool part, double x, double y,
+GPR_COLD(GPR_INL_PAIR) bool pair_circle(const PlanArgs& a, unsigned lane, int m, bool part, double x, double y,
                                             double r, int safety, uint32_t env_global, uint32_t event, uint32_t stream) {
     bool hit = false;
     if (G == 1) return false;
@@ -178,9 +179,8 @@ static __device__ __noinline__ bool pair_circle(const PlanArgs& a, unsigned lane
 // neighbour, an unsafe corner also the diagonal one), so the clearance is the smallest L-infinity gap between the
 // rectangle and a missing cell of the 3x3 neighbourhood, capped by the gap to the ring beyond it (>= tile width - c),
 // minus wall_delta.  It does not depend on how close the verdict of THIS cycle was.
-__device__ __forceinline__ int wall_fast(const PlanArgs& a, const Tables& tb, double x, double y, float cx, float cy, int gi,
+__device__ __forceinline__ int wall_core(const PlanArgs& a, const Tables& tb, float fx, float fy, float cx, float cy, int gi,
                                          int gj, float& clear) {
-    const float fx = (float)dsub(x, tb.xlo[gi]), fy = (float)dsub(y, tb.ylo[gj]);
     const float wc = a.wxf - cx, hc = a.wyf - cy;
     const float gw = fx - cx, ge = wc - fx, gs = fy - cy, gn = hc - fy;  // gaps to the W / E columns and S / N rows
     const bool inside = fx > 0.f && fx < a.wxf && fy > 0.f && fy < a.wyf;
@@ -201,6 +201,18 @@ __device__ __forceinline__ int wall_fast(const PlanArgs& a, const Tables& tb, do
     if (!(fminf(mx, my) >= a.wall_delta) || !inside) return 2;
     const uint32_t u = (gw < 0.f ? 1u : 0u) | (ge < 0.f ? 2u : 0u) | (gs < 0.f ? 4u : 0u) | (gn < 0.f ? 8u : 0u);
     return ((code & CELL_3X3) || sides_ok(u, code)) ? 1 : 0;
+}
+__device__ __forceinline__ int wall_fast(const PlanArgs& a, const Tables& tb, double x, double y, float cx, float cy, int gi,
+                                         int gj, float& clear) {
+    return wall_core(a, tb, (float)dsub(x, tb.xlo[gi]), (float)dsub(y, tb.ylo[gj]), cx, cy, gi, gj, clear);
+}
+// the same screen for a float32 position (rejection sampling): the cell is guessed from the float coordinates; a
+// coordinate within wall_delta of a cell border comes back "too close to call" like any other near-threshold case
+__device__ __forceinline__ int wall_screen_f(const PlanArgs& a, const Tables& tb, float xf, float yf, float cx, float cy) {
+    const int gi = min(max(__float2int_rd(xf * a.inv_wxf), 0), a.L.nx - 1);
+    const int gj = min(max(__float2int_rd(yf * a.inv_wyf), 0), a.L.ny - 1);
+    float clear;
+    return wall_core(a, tb, xf - tb.xlof[gi], yf - tb.ylof[gj], cx, cy, gi, gj, clear);
 }
 
 __device__ __forceinline__ void guess_cell(const PlanArgs& a, double x, double y, int& gi, int& gj) {
@@ -278,13 +290,15 @@ __device__ __forceinline__ bool pair_circle_fast(const PlanArgs& a, unsigned lan
     return hit;
 }
 
-// Box shape: float32 bounding-circle screen of the mover-mover check (warp-collective).  Two rectangles whose centres are
-// farther apart than the sum of their half diagonals (+ noise bound + float slack) cannot intersect (geom:107-138), so such
-// a pair is a certain miss and `margin` says how much the two movers may still travel; `near` marks lanes with a pair the
-// screen cannot clear (the caller then runs the exact rectangle test for the warp).
+// Box shape: float32 screen of the mover-mover check (warp-collective).  Planning movers never rotate (the only rotation
+// is the sensor noise on the quaternion), so each rectangle lies inside the axis-aligned box [x +- ex] x [y +- ey] with
+// (ex, ey) = half sizes widened by the noise-rotation bound.  Two such boxes that are separated along x OR along y by more
+// than the position-noise bound + float slack `mg` cannot have intersecting edges (geom:107-138): a certain miss, and
+// `margin` is the largest of the two axis gaps — the L-infinity distance the pair may still close before that changes.
+// `near` marks lanes with a pair the screen cannot clear (the caller then runs the exact rectangle test for the warp).
 template <int G>
-__device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part, double x, double y, float diagf, float mg,
-                                                bool& near, float& margin) {
+__device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part, double x, double y, float exf, float eyf,
+                                                float mg, bool& near, float& margin) {
     near = false;
     margin = 3.0e38f;
     if (G == 1) return;
@@ -294,10 +308,10 @@ __device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part,
     for (int k = 1; k <= G / 2; ++k) {
         const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
         const float oxf = __shfl_sync(FULL, xf, src), oyf = __shfl_sync(FULL, yf, src);
-        const float thi = (diagf + __shfl_sync(FULL, diagf, src) + mg) * 1.000001f;
+        const float tx = (exf + __shfl_sync(FULL, exf, src) + mg) * 1.000001f;
+        const float ty = (eyf + __shfl_sync(FULL, eyf, src) + mg) * 1.000001f;
         const bool both = part && oxf < 1e29f;
-        const float dx = xf - oxf, dy = yf - oyf;
-        const float mgn = sqrtf(dx * dx + dy * dy) * 0.999999f - thi;
+        const float mgn = fmaxf(fabsf(xf - oxf) * 0.999999f - tx, fabsf(yf - oyf) * 0.999999f - ty);
         if (both) {
             near = near || !(mgn > 0.f);
             margin = fminf(margin, fmaxf(mgn, 0.f));
@@ -349,7 +363,7 @@ __device__ __forceinline__ void store_obs(const PlanArgs& a, const Lane<G>& ln, 
 // out of line, so the hot screening loop stays small.  Warp-collective.  Returns true (in every lane) when an attempt of
 // this Philox block round was accepted; `out` then holds, for mover m = lane % G, the position of the first accepted one.
 template <int G, bool BOX, int KIND>
-static __device__ __noinline__ bool sample_confirm(const PlanArgs& a, const Tables& tb, unsigned lane, unsigned gmask,
+GPR_COLD(GPR_INL_CONFIRM) bool sample_confirm(const PlanArgs& a, const Tables& tb, unsigned lane, unsigned gmask,
                                                    int cap, uint32_t blk, gpr_u32x4 r, unsigned cand_bits,
                                                    unsigned needx_bits, uint32_t eg, uint32_t ev, double2& out) {
     const int m = (int)(lane % G);
@@ -416,15 +430,15 @@ static __device__ __noinline__ bool sample_confirm(const PlanArgs& a, const Tabl
 }
 
 template <int G, bool BOX, int KIND>
-__device__ __forceinline__ void sample_env(const PlanArgs& a, const Tables& tb, unsigned lane, unsigned gmask_, uint32_t eg,
-                                           uint32_t ev, double2& out, bool& failed) {
+__device__ __forceinline__ void sample_env_groups(const PlanArgs& a, const Tables& tb, unsigned lane, unsigned gmask_, uint32_t eg,
+                                                  uint32_t ev, double2& out, bool& failed) {
     constexpr int S = 32 / G;  // attempts tested per half-iteration
     const int slot = (int)(lane / G);
     const int m = (int)(lane % G);
     const bool has_mover = m < a.N;
     const int mm = has_mover ? m : 0;
-    const float rf = (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0];
-    const float diagf = rf + (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];  // box: |half diagonal| <= sx + sy
+    const float rf = (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0];   // circle radius / box half size x (with offset)
+    const float sf = (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];   // box half size y
     const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
     const unsigned base = lane & ~(unsigned)(G - 1);
     bool found = false;
@@ -451,9 +465,22 @@ __device__ __forceinline__ void sample_env(const PlanArgs& a, const Tables& tb, 
                         lo2 = a.goal_lo2f;
                         hi2 = a.goal_hi2f;
                     } else if (BOX) {
-                        const float td = diagf + __shfl_sync(FULL, diagf, src) + a.pair_mgf[0];
-                        lo2 = -1.f;  // boxes: the float test can only prove a miss (centres farther than the diagonals)
-                        hi2 = td * td;
+                        // axis-aligned rectangles (identity quaternion, plan:364): a gap along x or y is a certain miss;
+                        // overlap along both axes is a certain hit when all boxes have one size (no containment case,
+                        // which geom:107-138 would not report) — the rest goes to the exact test
+                        const float tx = rf + __shfl_sync(FULL, rf, src), ty = sf + __shfl_sync(FULL, sf, src);
+                        const float mg = a.pair_mgf[0];
+                        const float adx = fabsf(xf - oxf), ady = fabsf(yf - oyf);
+                        const bool mine = part && oxf < 1e29f;
+                        if (mine) {
+                            if (adx > tx + mg || ady > ty + mg) {
+                            } else if (a.uniform_pairs && adx < tx - mg && ady < ty - mg) {
+                                rej = true;
+                            } else {
+                                unc = true;
+                            }
+                        }
+                        continue;
                     } else if (a.uniform_pairs) {
                         lo2 = a.pair_lo2f[1][0];
                         hi2 = a.pair_hi2f[1][0];
@@ -486,6 +513,191 @@ __device__ __forceinline__ void sample_env(const PlanArgs& a, const Tables& tb, 
         gpr_sample_xy(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE, (uint32_t)KIND, (uint32_t)(cap - 1), (uint32_t)m, &ux, &uy);
         out = make_double2(dadd(a.min_xy[0], dmul(a.span_xy[0], ux)), dadd(a.min_xy[1], dmul(a.span_xy[1], uy)));
         failed = true;
+    }
+}
+
+// ---- rejection sampling, one lane per PAIR OF ATTEMPTS (G <= 8) ---------------------------------------------------------
+// The same sequence of attempts as sample_env_groups (same Philox blocks: block (2*b + KIND, mover m) carries attempts 2b
+// and 2b+1 of mover m), but each lane draws ALL movers of its two attempts and screens them without any shuffle: 64
+// attempts per warp iteration.  The float32 screens (pair distances, wall_screen_f) give one of three verdicts per attempt:
+// certainly rejected / certainly accepted / too close to call.  The first attempt in index order that is accepted wins;
+// a too-close-to-call attempt that comes before any accepted one is decided exactly (float64, confirm_attempt) first.
+// Verdict on ONE attempt that survived the pair screen; lanes 0..G-1 hold its mover m = lane (position x, y as the oracle
+// computes it).  Warp-collective.  pairs_certain: the float32 pair screen already proved that no pair is too close;
+// otherwise the pairs are re-tested exactly (plan:381 / 408-413).  The wall check with the safety offset (plan:379 / 406)
+// is made here for every candidate: float32 screen on the exact position, exact float64 test when too close to call.
+template <int G, bool BOX, int KIND>
+__device__ __forceinline__ bool confirm_attempt(const PlanArgs& a, const Tables& tb, unsigned lane, double x, double y,
+                                                bool pairs_certain, uint32_t eg, uint32_t ev) {
+    const int m = (int)(lane % G);
+    const bool part = lane < (unsigned)G && m < a.N;
+    const int mm = part ? m : 0;
+    const double cw0 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 0], cw1 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 1];
+    bool hit = false;
+    if (G > 1 && !pairs_certain) {  // (uniform branch)
+        const double cs0 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0], cs1 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
+        if (KIND == 0) {
+            if (BOX) {
+                Rect rm;
+                rect_vertices_axis(x, y, cs0, cs1, rm);
+                hit = pair_check<G, true>(lane, m, part, x, y, cs0, cs1, rm, false, 0.0);
+            } else {
+                hit = pair_circle<G, false>(a, lane, m, part, x, y, cs0, 1, eg, ev, 0u);
+            }
+        } else {
+            const unsigned base = lane & ~(unsigned)(G - 1);
+#pragma unroll
+            for (int k = 1; k <= G / 2; ++k) {
+                const int src = (int)(base | (unsigned)((m + k) & (G - 1)));
+                const double ox = __shfl_sync(FULL, x, src), oy = __shfl_sync(FULL, y, src);
+                const bool opart = __shfl_sync(FULL, (int)part, src) != 0;
+                const double dx = dsub(x, ox), dy = dsub(y, oy);
+                if (part && opart && sqrt_lt(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_goal_dist)) hit = true;
+            }
+        }
+    }
+    bool bad = false;
+    if (part) {
+        int gi, gj;
+        guess_cell(a, x, y, gi, gj);
+        float clear;
+        // box shape: the mover's rectangle is axis-aligned here (identity quaternion, no noise), so the rectangle screen
+        // with its own half sizes is exact whenever it is certain (an overlap with a missing cell makes a vertex unsafe
+        // towards a missing neighbour; no overlap leaves nothing for the inner-corner edge test to find)
+        const int f = wall_fast(a, tb, x, y, (float)cw0, BOX ? (float)cw1 : (float)cw0, gi, gj, clear);
+        if (f == 2) {
+            Rect rw;
+            if (BOX) rect_vertices_axis(x, y, cw0, cw1, rw);
+            bad = !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);
+        } else {
+            bad = f == 0;
+        }
+    }
+    return __ballot_sync(FULL, hit || bad) == 0u;
+}
+
+#ifndef GPR_LANES_MAX_G
+#define GPR_LANES_MAX_G 4  // widest lane group sampled with one lane per attempt pair (wider ones: one group per attempt;
+                           // measured on B200: G=8 gains nothing from it — 32 Philox words per lane spill)
+#endif
+template <int G, bool BOX, int KIND>
+__device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables& tb, unsigned lane, uint32_t eg, uint32_t ev,
+                                                 double2& out, bool& failed) {
+    static_assert(G <= 8, "one lane draws all movers: register budget");
+    const int N = a.N;
+    const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
+    const int m_self = (int)(lane % G);
+    // collision sizes with the safety offset (plan:381), as floats for the pair screen
+    float rf[G], sf[G];
+#pragma unroll
+    for (int m = 0; m < G; ++m) {
+        const int mm = m < N ? m : 0;
+        rf[m] = (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0];
+        sf[m] = (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
+    }
+    const float mg = a.pair_mgf[0];
+    const bool uni = KIND == 1 || a.uniform_pairs != 0;
+    const float lo2u = KIND == 1 ? a.goal_lo2f : a.pair_lo2f[1][0], hi2u = KIND == 1 ? a.goal_hi2f : a.pair_hi2f[1][0];
+    bool found = false;
+#pragma unroll 1
+    for (int t0 = 0; t0 < cap && !found; t0 += 64) {
+        const uint32_t blk = (uint32_t)(t0 / 2) + lane;
+        gpr_u32x4 r[G];
+#pragma unroll
+        for (int m = 0; m < G; ++m) {
+            if (m < N) r[m] = gpr_rng_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)KIND, (uint32_t)m);
+            else r[m].v[0] = r[m].v[1] = r[m].v[2] = r[m].v[3] = 0u;
+        }
+        unsigned accb = 0u, uncb = 0u;  // this lane's pair-screen verdicts for its attempts h = 0, 1
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float xf[G], yf[G];
+#pragma unroll
+            for (int m = 0; m < G; ++m) {
+                // (lanes of a group wider than num_movers: park the spare movers far away from everything, no branches)
+                xf[m] = m < N ? fmaf(a.spanxf, (float)r[m].v[2 * h] * 2.3283064365386963e-10f, a.minxf) : 1e8f * (float)(m + 1);
+                yf[m] = m < N ? fmaf(a.spanyf, (float)r[m].v[2 * h + 1] * 2.3283064365386963e-10f, a.minyf) : 0.f;
+            }
+            bool rej = false, unc = false;
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+#pragma unroll
+                for (int j = i + 1; j < G; ++j) {
+                    const float dx = xf[i] - xf[j], dy = yf[i] - yf[j];
+                    if (KIND == 0 && BOX) {
+                        // axis-aligned rectangles: a gap along x or y is a certain miss, overlap along both axes a certain
+                        // hit when all boxes have one size (else containment, which geom:107-138 does not report, is possible)
+                        const float tx = rf[i] + rf[j], ty = sf[i] + sf[j];
+                        const float adx = fabsf(dx), ady = fabsf(dy);
+                        const bool miss = adx > tx + mg || ady > ty + mg;
+                        const bool hitc = uni && adx < tx - mg && ady < ty - mg;
+                        rej = rej || hitc;
+                        unc = unc || (!miss && !hitc);
+                    } else {
+                        const float tt = rf[i] + rf[j];
+                        const float lo2 = uni ? lo2u : (tt > mg ? (tt - mg) * (tt - mg) : -1.f);
+                        const float hi2 = uni ? hi2u : (tt + mg) * (tt + mg);
+                        const float d2 = dx * dx + dy * dy;
+                        rej = rej || d2 < lo2;
+                        unc = unc || !(d2 < lo2 || d2 > hi2);
+                    }
+                }
+            }
+            const bool valid = 2 * (int)blk + h < cap;
+            if (valid && !rej) {
+                if (unc) uncb |= 1u << h;
+                else accb |= 1u << h;
+            }
+        }
+        // ---- candidates in index order (lane-major, h-minor): the first one that also passes the wall check wins
+        unsigned acc0 = __ballot_sync(FULL, accb & 1u), acc1 = __ballot_sync(FULL, accb & 2u);
+        unsigned unc0 = __ballot_sync(FULL, uncb & 1u), unc1 = __ballot_sync(FULL, uncb & 2u);
+        while (!found && (acc0 | acc1 | unc0 | unc1)) {
+            const int l0 = __ffs(acc0 | acc1 | unc0 | unc1) - 1;
+            const unsigned bit = 1u << l0;
+            const int h0 = ((acc0 | unc0) & bit) ? 0 : 1;
+            const bool certain = ((h0 == 0 ? acc0 : acc1) & bit) != 0u;
+            // positions of that attempt -> lane m holds mover m (every lane: m = lane % G, only lanes < G matter)
+            double px = 0.0, py = 0.0;
+#pragma unroll
+            for (int m = 0; m < G; ++m) {
+                const uint32_t wx = __shfl_sync(FULL, h0 ? r[m].v[2] : r[m].v[0], l0);
+                const uint32_t wy = __shfl_sync(FULL, h0 ? r[m].v[3] : r[m].v[1], l0);
+                if (m == m_self) {
+                    px = dadd(a.min_xy[0], dmul(a.span_xy[0], gpr_uniform32(wx)));  // plan:377/405
+                    py = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform32(wy)));
+                }
+            }
+            if (confirm_attempt<G, BOX, KIND>(a, tb, lane, px, py, certain, eg, ev)) {
+                out = make_double2(px, py);
+                found = true;
+            } else if (h0 == 0) {
+                acc0 &= ~bit;
+                unc0 &= ~bit;
+            } else {
+                acc1 &= ~bit;
+                unc1 &= ~bit;
+            }
+        }
+    }
+    if (!found) {
+        // the reference would loop forever (plan:369); keep the last attempt's sample and report the failure
+        double ux, uy;
+        gpr_sample_xy(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE, (uint32_t)KIND, (uint32_t)(cap - 1), (uint32_t)m_self, &ux, &uy);
+        out = make_double2(dadd(a.min_xy[0], dmul(a.span_xy[0], ux)), dadd(a.min_xy[1], dmul(a.span_xy[1], uy)));
+        failed = true;
+    }
+}
+
+// One environment (global index eg, RNG event ev), whole warp: on return EVERY lane holds, for mover m = lane % G, the
+// position of the first accepted attempt (or of the last attempt, with failed = true, if the cap was hit).
+template <int G, bool BOX, int KIND>
+__device__ __forceinline__ void sample_env(const PlanArgs& a, const Tables& tb, unsigned lane, unsigned gmask_, uint32_t eg,
+                                           uint32_t ev, double2& out, bool& failed) {
+    if constexpr (G <= GPR_LANES_MAX_G) {
+        sample_env_lanes<G, BOX, KIND>(a, tb, lane, eg, ev, out, failed);
+    } else {
+        sample_env_groups<G, BOX, KIND>(a, tb, lane, gmask_, eg, ev, out, failed);
     }
 }
 
@@ -684,7 +896,8 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
     // rotation is the sensor noise on the quaternion)
     const float bxf = BOX ? (float)cw0 + a.rot_extf * (float)(cw0 + cw1) : cw0f;
     const float byf = BOX ? (float)cw1 + a.rot_extf * (float)(cw0 + cw1) : cw0f;
-    const float diagf = BOX ? sqrtf((float)cm0 * (float)cm0 + (float)cm1 * (float)cm1) * 1.000001f : 0.f;
+    const float pxf = BOX ? (float)cm0 + a.rot_extf * (float)(cm0 + cm1) : 0.f;  // same for the mover-check sizes
+    const float pyf = BOX ? (float)cm1 + a.rot_extf * (float)(cm0 + cm1) : 0.f;
     float travel = 0.f;                  // sum over cycles of an upper bound of |v|  (distance / dt)
     float lim_w = -1.f, lim_p = -1.f;    // `travel` values up to which the wall / pair check is certified negative
     bool any_alive = __any_sync(FULL, alive);
@@ -693,48 +906,56 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
         const bool part = alive && ln.active;
         float n4[4] = {0.f, 0.f, 0.f, 0.f};
         bool have0 = false;  // block 0 of this cycle generated?
-        if (part) {
-            // plan:420-450 _mujoco_step_callback; d = derivative entering the velocity clip (action or limited acc)
+        // ---- plan:420-450 _mujoco_step_callback + mj_step
+        // Hot path, decided for the whole warp: every mover "free-runs" — neither ensure_max_dyn_val clip can trigger and
+        // the velocity noise (plan:430) cannot matter (|v + dt*a| stays below v_max minus the noise bound), so
+        // ensure_max_dyn_val passes its inputs through: qacc = a (acc mode) or act + dt*j (jerk mode, integrator actuator
+        // with actearly, plan:305-311), qvel += dt*qacc.  The sums below are the very expressions the general path
+        // evaluates (same operands, same two roundings), so both paths produce identical bits.
+        const double nax = a.learn_jerk ? dadd(dmul(a.dt, u.x), acc.x) : u.x;
+        const double nay = a.learn_jerk ? dadd(dmul(a.dt, u.y), acc.y) : u.y;
+        const double tx = dadd(dmul(a.dt, nax), v.x), ty = dadd(dmul(a.dt, nay), v.y);
+        bool free_run = dadd(dmul(tx, tx), dmul(ty, ty)) < (NOISE ? a.v_lazy2 : a.v_max2_lo);
+        if (a.learn_jerk) free_run = free_run && dadd(dmul(nax, nax), dmul(nay, nay)) < a.a_max2_lo;
+        if (!__any_sync(FULL, part && !free_run)) {
+            if (part) {
+                acc.x = nax;
+                acc.y = nay;
+                v.x = tx;
+                v.y = ty;
+            }
+        } else if (part) {
+            // general path; d = derivative entering the velocity clip (action or limited acc)
             double dxv = u.x, dyv = u.y, jx = 0.0, jy = 0.0;
             if (a.learn_jerk) ensure_max(acc.x, acc.y, a.a_max, a.a_max2_lo, u.x, u.y, a.dt, dxv, dyv, jx, jy);  // plan:434
-            // plan:437 / 442 on the noise-free velocity first: below v_lazy2 neither the clip nor the velocity noise
-            // (plan:430) can change anything and ensure_max_dyn_val passes its inputs through
-            const double tx = dadd(dmul(a.dt, dxv), v.x), ty = dadd(dmul(a.dt, dyv), v.y);
-            const bool free_run = dadd(dmul(tx, tx), dmul(ty, ty)) < (NOISE ? a.v_lazy2 : a.v_max2_lo);
-            if (free_run && !a.learn_jerk) {
-                acc.x = dxv;  // dyntype none, gain = mass (plan:314-320): qacc = ctrl
-                acc.y = dyv;
-                v.x = tx;     // == v + dt*qacc (the same two roundings)
-                v.y = ty;
-            } else {
-                double ax = dxv, ay = dyv;
-                if (!free_run) {
-                    double velx = v.x, vely = v.y;
-                    if (NOISE) {
-                        normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
-                        have0 = true;
-                        velx = noisy(v.x, n4[0], a.sigma_v);
-                        vely = noisy(v.y, n4[1], a.sigma_v);
-                    }
-                    double t0, t1;
-                    ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);
+            double velx = v.x, vely = v.y;
+            if (NOISE) {
+                // the velocity noise can only matter if the un-noised |dt*d + v| is within its bound of v_max
+                const double sx = dadd(dmul(a.dt, dxv), v.x), sy = dadd(dmul(a.dt, dyv), v.y);
+                if (!(dadd(dmul(sx, sx), dmul(sy, sy)) < a.v_lazy2)) {
+                    normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
+                    have0 = true;
+                    velx = noisy(v.x, n4[0], a.sigma_v);
+                    vely = noisy(v.y, n4[1], a.sigma_v);
                 }
-                if (a.learn_jerk) {
-                    if (dxv != ax || dyv != ay) {  // plan:438
-                        jx = ddiv(dsub(ax, acc.x), a.dt);
-                        jy = ddiv(dsub(ay, acc.y), a.dt);
-                    }
-                    // mj_step, integrator actuator with actearly (plan:305-311): act += dt*ctrl; qacc = act
-                    acc.x = dadd(acc.x, dmul(a.dt, jx));
-                    acc.y = dadd(acc.y, dmul(a.dt, jy));
-                } else {
-                    acc.x = ax;
-                    acc.y = ay;
-                }
-                // semi-implicit Euler (MuJoCo): qvel += dt*qacc
-                v.x = dadd(v.x, dmul(a.dt, acc.x));
-                v.y = dadd(v.y, dmul(a.dt, acc.y));
             }
+            double t0, t1, ax, ay;
+            ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);  // plan:437 / 442
+            if (a.learn_jerk) {
+                if (dxv != ax || dyv != ay) {  // plan:438
+                    jx = ddiv(dsub(ax, acc.x), a.dt);
+                    jy = ddiv(dsub(ay, acc.y), a.dt);
+                }
+                acc.x = dadd(acc.x, dmul(a.dt, jx));  // act += dt*ctrl; qacc = act
+                acc.y = dadd(acc.y, dmul(a.dt, jy));
+            } else {
+                acc.x = ax;  // dyntype none, gain = mass (plan:314-320): qacc = ctrl
+                acc.y = ay;
+            }
+            v.x = dadd(v.x, dmul(a.dt, acc.x));  // semi-implicit Euler (MuJoCo): qvel += dt*qacc
+            v.y = dadd(v.y, dmul(a.dt, acc.y));
+        }
+        if (part) {
             p.x = dadd(p.x, dmul(a.dt, v.x));  // qpos += dt*qvel
             p.y = dadd(p.y, dmul(a.dt, v.y));
             // |v| <= max + min/2 of the absolute components; 1e-4 covers the float roundings of the running sum
@@ -785,9 +1006,9 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
                 hit = pair_circle_fast<G, NOISE>(a, ln.lane, ln.m, part, p.x, p.y, cm0, 0, ln.env_global, event,
                                                  s0 + GPR_RNG_BLOCK_MOVER, clear_p);
             } else {
-                // bounding-circle screen; the exact rectangle test of geom:107-138 only for a warp with an uncleared pair
+                // axis-gap screen; the exact rectangle test of geom:107-138 only for a warp with an uncleared pair
                 bool near;
-                pair_box_screen<G>(ln.lane, ln.m, part, p.x, p.y, diagf, a.pair_mgf[NOISE ? 1 : 0], near, clear_p);
+                pair_box_screen<G>(ln.lane, ln.m, part, p.x, p.y, pxf, pyf, a.pair_mgf[NOISE ? 1 : 0], near, clear_p);
                 if (__any_sync(FULL, near)) {
                     double mx = p.x, my = p.y;
                     Rect rm;

@@ -171,39 +171,92 @@ __device__ __forceinline__ void push_store_obs(const PushArgs& a, int e, float* 
     if (DG) reinterpret_cast<float2*>(DG)[e] = make_float2((float)goal.x, (float)goal.y);
 }
 
-// push:373-417 + basic:1797-1805 for one env. Returns true if the object rejection loop hit the cap.
-template <bool BOX, bool NOISE>
-__device__ __forceinline__ bool push_reset_one(const PushArgs& a, const Tables& tb, PushState& s, uint32_t env_global,
-                                               uint32_t event, const double2* inj_start, const double2* inj_goal,
-                                               const double2* inj_object, int e, bool& wc) {
+// push:373-417 + basic:1797-1805, split in three stages so that the object-placement loop (push:392-407) can be shared by
+// the warp: acceptance is ~75% per draw on average, but a mover spawned near the layout centre leaves only a sliver (or
+// nothing) of the object box outside min_mo_dist, and one lane looping thousands of draws would stall its whole warp.
+//   stage A (lane-local)      : mover start, the first kSeqDraws object draws
+//   stage B (warp-collective) : for every lane still without an accepted draw, all 32 lanes test 32 consecutive draws at
+//                               once; the lowest accepted index wins — exactly the sequential loop's result
+//   stage C (lane-local)      : goal, fresh MjData, reset-time wall check
+constexpr int kSeqDraws = 4;
+
+__device__ __forceinline__ bool push_object_draw(const PushArgs& a, uint32_t env_global, uint32_t event, int t, double mx,
+                                                 double my, double& ox, double& oy) {
     double ux, uy;
+    gpr_sample_xy(a.seed, env_global, event, GPR_RNG_RESET_OBJECT, 0u, (uint32_t)t, 0u, &ux, &uy);
+    ox = dadd(a.obj_min[0], dmul(a.obj_span[0], ux));
+    oy = dadd(a.obj_min[1], dmul(a.obj_span[1], uy));
+    const double dx = dsub(ox, mx), dy = dsub(oy, my);
+    return !sqrt_le(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_mo_dist);  // push:407 strict '>'
+}
+
+// stage A.  Returns true when the object position is settled (injected or accepted).
+__device__ __forceinline__ bool push_reset_a(const PushArgs& a, PushState& s, uint32_t env_global, uint32_t event,
+                                             const double2* inj_start, const double2* inj_object, int e) {
     if (inj_start) {
         s.M.x = inj_start[e].x;
         s.M.y = inj_start[e].y;
     } else {  // push:387-389
+        double ux, uy;
         gpr_sample_xy(a.seed, env_global, event, GPR_RNG_RESET_SAMPLE, 0u, 0u, 0u, &ux, &uy);
         s.M.x = dadd(a.min_xy[0], dmul(a.span_xy[0], ux));
         s.M.y = dadd(a.min_xy[1], dmul(a.span_xy[1], uy));
     }
-    bool failed = false;
     if (inj_object) {
         s.O.x = inj_object[e].x;
         s.O.y = inj_object[e].y;
-    } else {  // push:392-404: redraw until the object is farther than min_mo_dist from the mover (strict '>')
-        const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
-        bool ok = false;
-        for (int t = 0; t < cap && !ok; ++t) {
-            gpr_sample_xy(a.seed, env_global, event, GPR_RNG_RESET_OBJECT, 0u, (uint32_t)t, 0u, &ux, &uy);
-            s.O.x = dadd(a.obj_min[0], dmul(a.obj_span[0], ux));
-            s.O.y = dadd(a.obj_min[1], dmul(a.obj_span[1], uy));
-            const double dx = dsub(s.O.x, s.M.x), dy = dsub(s.O.y, s.M.y);
-            ok = !sqrt_le(dadd(dmul(dx, dx), dmul(dy, dy)), a.min_mo_dist);
-        }
-        failed = !ok;
+        return true;
     }
+    const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
+    bool ok = false;
+    for (int t = 0; t < kSeqDraws && t < cap && !ok; ++t) ok = push_object_draw(a, env_global, event, t, s.M.x, s.M.y, s.O.x, s.O.y);
+    return ok;
+}
+
+// stage B, warp-collective: EVERY lane of the warp must call it.  pend: this lane still needs an object position.
+// Returns true (for a pending lane) if the loop ran out of attempts (the last draw is kept, like the oracle does).
+__device__ __forceinline__ bool push_reset_b(const PushArgs& a, PushState& s, uint32_t env_global, uint32_t event, bool pend) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
+    bool failed = false;
+    unsigned todo = __ballot_sync(FULL, pend);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t eg = __shfl_sync(FULL, env_global, leader), ev = __shfl_sync(FULL, event, leader);
+        const double mx = __shfl_sync(FULL, s.M.x, leader), my = __shfl_sync(FULL, s.M.y, leader);
+        bool found = false;
+        double wx = 0.0, wy = 0.0;
+        for (int t0 = kSeqDraws; t0 < cap && !found; t0 += 32) {
+            const int t = t0 + (int)lane;
+            double ox, oy;
+            const bool acc = t < cap && push_object_draw(a, eg, ev, t, mx, my, ox, oy);
+            const unsigned accm = __ballot_sync(FULL, acc);
+            if (accm) {
+                const int win = __ffs(accm) - 1;
+                wx = __shfl_sync(FULL, ox, win);
+                wy = __shfl_sync(FULL, oy, win);
+                found = true;
+            }
+        }
+        if (!found) push_object_draw(a, eg, ev, cap - 1, mx, my, wx, wy);  // keep the last draw (uniform across lanes)
+        if ((int)lane == leader) {
+            s.O.x = wx;
+            s.O.y = wy;
+            failed = !found;
+        }
+    }
+    return failed;
+}
+
+// stage C
+template <bool BOX, bool NOISE>
+__device__ __forceinline__ void push_reset_c(const PushArgs& a, const Tables& tb, PushState& s, uint32_t env_global,
+                                             uint32_t event, const double2* inj_goal, int e, bool& wc) {
     if (inj_goal) {
         s.goal = inj_goal[e];
     } else {  // push:409-411
+        double ux, uy;
         gpr_sample_xy(a.seed, env_global, event, GPR_RNG_RESET_OBJECT, 1u, 0u, 0u, &ux, &uy);
         s.goal.x = dadd(a.obj_min[0], dmul(a.obj_span[0], ux));
         s.goal.y = dadd(a.obj_min[1], dmul(a.obj_span[1], uy));
@@ -221,7 +274,6 @@ __device__ __forceinline__ bool push_reset_one(const PushArgs& a, const Tables& 
     float n4[4] = {0.f, 0.f, 0.f, 0.f};
     if (NOISE) gpr_normal4(a.seed, env_global, event, GPR_RNG_RESET_CHECK, 0u, n4);
     wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 1, n4[0], n4[1], env_global, event, GPR_RNG_RESET_CHECK_WQUAT);
-    return failed;
 }
 
 __device__ __forceinline__ void push_reward(bool reached, bool wc, float& reward, bool& term, bool& succ) {
@@ -236,19 +288,26 @@ __global__ void __launch_bounds__(128) pushing_step_kernel(const __grid_constant
     load_tables(tb, a.L);
     __syncthreads();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.B) return;
+    const bool valid = e < a.B;  // (no early return: the reset's stage B is warp-collective)
     const uint32_t env_global = a.env_base + (uint32_t)e;
     PushState s;
-    push_load(a, e, s);
-    uint32_t event = a.rng[e];
-    int elapsed = a.elapsed[e];
-    const bool pending = a.autoreset == GPR_AUTORESET_NEXT_STEP && a.needs_reset[e] != 0;
+    memset(&s, 0, sizeof(s));
+    uint32_t event = 0;
+    int elapsed = 0;
+    bool pending = false;
+    if (valid) {
+        push_load(a, e, s);
+        event = a.rng[e];
+        elapsed = a.elapsed[e];
+        pending = a.autoreset == GPR_AUTORESET_NEXT_STEP && a.needs_reset[e] != 0;
+    }
     double obs[6] = {0, 0, 0, 0, 0, 0};
     double2 ag = make_double2(0, 0);
     bool reached = false;
     float reward = 0.f;
     bool term = false, succ = false, wc = false;
-    if (!pending) {
+    const bool stepped = valid && !pending;
+    if (stepped) {
         const float2 af = a.action[e];
         const double ux = fmin(fmax((double)af.x, -a.act_lim), a.act_lim);  // basic:1869-1873
         const double uy = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
@@ -291,7 +350,6 @@ __global__ void __launch_bounds__(128) pushing_step_kernel(const __grid_constant
         event += 1u;
         elapsed += 1;
     }
-    const bool stepped = !pending;
     const bool trunc = stepped && a.max_episode_steps > 0 && elapsed >= a.max_episode_steps;
     const bool done = stepped && (term || trunc);
     if (stepped) {
@@ -311,12 +369,18 @@ __global__ void __launch_bounds__(128) pushing_step_kernel(const __grid_constant
         if (a.out.mover_collision) a.out.mover_collision[e] = 0;
         if (a.out.wall_collision) a.out.wall_collision[e] = wc;
     }
-    const bool need = (a.autoreset == GPR_AUTORESET_SAME_STEP && done) || pending;
+    // ---- auto-reset (push:373-417), stages A / B / C
+    const bool need = valid && ((a.autoreset == GPR_AUTORESET_SAME_STEP && done) || pending);
+    bool settled = true;
     if (need) {
         if (a.autoreset == GPR_AUTORESET_SAME_STEP)
             push_store_obs(a, e, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, obs, ag, s.goal);
+        settled = push_reset_a(a, s, env_global, event, nullptr, nullptr, e);
+    }
+    const bool failed = push_reset_b(a, s, env_global, event, need && !settled);
+    if (need) {
         bool rwc;
-        const bool failed = push_reset_one<BOX, NOISE>(a, tb, s, env_global, event, nullptr, nullptr, nullptr, e, rwc);
+        push_reset_c<BOX, NOISE>(a, tb, s, env_global, event, nullptr, e, rwc);
         push_observe<NOISE>(a, s, env_global, event, obs, ag, reached);
         event += 1u;
         elapsed = 0;
@@ -333,6 +397,7 @@ __global__ void __launch_bounds__(128) pushing_step_kernel(const __grid_constant
             if (a.out.wall_collision) a.out.wall_collision[e] = rwc;
         }
     }
+    if (!valid) return;
     push_store_obs(a, e, a.out.observation, a.out.achieved_goal, a.out.desired_goal, obs, ag, s.goal);
     push_store(a, e, s);
     a.rng[e] = event;
@@ -346,13 +411,20 @@ __global__ void __launch_bounds__(128) pushing_reset_kernel(const __grid_constan
     load_tables(tb, a.L);
     __syncthreads();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.B) return;
-    if (a.reset_mask && !a.reset_mask[e]) return;
+    const bool need = e < a.B && !(a.reset_mask && !a.reset_mask[e]);
     const uint32_t env_global = a.env_base + (uint32_t)e;
     PushState s;
-    const uint32_t event = a.rng[e];
+    memset(&s, 0, sizeof(s));
+    uint32_t event = 0;
+    bool settled = true;
+    if (need) {
+        event = a.rng[e];
+        settled = push_reset_a(a, s, env_global, event, a.inject_start, a.inject_object, e);
+    }
+    const bool failed = push_reset_b(a, s, env_global, event, need && !settled);
+    if (!need) return;
     bool wc;
-    const bool failed = push_reset_one<BOX, NOISE>(a, tb, s, env_global, event, a.inject_start, a.inject_goal, a.inject_object, e, wc);
+    push_reset_c<BOX, NOISE>(a, tb, s, env_global, event, a.inject_goal, e, wc);
     double obs[6];
     double2 ag;
     bool reached;

@@ -266,6 +266,14 @@ class BatchedCore:
             all_reduce_stats(out)
         return stats_dict(out.tolist())
 
+    def kernel_times(self, enable: bool = True) -> dict[str, float]:
+        """Per-kernel device time of the ``step`` calls since the last query (``gpr_kernel_times``): CUDA events recorded
+        around each kernel on the launching stream.  The first call just switches the recording on."""
+        out = (ctypes.c_double * 3)()
+        _lib.check(self.lib.gpr_kernel_times(self.handle, int(enable), out))
+        n = max(out[2], 1.0)
+        return {'steps': out[2], 'step_kernel_ms': out[0] / n, 'autoreset_kernel_ms': out[1] / n}
+
     def reset_failures(self) -> int:
         c = ctypes.c_uint32()
         _lib.check(self.lib.gpr_reset_failures(self.handle, ctypes.byref(c)))

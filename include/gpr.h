@@ -232,6 +232,12 @@ GPR_API int gpr_episode_stats(gpr_handle* h, double* dst, int reset_after, void*
 /* Number of resets whose rejection-sampling loop hit max_reset_attempts since creation (synchronous D2H read). */
 GPR_API int gpr_reset_failures(gpr_handle* h, uint32_t* host_count);
 
+/* Per-kernel device times of gpr_step (measurement aid, off by default).  enable != 0: every following gpr_step brackets
+ * its kernels with CUDA events on the caller's stream.  host_ms (may be NULL) receives, after synchronising those events,
+ * [0] total ms of the step kernel, [1] total ms of the auto-reset kernel, [2] number of gpr_step calls covered, and the
+ * accumulation restarts.  enable == 0 stops recording. */
+GPR_API int gpr_kernel_times(gpr_handle* h, int enable, double* host_ms);
+
 /* Number of kernels this library has launched on behalf of the handle (bench "gpu_launches" evidence). */
 GPR_API uint64_t gpr_launch_count(const gpr_handle* h);
 

@@ -48,6 +48,7 @@ typedef struct gpr_push_params {
     double k_rot, d_rot;          /* yaw impedance: stiffness, damping */
     double sol_B, sol_K;          /* B = 2/(dmax tc), K = 1/(dmax^2 tc^2 dr^2) */
     double imp_d0, imp_dw, imp_width, imp_mid, imp_power;
+    double contact_r2; /* (sum of the two circumradii * 1.0001)^2: centres farther apart cannot touch */
     int iterations;
 } gpr_push_params;
 
@@ -76,6 +77,11 @@ static inline void gpr_push_params_from_config(const gpr_config* c, gpr_push_par
     P->imp_mid = c->solimp[3];
     P->imp_power = c->solimp[4];
     P->iterations = c->contact_iterations;
+    {
+        const double rm = sqrt(c->mover_half[0] * c->mover_half[0] + c->mover_half[1] * c->mover_half[1]);
+        const double ro = sqrt(2.0 * c->object_half_xy * c->object_half_xy);
+        P->contact_r2 = ((rm + ro) * 1.0001) * ((rm + ro) * 1.0001);
+    }
 }
 
 typedef struct gpr_body2 {
@@ -260,7 +266,10 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
     double aO[3] = {-P->obj_damping * O->vx * imO, -P->obj_damping * O->vy * imO, -P->obj_damping * O->w * iIO};
 
     gpr_contact2 ct[2];
-    const int nc = gpr_box_box(M, P->mover_hx, P->mover_hy, O, P->obj_h, ct);
+    /* boxes whose centres are farther apart than the sum of their circumradii are separated (the separating-axis test
+     * below would say so too): skip the manifold computation */
+    const double cdx = O->x - M->x, cdy = O->y - M->y;
+    const int nc = (cdx * cdx + cdy * cdy > P->contact_r2) ? 0 : gpr_box_box(M, P->mover_hx, P->mover_hy, O, P->obj_h, ct);
     const int obj_moving = (O->vx != 0.0) || (O->vy != 0.0) || (O->w != 0.0);
     double fO[3] = {0.0, 0.0, 0.0}, fM[3] = {0.0, 0.0, 0.0}; /* accumulated constraint wrenches */
 
