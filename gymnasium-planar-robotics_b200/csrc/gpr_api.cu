@@ -427,6 +427,15 @@ static PushArgs push_args(const gpr_handle* h, const gpr_outputs* out) {
         for (int sft = 0; sft < 2; ++sft) a.c_wall[sft][k] = c.c_wall[sft][0][k];
     }
     a.min_mo_dist = c.min_mo_dist;
+    {
+        // lazy-noise / float-screen constants, the same construction as in plan_args
+        const double vb = 6.0 * c.std_noise[1] + 1e-12;
+        a.v_lazy2 = (c.v_max - vb) > 0.0 ? (c.v_max - vb) * (c.v_max - vb) * (1.0 - 1e-14) : -1.0;
+        a.wxf = (float)(2.0 * c.tile_half[0]);
+        a.wyf = (float)(2.0 * c.tile_half[1]);
+        a.wall_delta = (float)((h->noise ? 6.0 * c.std_noise[0] * 1.01 : 0.0) + 1e-5 * std::max(2.0 * c.tile_half[0], 2.0 * c.tile_half[1]));
+        a.inv_dtf = (float)((1.0 / c.cycle_time) * (1.0 - 1e-6));
+    }
     a.sigma_p = c.std_noise[0];
     a.sigma_v = c.std_noise[1];
     a.sigma_obj = c.object_noise_xy;

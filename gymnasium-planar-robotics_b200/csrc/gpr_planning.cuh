@@ -179,7 +179,8 @@ GPR_COLD(GPR_INL_PAIR) bool pair_circle(const PlanArgs& a, unsigned lane, int m,
 // neighbour, an unsafe corner also the diagonal one), so the clearance is the smallest L-infinity gap between the
 // rectangle and a missing cell of the 3x3 neighbourhood, capped by the gap to the ring beyond it (>= tile width - c),
 // minus wall_delta.  It does not depend on how close the verdict of THIS cycle was.
-__device__ __forceinline__ int wall_core(const PlanArgs& a, const Tables& tb, float fx, float fy, float cx, float cy, int gi,
+template <class Args>  // PlanArgs or PushArgs: needs wxf, wyf, wall_delta, L
+__device__ __forceinline__ int wall_core(const Args& a, const Tables& tb, float fx, float fy, float cx, float cy, int gi,
                                          int gj, float& clear) {
     const float wc = a.wxf - cx, hc = a.wyf - cy;
     const float gw = fx - cx, ge = wc - fx, gs = fy - cy, gn = hc - fy;  // gaps to the W / E columns and S / N rows
@@ -202,7 +203,8 @@ __device__ __forceinline__ int wall_core(const PlanArgs& a, const Tables& tb, fl
     const uint32_t u = (gw < 0.f ? 1u : 0u) | (ge < 0.f ? 2u : 0u) | (gs < 0.f ? 4u : 0u) | (gn < 0.f ? 8u : 0u);
     return ((code & CELL_3X3) || sides_ok(u, code)) ? 1 : 0;
 }
-__device__ __forceinline__ int wall_fast(const PlanArgs& a, const Tables& tb, double x, double y, float cx, float cy, int gi,
+template <class Args>
+__device__ __forceinline__ int wall_fast(const Args& a, const Tables& tb, double x, double y, float cx, float cy, int gi,
                                          int gj, float& clear) {
     return wall_core(a, tb, (float)dsub(x, tb.xlo[gi]), (float)dsub(y, tb.ylo[gj]), cx, cy, gi, gj, clear);
 }
@@ -215,7 +217,8 @@ __device__ __forceinline__ int wall_screen_f(const PlanArgs& a, const Tables& tb
     return wall_core(a, tb, xf - tb.xlof[gi], yf - tb.ylof[gj], cx, cy, gi, gj, clear);
 }
 
-__device__ __forceinline__ void guess_cell(const PlanArgs& a, double x, double y, int& gi, int& gj) {
+template <class Args>
+__device__ __forceinline__ void guess_cell(const Args& a, double x, double y, int& gi, int& gj) {
     gi = min(max(__double2int_rd(dmul(x, a.L.inv_wx)), 0), a.L.nx - 1);
     gj = min(max(__double2int_rd(dmul(y, a.L.inv_wy)), 0), a.L.ny - 1);
 }

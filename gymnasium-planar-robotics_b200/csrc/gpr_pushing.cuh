@@ -13,6 +13,7 @@
 
 #include "../../include/gpr_push_physics.h"
 #include "gpr_device.cuh"
+#include "gpr_planning.cuh"  // wall_core / wall_fast / guess_cell / normal4_cold
 
 namespace gpr {
 
@@ -29,6 +30,8 @@ struct PushArgs {
     double min_mo_dist;                    // push:279-288, strict '>' accepts
     double sigma_p, sigma_v, sigma_obj;    // sensor noise; object position noise 1e-5 (push:178)
     double c_wall[2][2];                   // [safety][xy] mover collision size incl. offsets (basic:487)
+    double v_lazy2;                        // (v_max - velocity-noise bound)^2: below it neither clip nor noise matters
+    float wxf, wyf, wall_delta, inv_dtf;   // float32 wall screen (see wall_core) and travel budget, as in PlanArgs
     LayoutArgs L;
     gpr_push_params P;
     // state (SoA, float64)
@@ -282,13 +285,44 @@ __device__ __forceinline__ void push_reward(bool reached, bool wc, float& reward
     succ = reached && !wc;                          // push:602
 }
 
+// ---- the env-step kernel -------------------------------------------------------------------------------------------------
+// Per cycle a lane is either FREE (object at rest and out of the mover's reach: gpr_push_substep reduces to integrating the
+// mover, ~60 instructions) or in the CONTACT regime (manifold + 8 projected Gauss-Seidel sweeps, thousands of float64
+// instructions).  With random actions ~20% of the envs are in the contact regime at any time, i.e. nearly every warp would
+// execute the long path with a handful of active lanes.  The kernel therefore COMPACTS them: contact lanes queue their
+// inputs in shared memory, the first `count` threads of the CTA run gpr_push_substep on the queue with full warps, and the
+// owners read their results back.  gpr_push_substep is a pure function of its inputs, so this changes no result bit.
+constexpr int kPushCta = 128;
+constexpr int kPushFields = 16;  // mover (7) + object (7) + commanded acceleration (2); results reuse the slots
+
+__device__ __forceinline__ void push_q_put(double (*q)[kPushCta], int slot, const gpr_body2& M, const gpr_body2& O, double a0,
+                                           double a1) {
+    q[0][slot] = M.x;  q[1][slot] = M.y;  q[2][slot] = M.c;  q[3][slot] = M.s;  q[4][slot] = M.vx;  q[5][slot] = M.vy;  q[6][slot] = M.w;
+    q[7][slot] = O.x;  q[8][slot] = O.y;  q[9][slot] = O.c;  q[10][slot] = O.s; q[11][slot] = O.vx; q[12][slot] = O.vy; q[13][slot] = O.w;
+    q[14][slot] = a0;  q[15][slot] = a1;
+}
+__device__ __forceinline__ void push_q_get(double (*q)[kPushCta], int slot, gpr_body2& M, gpr_body2& O, double& a0, double& a1) {
+    M.x = q[0][slot];  M.y = q[1][slot];  M.c = q[2][slot];  M.s = q[3][slot];  M.vx = q[4][slot];  M.vy = q[5][slot];  M.w = q[6][slot];
+    O.x = q[7][slot];  O.y = q[8][slot];  O.c = q[9][slot];  O.s = q[10][slot]; O.vx = q[11][slot]; O.vy = q[12][slot]; O.w = q[13][slot];
+    a0 = q[14][slot];  a1 = q[15][slot];
+}
+
+#ifndef GPR_PUSH_MINB
+#define GPR_PUSH_MINB 4
+#endif
+#ifndef GPR_PUSH_SPREAD
+#define GPR_PUSH_SPREAD 0
+#endif
 template <bool BOX, bool NOISE>
-__global__ void __launch_bounds__(128) pushing_step_kernel(const __grid_constant__ PushArgs a) {
+__global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(const __grid_constant__ PushArgs a) {
     __shared__ Tables tb;
+    __shared__ double q[kPushFields][kPushCta];
+    __shared__ int q_count;
     load_tables(tb, a.L);
+    if (threadIdx.x == 0) q_count = 0;
     __syncthreads();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = e < a.B;  // (no early return: the reset's stage B is warp-collective)
+    const bool valid = e < a.B;  // (no early return: barriers and the reset's stage B are collective)
     const uint32_t env_global = a.env_base + (uint32_t)e;
     PushState s;
     memset(&s, 0, sizeof(s));
@@ -307,44 +341,119 @@ __global__ void __launch_bounds__(128) pushing_step_kernel(const __grid_constant
     float reward = 0.f;
     bool term = false, succ = false, wc = false;
     const bool stepped = valid && !pending;
+    double ux = 0.0, uy = 0.0;
     if (stepped) {
         const float2 af = a.action[e];
-        const double ux = fmin(fmax((double)af.x, -a.act_lim), a.act_lim);  // basic:1869-1873
-        const double uy = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
-        for (int cyc = 0; cyc < a.num_cycles; ++cyc) {  // basic:1879
-            float n4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (NOISE) gpr_normal4(a.seed, env_global, event, (uint32_t)cyc * 4u + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
-            // push:419-455 _mujoco_step_callback
-            double velx = s.M.vx, vely = s.M.vy;
-            if (NOISE) {
-                velx = dadd(velx, dmul((double)n4[0], a.sigma_v));
-                vely = dadd(vely, dmul((double)n4[1], a.sigma_v));
-            }
-            double cx, cy, t0, t1;
-            if (a.learn_jerk) {
-                double atx, aty, jx, jy, ax, ay;
-                ensure_max(s.acc.x, s.acc.y, a.a_max, a.a_max2_lo, ux, uy, a.dt, atx, aty, jx, jy);  // push:432 (acc = real qacc)
-                ensure_max(velx, vely, a.v_max, a.v_max2_lo, atx, aty, a.dt, t0, t1, ax, ay);        // push:435
-                if (atx != ax || aty != ay) {                                                        // push:436
-                    jx = ddiv(dsub(ax, s.acc.x), a.dt);
-                    jy = ddiv(dsub(ay, s.acc.y), a.dt);
+        ux = fmin(fmax((double)af.x, -a.act_lim), a.act_lim);  // basic:1869-1873
+        uy = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
+    }
+    // circle shape: wall check with a travel budget exactly as in planning_step_kernel (certified clearance, wall_core)
+    int gi = 0, gj = 0;
+    guess_cell(a, s.M.x, s.M.y, gi, gj);
+    const float cwf = (float)a.c_wall[0][0];
+    float travel = 0.f, lim_w = -1.f;
+    bool active = stepped;
+    for (int cyc = 0; cyc < a.num_cycles; ++cyc) {  // basic:1879
+        if (!__syncthreads_or(active)) break;        // (also separates the queue uses of consecutive cycles)
+        const uint32_t s0 = (uint32_t)cyc * 4u;
+        float n4[4] = {0.f, 0.f, 0.f, 0.f};
+        bool have0 = false;
+        bool queued = false;
+        int slot = 0;
+        if (active) {
+            // push:419-455 _mujoco_step_callback; the velocity noise (push:428) is generated only where it can matter
+            double cx, cy;
+            {
+                double dxv = ux, dyv = uy, jx = 0.0, jy = 0.0;
+                if (a.learn_jerk) ensure_max(s.acc.x, s.acc.y, a.a_max, a.a_max2_lo, ux, uy, a.dt, dxv, dyv, jx, jy);  // push:432 (real qacc)
+                double velx = s.M.vx, vely = s.M.vy;
+                if (NOISE) {
+                    const double sx = dadd(dmul(a.dt, dxv), s.M.vx), sy = dadd(dmul(a.dt, dyv), s.M.vy);
+                    if (BOX || !(dadd(dmul(sx, sx), dmul(sy, sy)) < a.v_lazy2)) {
+                        normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
+                        have0 = true;
+                        velx = dadd(velx, dmul((double)n4[0], a.sigma_v));
+                        vely = dadd(vely, dmul((double)n4[1], a.sigma_v));
+                    }
                 }
-                // integrator actuator with actearly (push:305-311): act += dt*ctrl, force uses the new act
-                s.act.x = dadd(s.act.x, dmul(a.dt, jx));
-                s.act.y = dadd(s.act.y, dmul(a.dt, jy));
-                cx = s.act.x;
-                cy = s.act.y;
-            } else {
-                ensure_max(velx, vely, a.v_max, a.v_max2_lo, ux, uy, a.dt, t0, t1, cx, cy);  // push:440
+                double t0, t1, ax, ay;
+                ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);  // push:435 / 440
+                if (a.learn_jerk) {
+                    if (dxv != ax || dyv != ay) {  // push:436
+                        jx = ddiv(dsub(ax, s.acc.x), a.dt);
+                        jy = ddiv(dsub(ay, s.acc.y), a.dt);
+                    }
+                    // integrator actuator with actearly (push:305-311): act += dt*ctrl, force uses the new act
+                    s.act.x = dadd(s.act.x, dmul(a.dt, jx));
+                    s.act.y = dadd(s.act.y, dmul(a.dt, jy));
+                    cx = s.act.x;
+                    cy = s.act.y;
+                } else {
+                    cx = ax;
+                    cy = ay;
+                }
             }
-            double qax, qay;
-            gpr_push_substep(&a.P, &s.M, &s.O, cx, cy, &qax, &qay);  // mj_step (basic:1882)
-            s.acc = make_double2(qax, qay);
-            // basic:1888-1894 wall check; no mover-mover check with one mover; push:607 asserts no mover collision
-            wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 0, n4[2], n4[3], env_global, event,
-                                           (uint32_t)cyc * 4u + GPR_RNG_BLOCK_WALL_QUAT);
-            if (wc) break;  // basic:1904
+            // mj_step (basic:1882): contact regime -> queue, free regime -> in place
+            const double ddx = s.O.x - s.M.x, ddy = s.O.y - s.M.y;
+            const bool contact = !(ddx * ddx + ddy * ddy > a.P.contact_r2) || s.O.vx != 0.0 || s.O.vy != 0.0 || s.O.w != 0.0;
+            if (contact) {
+                slot = atomicAdd(&q_count, 1);
+                push_q_put(q, slot, s.M, s.O, cx, cy);
+                queued = true;
+            } else {
+                double qax, qay;
+                gpr_push_substep(&a.P, &s.M, &s.O, cx, cy, &qax, &qay);
+                s.acc = make_double2(qax, qay);
+            }
         }
+        __syncthreads();
+        {
+            // queue item i -> lane i / W of warp i % W (W warps per CTA): the items fill the low lanes of ALL warps, so the
+            // long dependent float64 chains of the contact solve overlap across W warps per CTA instead of one
+            // (GPR_PUSH_SPREAD=0: item i -> thread i, the densest packing)
+            const int n = q_count;
+            constexpr int W = kPushCta / 32;
+            const int item = GPR_PUSH_SPREAD ? (int)(threadIdx.x & 31u) * W + (int)(threadIdx.x >> 5) : (int)threadIdx.x;
+            if (item < n) {
+                gpr_body2 M, O;
+                double a0, a1, qax, qay;
+                push_q_get(q, item, M, O, a0, a1);
+                gpr_push_substep(&a.P, &M, &O, a0, a1, &qax, &qay);
+                push_q_put(q, item, M, O, qax, qay);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) q_count = 0;
+        if (queued) {
+            double qax, qay;
+            push_q_get(q, slot, s.M, s.O, qax, qay);
+            s.acc = make_double2(qax, qay);
+        }
+        if (active) {
+            // basic:1888-1894 wall check; no mover-mover check with one mover; push:607 asserts no mover collision
+            if (BOX) {
+                if (NOISE && !have0) normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
+                wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 0, n4[2], n4[3], env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT);
+            } else {
+                const float avx = fabsf((float)s.M.vx), avy = fabsf((float)s.M.vy);
+                travel += (fmaxf(avx, avy) + 0.5f * fminf(avx, avy)) * 1.0001f;
+                if (!(travel < lim_w)) {
+                    float clear_w;
+                    const int f = wall_fast(a, tb, s.M.x, s.M.y, cwf, cwf, gi, gj, clear_w);
+                    if (f == 2) {  // too close to call in float32: the exact check on the noisy position
+                        if (NOISE && !have0) normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
+                        wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 0, n4[2], n4[3], env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT);
+                        guess_cell(a, s.M.x, s.M.y, gi, gj);
+                    } else {
+                        wc = f == 0;
+                    }
+                    lim_w = (travel + clear_w * a.inv_dtf) * 0.999999f;
+                }
+            }
+            if (wc) active = false;  // basic:1904
+        }
+    }
+    if (stepped) {
         push_observe<NOISE>(a, s, env_global, event, obs, ag, reached);
         push_reward(reached, wc, reward, term, succ);
         event += 1u;

@@ -49,6 +49,9 @@ typedef struct gpr_push_params {
     double sol_B, sol_K;          /* B = 2/(dmax tc), K = 1/(dmax^2 tc^2 dr^2) */
     double imp_d0, imp_dw, imp_width, imp_mid, imp_power;
     double contact_r2; /* (sum of the two circumradii * 1.0001)^2: centres farther apart cannot touch */
+    double g_R, g_inv; /* ground-friction rows: regulariser R and 1 / (A + R) — the same for all four corners */
+    double g_lim;      /* friction limit per corner: mu * m g / 4 */
+    double o_inv_lin, o_inv_rot; /* 1 / (m + dt D), 1 / (I + dt D): implicit joint damping of the object */
     int iterations;
 } gpr_push_params;
 
@@ -82,6 +85,15 @@ static inline void gpr_push_params_from_config(const gpr_config* c, gpr_push_par
         const double ro = sqrt(2.0 * c->object_half_xy * c->object_half_xy);
         P->contact_r2 = ((rm + ro) * 1.0001) * ((rm + ro) * 1.0001);
     }
+    {
+        /* a corner sits at distance sqrt(2) h from the centre; isotropic diagonal approximation of its inverse inertia */
+        const double Ag = 1.0 / P->obj_mass + (2.0 * P->obj_h * P->obj_h) * (1.0 / P->obj_inertia) * 0.5;
+        P->g_R = (1.0 - P->imp_d0) / P->imp_d0 * Ag;
+        P->g_inv = 1.0 / (Ag + P->g_R);
+        P->g_lim = P->mu * (P->obj_mass * P->gravity * 0.25);
+    }
+    P->o_inv_lin = 1.0 / (P->obj_mass + P->dt * P->obj_damping);
+    P->o_inv_rot = 1.0 / (P->obj_inertia + P->dt * P->obj_damping);
 }
 
 typedef struct gpr_body2 {
@@ -114,9 +126,9 @@ GPR_PHD void gpr_push_rotate(double* c, double* s, double a) {
     double sa = a - (a * a) * a * (1.0 / 6.0);
     double nc = (*c) * ca - (*s) * sa;
     double ns = (*s) * ca + (*c) * sa;
-    double n = sqrt(nc * nc + ns * ns);
-    *c = nc / n;
-    *s = ns / n;
+    double inv = 1.0 / sqrt(nc * nc + ns * ns);
+    *c = nc * inv;
+    *s = ns * inv;
 }
 
 /* yaw from (c, s) for small angles: asin series (|yaw| < 0.5 rad: rel. error < 2e-4; the impedance controller keeps the
@@ -277,7 +289,7 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
         /* ---- constraint rows */
         double cn[2] = {0.0, 0.0}, ctg[2] = {0.0, 0.0}; /* contact normal / tangent forces */
         double gfx[4] = {0.0, 0.0, 0.0, 0.0}, gfy[4] = {0.0, 0.0, 0.0, 0.0}; /* ground friction at the corners */
-        double rAx[2], rAy[2], rBx[2], rBy[2], Ann[2], Att[2], Rn[2], arn[2], art[2];
+        double rAx[2], rAy[2], rBx[2], rBy[2], Rn[2], invN[2], invT[2], arn[2], art[2];
         for (int k = 0; k < nc; ++k) {
             rAx[k] = ct[k].px - M->x;
             rAy[k] = ct[k].py - M->y;
@@ -286,28 +298,29 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
             const double nx = ct[k].nx, ny = ct[k].ny, tx = -ny, ty = nx;
             const double rAn = rAx[k] * ny - rAy[k] * nx, rBn = rBx[k] * ny - rBy[k] * nx; /* r x n */
             const double rAt = rAx[k] * ty - rAy[k] * tx, rBt = rBx[k] * ty - rBy[k] * tx;
-            Ann[k] = imM + imO + rAn * rAn * iIM + rBn * rBn * iIO;
-            Att[k] = imM + imO + rAt * rAt * iIM + rBt * rBt * iIO;
+            const double Ann = imM + imO + rAn * rAn * iIM + rBn * rBn * iIO;
+            const double Att = imM + imO + rAt * rAt * iIM + rBt * rBt * iIO;
             const double d = gpr_push_impedance(P, ct[k].depth);
-            Rn[k] = (1.0 - d) / d * Ann[k];
+            Rn[k] = (1.0 - d) / d * Ann;
+            invN[k] = 1.0 / (Ann + Rn[k]); /* (the sweeps below multiply instead of dividing) */
+            invT[k] = 1.0 / (Att + Rn[k]);
             /* relative velocity of the object w.r.t. the mover at the contact point */
             const double vrx = (O->vx - O->w * rBy[k]) - (M->vx - M->w * rAy[k]);
             const double vry = (O->vy + O->w * rBx[k]) - (M->vy + M->w * rAx[k]);
             arn[k] = -P->sol_B * (vrx * nx + vry * ny) + P->sol_K * d * ct[k].depth; /* r = -depth */
             art[k] = -P->sol_B * (vrx * tx + vry * ty);
         }
-        /* ground friction points: the four bottom corners of the object */
-        double gx[4], gy[4], Ag[4], Rg[4];
-        const double Ng = P->obj_mass * P->gravity * 0.25;
-        const double lim = P->mu * Ng;
+        /* ground friction points: the four bottom corners of the object; a_ref = -B v at each */
+        double gx[4], gy[4], bvx[4], bvy[4];
+        const double lim = P->g_lim, lim2 = lim * lim;
         {
             const double h = P->obj_h;
             const double cx[4] = {-h, -h, h, h}, cy[4] = {-h, h, h, -h};
             for (int g = 0; g < 4; ++g) {
                 gx[g] = O->c * cx[g] - O->s * cy[g];
                 gy[g] = O->s * cx[g] + O->c * cy[g];
-                Ag[g] = imO + (gx[g] * gx[g] + gy[g] * gy[g]) * iIO * 0.5; /* isotropic diagonal approximation */
-                Rg[g] = (1.0 - P->imp_d0) / P->imp_d0 * Ag[g];
+                bvx[g] = P->sol_B * (O->vx - O->w * gy[g]);
+                bvy[g] = P->sol_B * (O->vy + O->w * gx[g]);
             }
         }
         /* ---- projected Gauss-Seidel in acceleration space */
@@ -315,11 +328,12 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
             for (int k = 0; k < nc; ++k) {
                 const double nx = ct[k].nx, ny = ct[k].ny, tx = -ny, ty = nx;
                 /* current relative acceleration at the contact (object minus mover) */
-                double arx = (aO[0] + (fO[0] * imO) - (aO[2] + fO[2] * iIO) * rBy[k]) - (aM[0] + (fM[0] * imM) - (aM[2] + fM[2] * iIM) * rAy[k]);
-                double ary = (aO[1] + (fO[1] * imO) + (aO[2] + fO[2] * iIO) * rBx[k]) - (aM[1] + (fM[1] * imM) + (aM[2] + fM[2] * iIM) * rAx[k]);
+                double alO = aO[2] + fO[2] * iIO, alM = aM[2] + fM[2] * iIM;
+                double arx = (aO[0] + (fO[0] * imO) - alO * rBy[k]) - (aM[0] + (fM[0] * imM) - alM * rAy[k]);
+                double ary = (aO[1] + (fO[1] * imO) + alO * rBx[k]) - (aM[1] + (fM[1] * imM) + alM * rAx[k]);
                 /* normal row */
                 double res = (arx * nx + ary * ny) - arn[k] + Rn[k] * cn[k];
-                double fn = cn[k] - res / (Ann[k] + Rn[k]);
+                double fn = cn[k] - res * invN[k];
                 if (fn < 0.0) fn = 0.0;
                 double df = fn - cn[k];
                 cn[k] = fn;
@@ -330,10 +344,12 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
                 fM[1] -= df * ny;
                 fM[2] -= df * (rAx[k] * ny - rAy[k] * nx);
                 /* tangent row (friction cone |ft| <= mu fn) */
-                arx = (aO[0] + (fO[0] * imO) - (aO[2] + fO[2] * iIO) * rBy[k]) - (aM[0] + (fM[0] * imM) - (aM[2] + fM[2] * iIM) * rAy[k]);
-                ary = (aO[1] + (fO[1] * imO) + (aO[2] + fO[2] * iIO) * rBx[k]) - (aM[1] + (fM[1] * imM) + (aM[2] + fM[2] * iIM) * rAx[k]);
+                alO = aO[2] + fO[2] * iIO;
+                alM = aM[2] + fM[2] * iIM;
+                arx = (aO[0] + (fO[0] * imO) - alO * rBy[k]) - (aM[0] + (fM[0] * imM) - alM * rAy[k]);
+                ary = (aO[1] + (fO[1] * imO) + alO * rBx[k]) - (aM[1] + (fM[1] * imM) + alM * rAx[k]);
                 res = (arx * tx + ary * ty) - art[k] + Rn[k] * ctg[k];
-                double ft = ctg[k] - res / (Att[k] + Rn[k]);
+                double ft = ctg[k] - res * invT[k];
                 const double cone = P->mu * cn[k];
                 if (ft > cone) ft = cone;
                 if (ft < -cone) ft = -cone;
@@ -347,16 +363,14 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
                 fM[2] -= df * (rAx[k] * ty - rAy[k] * tx);
             }
             for (int g = 0; g < 4; ++g) {
-                /* velocity and acceleration of the corner; a_ref = -B v */
-                const double vx = O->vx - O->w * gy[g], vy = O->vy + O->w * gx[g];
+                /* acceleration of the corner */
                 const double alpha = aO[2] + fO[2] * iIO;
                 const double ax_ = (aO[0] + fO[0] * imO) - alpha * gy[g];
                 const double ay_ = (aO[1] + fO[1] * imO) + alpha * gx[g];
-                const double den = Ag[g] + Rg[g];
-                double fx = gfx[g] - (ax_ + P->sol_B * vx + Rg[g] * gfx[g]) / den;
-                double fy = gfy[g] - (ay_ + P->sol_B * vy + Rg[g] * gfy[g]) / den;
+                double fx = gfx[g] - (ax_ + bvx[g] + P->g_R * gfx[g]) * P->g_inv;
+                double fy = gfy[g] - (ay_ + bvy[g] + P->g_R * gfy[g]) * P->g_inv;
                 const double mag2 = fx * fx + fy * fy;
-                if (mag2 > lim * lim) { /* project onto the friction disc */
+                if (mag2 > lim2) { /* project onto the friction disc */
                     const double sc = lim / sqrt(mag2);
                     fx = fx * sc;
                     fy = fy * sc;
@@ -372,9 +386,9 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
     }
     /* ---- total accelerations; object damping implicit in velocity like MuJoCo's Euler: (M + dt D) a = f */
     const double axM = aM[0] + fM[0] * imM, ayM = aM[1] + fM[1] * imM, alM = aM[2] + fM[2] * iIM;
-    const double axO = (-P->obj_damping * O->vx + fO[0]) / (P->obj_mass + dt * P->obj_damping);
-    const double ayO = (-P->obj_damping * O->vy + fO[1]) / (P->obj_mass + dt * P->obj_damping);
-    const double alO = (-P->obj_damping * O->w + fO[2]) / (P->obj_inertia + dt * P->obj_damping);
+    const double axO = (-P->obj_damping * O->vx + fO[0]) * P->o_inv_lin;
+    const double ayO = (-P->obj_damping * O->vy + fO[1]) * P->o_inv_lin;
+    const double alO = (-P->obj_damping * O->w + fO[2]) * P->o_inv_rot;
     *qax = axM;
     *qay = ayM;
     /* ---- semi-implicit Euler */
