@@ -310,9 +310,10 @@ __device__ __forceinline__ unsigned group_mask(unsigned lane) {
 // mover–mover check (basic:355-424), warp-collective: EVERY lane of the warp must call it.
 //   part : this lane takes part (its env is being checked and the lane holds a mover)
 // returns this lane's OR over the pairs it evaluated; the caller ballots over the group.
+//   kmask: bit k set = this lane wants its pair (m, m+k) evaluated (a float32 screen may already have cleared the others)
 template <int G, bool BOX>
 __device__ __forceinline__ bool pair_check(unsigned lane, int m, bool part, double x, double y, double s0, double s1,
-                                           const Rect& rect, bool quirk, double quirk_rsum) {
+                                           const Rect& rect, bool quirk, double quirk_rsum, unsigned kmask = 0xffffffffu) {
     bool hit = false;
     if (G == 1) return false;
     const unsigned base = lane & ~(unsigned)(G - 1);
@@ -325,7 +326,7 @@ __device__ __forceinline__ bool pair_check(unsigned lane, int m, bool part, doub
         const double os0 = __shfl_sync(FULL, s0, src);
         const bool opart = __shfl_sync(FULL, (int)part, src) != 0;
         // for k == G/2 the pair (m, m+G/2) is seen from both ends: only the lower lane evaluates it
-        const bool mine = part && opart && !(k == G / 2 && m >= G / 2);
+        const bool mine = part && opart && ((kmask >> k) & 1u) && !(k == G / 2 && m >= G / 2);
         const double dx = dsub(x, ox), dy = dsub(y, oy);
         const double d2 = dadd(dmul(dx, dx), dmul(dy, dy));
         if (!BOX) {

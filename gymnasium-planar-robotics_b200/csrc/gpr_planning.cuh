@@ -301,9 +301,10 @@ __device__ __forceinline__ bool pair_circle_fast(const PlanArgs& a, unsigned lan
 // `near` marks lanes with a pair the screen cannot clear (the caller then runs the exact rectangle test for the warp).
 template <int G>
 __device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part, double x, double y, float exf, float eyf,
-                                                float mg, bool& near, float& margin) {
+                                                float mg, bool& near, float& margin, unsigned& kmask) {
     near = false;
     margin = 3.0e38f;
+    kmask = 0u;  // bit k: the pair (m, m+k) could not be cleared
     if (G == 1) return;
     const float xf = part ? (float)x : 1e30f, yf = part ? (float)y : 1e30f;
     const unsigned base = lane & ~(unsigned)(G - 1);
@@ -317,6 +318,7 @@ __device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part,
         const float mgn = fmaxf(fabsf(xf - oxf) * 0.999999f - tx, fabsf(yf - oyf) * 0.999999f - ty);
         if (both) {
             near = near || !(mgn > 0.f);
+            kmask |= !(mgn > 0.f) ? (1u << k) : 0u;
             margin = fminf(margin, fmaxf(mgn, 0.f));
         }
     }
@@ -1011,7 +1013,8 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
             } else {
                 // axis-gap screen; the exact rectangle test of geom:107-138 only for a warp with an uncleared pair
                 bool near;
-                pair_box_screen<G>(ln.lane, ln.m, part, p.x, p.y, pxf, pyf, a.pair_mgf[NOISE ? 1 : 0], near, clear_p);
+                unsigned kmask;
+                pair_box_screen<G>(ln.lane, ln.m, part, p.x, p.y, pxf, pyf, a.pair_mgf[NOISE ? 1 : 0], near, clear_p, kmask);
                 if (__any_sync(FULL, near)) {
                     double mx = p.x, my = p.y;
                     Rect rm;
@@ -1026,8 +1029,8 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
                     } else {
                         rect_vertices_axis(mx, my, cm0, cm1, rm);
                     }
-                    // decides every pair of the warp's envs (pairs the screen cleared are misses either way)
-                    hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0);
+                    // exact test of the pairs the screen could not clear (the cleared ones are certain misses)
+                    hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0, kmask);
                 }
             }
             // an env's pair clearance is the smallest one any of its lanes saw; each mover may use up half of it

@@ -206,6 +206,35 @@ def test_planning_autoreset_sampled_on_device(mode, num_movers, layout):
     env.close()
 
 
+@pytest.mark.parametrize('num_movers,shape,jerk', [(12, 'circle', False), (20, 'box', True), (32, 'circle', True), (7, 'box', False)],
+                         ids=['12circle', '20box-jerk', '32circle-jerk', '7box'])
+def test_planning_wide_lane_groups(num_movers, shape, jerk):
+    """Lane groups of 8, 16 and 32 (one warp per env at the maximum of 32 movers): full episodes with on-device
+    rejection sampling (the one-group-per-attempt sampler), sensor noise, auto-reset, on a 10x10 (16x16) layout with a hole."""
+    rng = np.random.default_rng(70 + num_movers)
+    n = 16 if num_movers > 24 else 10  # 32 movers need room: acceptance of all-at-once sampling is ~1e-2 on 16x16
+    layout = np.ones((n, n))
+    layout[4, 5] = 0
+    cp = {'shape': 'circle', 'size': 0.1, 'offset': 0.002} if shape == 'circle' else {'shape': 'box', 'size': np.array([0.08, 0.07]), 'offset_wall': 0.001}
+    env, ora = make_pair(256, layout_tiles=layout, num_movers=num_movers, std_noise=1e-5, learn_jerk=jerk, collision_params=cp,
+                         autoreset_mode='same_step', max_episode_steps=8, seed=3)
+    env.reset(seed=3)
+    ora.reset(seed=3)
+    assert_state_equal(env, ora, 'reset')
+    lim = 100.0 if jerk else 10.0
+    ends = 0
+    for t in range(24):
+        a = rng.uniform(-lim, lim, (256, 2 * num_movers)).astype(np.float32)
+        env.step(torch.as_tensor(a, device=DEV))
+        ora.step(a)
+        assert_outputs_equal(env, ora, f'N={num_movers} step {t}')
+        ends += int((ora.terminated | ora.truncated).sum())
+    assert ends > 256
+    assert_state_equal(env, ora, f'N={num_movers}')
+    assert env.core.reset_failures() == int(ora.reset_failed.sum())
+    env.close()
+
+
 def test_planning_per_mover_radii_and_quirk():
     """Per-mover circle radii: pairwise semantics by default, the reference's broadcast quirk (basic_envs.py:409) on demand."""
     for quirk in (False, True):
