@@ -21,11 +21,34 @@ _ENV_NAMES = (
     'BenchmarkPlanningEnv',
     'BenchmarkPushingEnv',
     'BenchmarkPlanningParallelEnv',
-    'register_gymnasium_envs',
     'shard_range',
     'all_reduce_stats',
     'stats_dict',
 )
+
+
+def register_gymnasium_envs() -> bool:
+    """Register 'BenchmarkPlanningEnv-v0' / 'BenchmarkPushingEnv-v0' (max_episode_steps=50) exactly like the reference's
+    ``__init__.py:21-41`` and, where gymnasium >= 1.0 offers it, the batched classes as ``vector_entry_point``.  Entry
+    points are strings, so nothing heavy is imported.  Returns False when gymnasium is not installed."""
+    try:
+        from gymnasium.envs.registration import register, registry
+    except Exception:
+        return False
+    for env_id, single, vec in (
+        ('BenchmarkPlanningEnv-v0', 'BenchmarkPlanningEnv', 'BenchmarkPlanningVecEnv'),
+        ('BenchmarkPushingEnv-v0', 'BenchmarkPushingEnv', 'BenchmarkPushingVecEnv'),
+    ):
+        if env_id in registry:
+            continue
+        try:
+            register(id=env_id, entry_point=f'{__name__}.envs:{single}', vector_entry_point=f'{__name__}.envs:{vec}', max_episode_steps=50)
+        except TypeError:  # gymnasium < 1.0
+            register(id=env_id, entry_point=f'{__name__}.envs:{single}', max_episode_steps=50)
+    return True
+
+
+register_gymnasium_envs()  # the reference registers its ids on import (__init__.py:41); a no-op without gymnasium
 
 
 def __getattr__(name):  # torch is imported only when an env class is first touched

@@ -620,27 +620,3 @@ class BenchmarkPlanningParallelEnv:
 
     def close(self):
         self._vec.close()
-
-
-# ----------------------------------------------------------------------------------------------------------------------
-# registration (same ids and TimeLimit as the reference's __init__.py:21-41); gymnasium is optional
-# ----------------------------------------------------------------------------------------------------------------------
-def register_gymnasium_envs() -> bool:
-    """Register 'BenchmarkPlanningEnv-v0' / 'BenchmarkPushingEnv-v0' (max_episode_steps=50) and, where gymnasium>=1.0
-    offers it, the batched classes as ``vector_entry_point``.  Returns False when gymnasium is not installed."""
-    try:
-        from gymnasium.envs.registration import register, registry
-    except Exception:
-        return False
-    pkg = __name__.rsplit('.', 1)[0]
-    for env_id, single, vec in (
-        ('BenchmarkPlanningEnv-v0', 'BenchmarkPlanningEnv', 'BenchmarkPlanningVecEnv'),
-        ('BenchmarkPushingEnv-v0', 'BenchmarkPushingEnv', 'BenchmarkPushingVecEnv'),
-    ):
-        if env_id in registry:
-            continue
-        try:
-            register(id=env_id, entry_point=f'{pkg}.envs:{single}', vector_entry_point=f'{pkg}.envs:{vec}', max_episode_steps=50)
-        except TypeError:  # gymnasium < 1.0
-            register(id=env_id, entry_point=f'{pkg}.envs:{single}', max_episode_steps=50)
-    return True

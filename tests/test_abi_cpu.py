@@ -107,3 +107,28 @@ def test_shard_range_partitions_exactly():
             assert parts[0][0] == 0 and sum(c for _, c in parts) == total
             for (b0, c0), (b1, _) in zip(parts, parts[1:]):
                 assert b0 + c0 == b1
+
+
+def test_env_ids_register_like_the_reference(monkeypatch):
+    """__init__.py:21-41 of the reference: both ids, max_episode_steps=50, registered on import (here: when gymnasium is
+    importable; a recording stub stands in for it)."""
+    import importlib
+    import sys
+    import types
+
+    calls = []
+    reg = types.ModuleType('gymnasium.envs.registration')
+    reg.registry = {}
+    reg.register = lambda **kw: (calls.append(kw), reg.registry.__setitem__(kw['id'], kw))
+    gym = types.ModuleType('gymnasium')
+    envs = types.ModuleType('gymnasium.envs')
+    gym.envs, envs.registration = envs, reg
+    for name, mod in (('gymnasium', gym), ('gymnasium.envs', envs), ('gymnasium.envs.registration', reg)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    assert gpr.register_gymnasium_envs() is True
+    assert [c['id'] for c in calls] == ['BenchmarkPlanningEnv-v0', 'BenchmarkPushingEnv-v0']
+    assert all(c['max_episode_steps'] == 50 for c in calls)
+    assert calls[0]['entry_point'].endswith('envs:BenchmarkPlanningEnv') and calls[1]['vector_entry_point'].endswith('envs:BenchmarkPushingVecEnv')
+    mod_name, cls_name = calls[0]['entry_point'].split(':')
+    assert hasattr(importlib.import_module(mod_name), cls_name)  # the entry point resolves
+    assert gpr.register_gymnasium_envs() is True and len(calls) == 2  # idempotent

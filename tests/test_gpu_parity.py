@@ -235,6 +235,78 @@ def test_planning_wide_lane_groups(num_movers, shape, jerk):
     env.close()
 
 
+def test_reference_wall_vectors_directly_on_the_gpu():
+    """The reference's OWN wall-check test vectors (tests/test_basic_env.py, committed as tests/golden/
+    reference_test_vectors.json together with the outputs of the unmodified reference function) against the CUDA path
+    directly, without the oracle in between: every test position becomes the injected start of a one-mover env on the
+    test's layout and collision size, and reset()'s wall flag (basic_envs.py:1799-1801) must equal 1 - expected.
+    Cases with rotated movers (yaw 45 / 90 deg) are not reachable in the planning env (movers never rotate) and are
+    covered through the oracle (tests/test_oracle_golden.py)."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_test_vectors.json')) as f:
+        cases = json.load(f)['wall']
+    used = points = 0
+    for c in cases:
+        q = np.asarray(c['qpos'], dtype=np.float64)
+        cs = np.asarray(c['csize_total'], dtype=np.float64)
+        if not np.allclose(q[:, 3:], [1, 0, 0, 0]):
+            continue
+        assert c['expected'] == c['reference_output']  # the reference passes its own test
+        layout = np.asarray(c['layout'])
+        for size in np.unique(cs, axis=0):
+            sel = np.all(cs == size, axis=1)
+            cp = {'shape': c['shape'], 'size': float(size[0]) if c['shape'] == 'circle' else size.copy()}
+            try:
+                env = gpr.BenchmarkPlanningVecEnv(int(sel.sum()), layout_tiles=layout, num_movers=1, device=DEV, std_noise=0.0,
+                                                  collision_params=cp, autoreset_mode='off')
+            except gpr.GprError:
+                continue  # shapes as large as a tile trip an assert in the reference (basic_envs.py:650): refused up front
+            st = q[sel][:, None, :2]
+            env.reset(seed=0, options={'mover_start_xy_pos': st, 'mover_goal_xy_pos': st})
+            torch.cuda.synchronize()
+            got = env.core.buf['wall_collision'].cpu().numpy().astype(int)
+            exp = 1 - np.asarray(c['expected'])[sel]
+            assert np.array_equal(got, exp), (c['shape'], size, layout.tolist(), q[sel][got != exp])
+            points += int(sel.sum())
+            env.close()
+        used += 1
+    assert used >= 40 and points >= 400
+
+
+def test_sampled_starts_follow_the_reference_distribution():
+    """Reset sampling cannot be compared draw for draw (NumPy's PCG64 vs Philox), so it is compared in distribution: the
+    reference's loop (planning:369-385: draw all movers uniformly, redraw everything until no pair is closer than 2r)
+    restated in NumPy against the on-device sampler, two-sample Kolmogorov-Smirnov on coordinates and pair distances."""
+    from scipy import stats
+
+    B, N = 16384, 4
+    env = gpr.BenchmarkPlanningVecEnv(B, layout_tiles=np.ones((3, 3)), num_movers=N, device=DEV, std_noise=0.0, seed=11)
+    env.reset(seed=11)
+    p = env.get_state()['pos'].cpu().numpy()
+    g = env.get_state()['goal'].cpu().numpy()
+    env.close()
+    rng = np.random.default_rng(0)
+    ref = np.zeros((0, N, 2))
+    while ref.shape[0] < B:
+        c = rng.uniform(0.11, 0.55, (400000, N, 2))
+        d = np.linalg.norm(c[:, :, None] - c[:, None], axis=-1) + 9 * np.eye(N)
+        ref = np.concatenate([ref, c[(d > 0.22).all(axis=(1, 2))]])
+    ref = ref[:B]
+
+    def feats(x):
+        d = np.linalg.norm(x[:, :, None] - x[:, None], axis=-1)[:, np.triu_indices(N, 1)[0], np.triu_indices(N, 1)[1]]
+        return {'x': x[..., 0].ravel(), 'y': x[..., 1].ravel(), 'min_pair': d.min(axis=1), 'max_pair': d.max(axis=1), 'x0': x[:, 0, 0]}
+
+    for name, arr in (('start', p), ('goal', g)):
+        fa, fb = feats(arr), feats(ref)
+        for k in fa:
+            pv = stats.ks_2samp(fa[k], fb[k]).pvalue
+            assert pv > 1e-4, f'{name} {k}: KS p-value {pv}'
+        assert (fa['min_pair'] >= 0.22).all() and arr.min() >= 0.11 and arr.max() <= 0.55
+
+
 def test_planning_per_mover_radii_and_quirk():
     """Per-mover circle radii: pairwise semantics by default, the reference's broadcast quirk (basic_envs.py:409) on demand."""
     for quirk in (False, True):
