@@ -247,12 +247,16 @@ def run_b200(args, wl):
     for i in range(3):
         env.step_host(hacts[i % 4])
     e2e_steps = max(10, args.steps // 4)
+    env.core.kernel_times(True)
     barrier()
     t0 = time.perf_counter()
+    acc = 0.0
     for i in range(e2e_steps):
         out = env.step_host(hacts[i % 4])
+        acc += float(out[1][0])  # the host reads the step's result (reward of env 0) before issuing the next step
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_kt = env.core.kernel_times(False)  # device time of the same kernels when their I/O lives in pinned host memory
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -313,6 +317,7 @@ def run_b200(args, wl):
                          'note': 'issue-bound kernel (40-cycle float64 loop per env): see profiles/ for issue-slot and stall breakdown'},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+                    'ms_per_step': 1e3 * float(te.item()) / e2e_steps, 'kernel_ms_with_host_io': {'step': e2e_kt['step_kernel_ms'], 'autoreset': e2e_kt['autoreset_kernel_ms']},
                     'api': f'{type(env).__name__}.step_host -> gpr_step_host: NumPy views of page-locked host arrays in/out, read and written in place by the kernels over PCIe (zero-copy), stream sync before returning'},
             'gpu_launches': int(launches), 'clocks': clocks,
             'episode_stats': stats, 'reset_failures': fails, 'wall_s_timed_region': wall,

@@ -190,7 +190,10 @@ class BatchedCore:
         """The same step called with HOST buffers (``gpr_step_host``): NumPy action in, NumPy results out.  The result
         arrays are page-locked, so the kernels write them in place over PCIe (no staging copy); an action array obtained
         from ``pinned_action_buffer`` is likewise read in place, any other one is staged through pinned memory."""
-        a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.num_envs, self.action_dim)
+        if action.dtype == np.float32 and action.flags.c_contiguous and action.size == self.num_envs * self.action_dim:
+            a = action  # (the common case: no NumPy calls on the per-step path)
+        else:
+            a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.num_envs, self.action_dim)
         if self._host is None:
             # page-locked result arrays (torch owns the memory, NumPy views it)
             self._host_pin = {k: torch.zeros(tuple(v.shape), dtype=v.dtype, pin_memory=True) for k, v in self.buf.items()}
@@ -360,6 +363,7 @@ class _VecEnvBase:
         self.metadata = dict(self.metadata)
         self.metadata['autoreset_mode'] = {0: 'disabled', 1: 'same_step', 2: 'next_step'}[int(cfg.autoreset_mode)]
         self.closed = False
+        self._host_ret = None
 
     # -- views
     def _obs(self) -> dict[str, torch.Tensor]:
@@ -402,12 +406,15 @@ class _VecEnvBase:
     def step_host(self, action: np.ndarray):
         """step() for callers that live on the host (NumPy in / NumPy out through ``gpr_step_host``)."""
         h = self.core.step_host(action)
-        obs = {'observation': h['observation'], 'achieved_goal': h['achieved_goal'], 'desired_goal': h['desired_goal']}
-        # the flag arrays hold 0/1 bytes: view them as bool instead of converting (the arrays are reused every step)
-        info = {k: h[k].view(np.bool_) for k in ('is_success', 'mover_collision', 'wall_collision')}
-        if 'final_observation' in h:
-            info['final_obs'] = {k: h['final_' + k] for k in ('observation', 'achieved_goal', 'desired_goal')}
-        return obs, h['reward'], h['terminated'].view(np.bool_), h['truncated'].view(np.bool_), info
+        if self._host_ret is None:
+            # the result arrays are persistent (rewritten in place every step), so the returned structure is built once;
+            # the flag arrays hold 0/1 bytes and are viewed as bool instead of converted
+            obs = {'observation': h['observation'], 'achieved_goal': h['achieved_goal'], 'desired_goal': h['desired_goal']}
+            info = {k: h[k].view(np.bool_) for k in ('is_success', 'mover_collision', 'wall_collision')}
+            if 'final_observation' in h:
+                info['final_obs'] = {k: h['final_' + k] for k in ('observation', 'achieved_goal', 'desired_goal')}
+            self._host_ret = (obs, h['reward'], h['terminated'].view(np.bool_), h['truncated'].view(np.bool_), info)
+        return self._host_ret
 
     def compute_reward(self, achieved_goal, desired_goal, info=None):
         mc, wc = self._split_info(info)

@@ -1,3 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+for rep in 1 2; do timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu --quick > gpurun_out/bench_r1t_$rep.log 2>&1; done
