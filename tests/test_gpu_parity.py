@@ -465,6 +465,50 @@ def test_full_size_properties():
     env2.close()
 
 
+def test_full_size_pettingzoo_eight_movers_box_jerk():
+    """BASELINE configs[3] at full size: PettingZoo-parallel form, 8 movers, box collision shape, learn_jerk=True,
+    262,144 envs (5x5 tiles, see bench.py).  Size-independent properties over 12 steps with auto-reset, and the agent
+    views must be exactly the columns of the vector env's tensors."""
+    B, N = 262144, 8
+    kw = dict(learn_jerk=True, collision_params={'shape': 'box', 'size': np.array([0.08, 0.08])}, seed=4321)
+    pz = gpr.BenchmarkPlanningParallelEnv(B, np.ones((5, 5)), N, device=DEV, **kw)
+    twin = gpr.BenchmarkPlanningVecEnv(B, np.ones((5, 5)), N, device=DEV, **kw)
+    obs, infos = pz.reset(seed=4321)
+    twin.reset(seed=4321)
+    assert pz.agents == [f'mover_{i}' for i in range(N)] and obs['mover_7']['observation'].shape == (B, 4)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    finished = 0
+    for t in range(12):
+        a = (torch.rand((B, N, 2), device=DEV, generator=g) * 2 - 1) * 100
+        obs, rew, term, trunc, infos = pz.step({f'mover_{i}': a[:, i] for i in range(N)})
+        o2, r2, t2, tr2, i2 = twin.step(a.reshape(B, 2 * N))
+        assert torch.equal(rew['mover_0'], r2) and torch.equal(term['mover_3'], t2)          # same env, re-keyed
+        full = o2['observation']                                                                # [vel(8x2), acc(8x2)]
+        for i in (0, 5, 7):
+            ob = obs[f'mover_{i}']
+            assert torch.equal(ob['observation'][:, :2], full[:, 2 * i:2 * i + 2])
+            assert torch.equal(ob['observation'][:, 2:], full[:, 2 * N + 2 * i:2 * N + 2 * i + 2])
+            assert torch.equal(ob['achieved_goal'], o2['achieved_goal'][:, 2 * i:2 * i + 2])
+        info = infos['mover_0']
+        coll = info['mover_collision'] | info['wall_collision']
+        assert torch.equal(t2, coll | info['is_success']) and torch.equal(r2 == -50, coll)
+        st = twin.get_state()
+        assert (st['vel'].norm(dim=-1) <= 2.0 + 1e-4).all() and (st['acc'].norm(dim=-1) <= 10.0 * (1 + 1e-9)).all()
+        done = t2 | tr2
+        finished += int(done.sum())
+        if done.any():
+            p = st['pos'][done]
+            lo, hi = twin.cfg.min_xy_pos[0], twin.cfg.max_xy_pos[0]
+            assert abs(lo - 0.08) < 1e-12 and abs(hi - (1.08 + 0.06 - 0.08)) < 1e-12  # planning:262-267 with the box margin
+            assert (p >= lo).all() and (p <= hi).all()
+            d = (p[:, :, None, :] - p[:, None, :, :]).abs()
+            apart = (d[..., 0] > 0.16) | (d[..., 1] > 0.16) | torch.eye(N, device=DEV, dtype=torch.bool)
+            assert apart.all()                                      # fresh starts: no two 0.16 m boxes overlap
+    assert finished > B // 2 and twin.core.reset_failures() == 0
+    pz.close()
+    twin.close()
+
+
 def test_single_env_and_pettingzoo_forms():
     """The reference's single-env call signatures (NumPy float64) and the PettingZoo-parallel re-keying."""
     env = gpr.BenchmarkPlanningEnv(layout_tiles=np.ones((3, 3)), num_movers=2, show_2D_plot=False, render_mode=None, std_noise=0.0)

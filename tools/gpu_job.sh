@@ -1,4 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-for rep in 1 2; do timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu --quick > gpurun_out/bench_r1t_$rep.log 2>&1; done
+timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "full_size" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
