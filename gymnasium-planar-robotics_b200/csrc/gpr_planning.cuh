@@ -783,30 +783,53 @@ __device__ __forceinline__ void reset_checks(const PlanArgs& a, const Tables& tb
             }
         }
     } else {
-        double wx = p.x, wy = p.y, mx = p.x, my = p.y;
-        Rect rw, rm;
-        if (NOISE) {
-            float n4[4];
-            normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, n4);
-            wx = noisy(p.x, n4[0], a.sigma_p);
-            wy = noisy(p.y, n4[1], a.sigma_p);
-            mx = noisy(p.x, n4[2], a.sigma_p);
-            my = noisy(p.y, n4[3], a.sigma_p);
-            float q[4];
-            normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_WQUAT, (uint32_t)ln.m, q);
-            rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
-                          dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
-            if (G > 1) {
-                normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_MQUAT, (uint32_t)ln.m, q);
-                rect_vertices(mx, my, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
-                              dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
-            }
-        } else {
-            rect_vertices_axis(wx, wy, cw0, cw1, rw);
-            rect_vertices_axis(mx, my, cm0, cm1, rm);
+        // float32 screens first (bounding rectangle for the walls, axis gaps for the pairs — the mover is axis-aligned up to
+        // the sensor noise on its quaternion, see planning_step_kernel); exact tests only where they cannot decide
+        const float ext_w = a.rot_extf * (float)(cw0 + cw1), ext_m = a.rot_extf * (float)(cm0 + cm1);
+        int f = 1;
+        if (part) {
+            int gi, gj;
+            guess_cell(a, p.x, p.y, gi, gj);
+            float clear;
+            f = wall_fast(a, tb, p.x, p.y, (float)cw0 + ext_w, (float)cw1 + ext_w, gi, gj, clear);
         }
-        bad = part && !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
-        hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0);
+        const bool wneed = part && f != 1;  // (0 is not a verdict: the bounding rectangle is conservative)
+        bool near;
+        float clear_p;
+        unsigned kmask;
+        pair_box_screen<G>(ln.lane, ln.m, part, p.x, p.y, (float)cm0 + ext_m, (float)cm1 + ext_m, a.pair_mgf[NOISE ? 1 : 0], near,
+                           clear_p, kmask);
+        bad = false;
+        hit = false;
+        const bool wany = __any_sync(FULL, wneed), pany = G > 1 && __any_sync(FULL, near);
+        if (wany || pany) {
+            double wx = p.x, wy = p.y, mx = p.x, my = p.y;
+            Rect rw, rm;
+            if (NOISE) {
+                float n4[4];
+                normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, n4);
+                wx = noisy(p.x, n4[0], a.sigma_p);
+                wy = noisy(p.y, n4[1], a.sigma_p);
+                mx = noisy(p.x, n4[2], a.sigma_p);
+                my = noisy(p.y, n4[3], a.sigma_p);
+                float q[4];
+                if (wany) {
+                    normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_WQUAT, (uint32_t)ln.m, q);
+                    rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                                  dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
+                }
+                if (pany) {
+                    normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_MQUAT, (uint32_t)ln.m, q);
+                    rect_vertices(mx, my, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                                  dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
+                }
+            } else {
+                rect_vertices_axis(wx, wy, cw0, cw1, rw);
+                rect_vertices_axis(mx, my, cm0, cm1, rm);
+            }
+            if (wneed) bad = !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
+            if (pany) hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0, kmask);
+        }
     }
     const bool wnow = (__ballot_sync(FULL, bad) & ln.gmask) != 0u;
     const bool mnow = (__ballot_sync(FULL, hit) & ln.gmask) != 0u;
