@@ -69,24 +69,65 @@ def measured_hbm_peak() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """nvidia-smi SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line), sampled through NVML every
+    few milliseconds (the timed region of the default run is ~60 ms: `nvidia-smi` itself takes longer than that per query;
+    it remains the fallback when pynvml is missing)."""
 
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index: int):
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.source = 'nvidia-smi'
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the torch device
+            import torch
+
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), 'pci_bus_id') else None
+            self._h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        self._h = hh
+                        break
+            if self._h is None:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = pynvml
+            self.source = 'nvml'
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._h
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bits = [n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap]
+        return [sm, mx] + ['Active' if (r & b) else 'Not Active' for b in bits]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(',')])
+                if self._nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(',')])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.004 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -99,17 +140,17 @@ class ClockSampler:
 
     def summary(self) -> dict:
         sm, mx, reasons = [], 0.0, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for s in self.samples:
             try:
                 sm.append(float(s[0]))
                 mx = max(mx, float(s[1]))
-                for n, v in zip(names, s[2:6]):
-                    if v.lower().startswith('active'):
+                for n, v in zip(self.NAMES, s[2:6]):
+                    if str(v).lower().startswith('active'):
                         reasons.add(n)
             except Exception:
                 continue
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons), 'samples': len(sm),
+                'source': self.source}
 
 
 def make_cfg(wl, num_envs, env_index_base=0, **over):
