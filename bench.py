@@ -226,6 +226,9 @@ def run_b200(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     B = args.num_envs or wl['num_envs']
+    # one process per GPU: run on (and first-touch pinned memory from) the cores of the GPU's own NUMA node
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
+    numa_cpus = None if args.no_numa_bind else gpr.bind_to_gpu_numa(local)
 
     def build(**over):
         cls = gpr.BenchmarkPlanningVecEnv if wl['kind'] == 'planning' else gpr.BenchmarkPushingVecEnv
@@ -339,6 +342,8 @@ def run_b200(args, wl):
         # CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
         cpu = None
         if world == 1 and not args.no_cpu:
+            if full_affinity is not None:
+                os.sched_setaffinity(0, full_affinity)  # the CPU baseline may use every host core again
             threads = host_threads()
             cb, cs = 2048, 10
             v1 = time_oracle(wl, cb, cs, 2, threads)
@@ -351,7 +356,8 @@ def run_b200(args, wl):
             'config': {'workload': wl['desc'], 'env_id': wl['env_id'], 'envs_per_gpu': B, 'num_cycles': int(env.cfg.num_cycles),
                        'substeps_per_s': value * int(env.cfg.num_cycles), 'std_noise': env.cfg.std_noise[0], 'autoreset': 'same_step',
                        'actions': 'uniform(-max,max), 8 pre-generated device tensors cycled',
-                       'l2': 'flushed between timed steps (256 MiB memset, outside the event pairs)', 'parallelism': f'env-shard x{world}'},
+                       'l2': 'flushed between timed steps (256 MiB memset, outside the event pairs)', 'parallelism': f'env-shard x{world}',
+                       'numa_bind': f'{len(numa_cpus)} cores local to the GPU' if numa_cpus else 'none'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': peak_src, 'algorithmic_bytes_per_env_step': abytes, 'algorithmic_bytes_per_launch': abytes * B,
                          'kernel_ms': step_kernel_ms, 'other_kernels_ms': {'autoreset': ktimes['autoreset_kernel_ms']}, 'kernel': 'planning_step_kernel' if wl['kind'] == 'planning' else 'pushing_step_kernel',
@@ -380,6 +386,7 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--quick', action='store_true', help='skip the extra context measurements')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
+    ap.add_argument('--no-numa-bind', action='store_true', help='do not pin the rank to the cores local to its GPU')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     wl = WORKLOADS[args.workload]

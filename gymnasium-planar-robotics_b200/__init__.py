@@ -51,6 +51,31 @@ def register_gymnasium_envs() -> bool:
 register_gymnasium_envs()  # the reference registers its ids on import (__init__.py:41); a no-op without gymnasium
 
 
+def bind_to_gpu_numa(device_index: int) -> list[int] | None:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (one process per GPU:
+    page-locked host buffers are then first-touched on the GPU's own NUMA node, so the zero-copy result traffic of
+    ``step_host`` does not cross the socket interconnect).  Call it before creating envs.  Returns the core list, or None
+    when NVML / affinity control is unavailable (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def __getattr__(name):  # torch is imported only when an env class is first touched
     if name in _ENV_NAMES or name == 'envs':
         import importlib

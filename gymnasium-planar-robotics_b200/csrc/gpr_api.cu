@@ -627,8 +627,19 @@ static void* device_alias(const void* p) {
 //   pageable destination    -> device staging, then one async copy into the handle's pinned mirror and a memcpy
 struct HostRoute {
     gpr_outputs dev;   // pointers handed to the kernels
-    bool staged[12];   // field k goes through d_stage / h_stage
+    bool staged[12];   // field k goes through d_stage (copy engine afterwards)
+    void* pinned[12];  // staged field whose destination is page-locked: the copy engine writes it directly
 };
+
+// GPR_HOST_IO=dma: results of *_host calls always go through device staging and the copy engine (into the caller's buffer
+// when it is page-locked), never through zero-copy stores.  For hosts where SM-issued PCIe writes scale badly.
+static bool host_io_dma() {
+    static const bool v = [] {
+        const char* e = getenv("GPR_HOST_IO");
+        return e && strcmp(e, "dma") == 0;
+    }();
+    return v;
+}
 
 static HostRoute route_outputs(gpr_handle* h, const StageLayout& L, const gpr_outputs* host_out) {
     HostRoute r;
@@ -638,6 +649,8 @@ static HostRoute route_outputs(gpr_handle* h, const StageLayout& L, const gpr_ou
         void* dst = *out_slot(&ho, k);
         if (!dst) continue;
         void* alias = device_alias(dst);
+        r.pinned[k] = alias ? dst : nullptr;
+        if (alias && host_io_dma()) alias = nullptr;
         r.staged[k] = alias == nullptr;
         *out_slot(&r.dev, k) = alias ? alias : (void*)((char*)h->d_stage + L.off[k]);
     }
@@ -649,10 +662,12 @@ static int finish_host_call(gpr_handle* h, const StageLayout& L, const HostRoute
     char* hs = (char*)h->h_stage;
     char* ds = (char*)h->d_stage;
     for (int k = 0; k < 12; ++k)
-        if (r.staged[k]) CU(cudaMemcpyAsync(hs + L.off[k], ds + L.off[k], L.bytes[k], cudaMemcpyDeviceToHost, h->host_stream));
+        if (r.staged[k])
+            CU(cudaMemcpyAsync(r.pinned[k] ? r.pinned[k] : (void*)(hs + L.off[k]), ds + L.off[k], L.bytes[k], cudaMemcpyDeviceToHost,
+                               h->host_stream));
     CU(cudaStreamSynchronize(h->host_stream));  // results (zero-copy stores included) are visible to the host after this
     for (int k = 0; k < 12; ++k)
-        if (r.staged[k]) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
+        if (r.staged[k] && !r.pinned[k]) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
     return GPR_OK;
 }
 

@@ -870,6 +870,11 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
     succ = all && !coll;
 }
 
+#ifndef GPR_STEP_UNROLL
+#define GPR_STEP_UNROLL 1
+#endif
+#define GPR_PRAGMA_(x) _Pragma(#x)
+#define GPR_UNROLL(n) GPR_PRAGMA_(unroll n)
 #ifndef GPR_STEP_MINB
 #define GPR_STEP_MINB 2
 #endif
@@ -933,6 +938,7 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
     float travel = 0.f;                  // sum over cycles of an upper bound of |v|  (distance / dt)
     float lim_w = -1.f, lim_p = -1.f;    // `travel` values up to which the wall / pair check is certified negative
     bool any_alive = __any_sync(FULL, alive);
+    GPR_UNROLL(GPR_STEP_UNROLL)
     for (int cyc = 0; cyc < a.num_cycles && any_alive; ++cyc) {
         const uint32_t s0 = (uint32_t)cyc * 4u;
         const bool part = alive && ln.active;

@@ -209,7 +209,10 @@ GPR_API int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* out,
 /* Same step, called the way a user of the reference calls it: HOST buffers in, HOST buffers out; returns after the host
  * buffers are valid.  `host_out` holds host pointers.  Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch
  * pinned tensors) are read and written by the kernels IN PLACE through their device alias (zero-copy: result stores cross
- * PCIe while the rest of the grid still computes); pageable buffers are staged through the handle's pinned mirror. */
+ * PCIe while the rest of the grid still computes); pageable buffers are staged through the handle's pinned mirror.
+ * Environment variable GPR_HOST_IO=dma (read once per process) routes the results of page-locked buffers through device
+ * staging and the copy engine instead — slower on an otherwise idle host (B200: 192M -> 119M env-steps/s at 65,536
+ * envs), faster when many GPUs write into one host at once (8 ranks: 436M -> 497M). */
 GPR_API int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out);
 GPR_API int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_outputs* host_out);
 

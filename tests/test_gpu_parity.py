@@ -17,6 +17,7 @@ import gymnasium_planar_robotics_b200 as gpr
 pytestmark = pytest.mark.gpu
 
 DEV = 'cuda:0'
+ROOT = __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))
 
 L_RAGGED = np.array([[1, 1, 0, 1], [1, 1, 1, 1], [0, 1, 1, 0], [1, 1, 1, 1], [1, 0, 1, 1]])
 L_HOLE = np.array([[1, 1, 1, 1], [1, 0, 1, 1], [1, 1, 1, 1], [1, 1, 1, 1]])
@@ -398,6 +399,44 @@ def test_step_host_matches_device_step():
         assert np.array_equal(i1['wall_collision'].cpu().numpy(), i2['wall_collision'])
     e1.close()
     e2.close()
+
+
+def test_step_host_copy_engine_route_matches(tmp_path):
+    """GPR_HOST_IO=dma (results through device staging + copy engine instead of zero-copy stores; read once per process,
+    hence the subprocess) and pageable caller buffers give the same results as the default route."""
+    import subprocess
+    import sys
+
+    code = r"""
+import sys, numpy as np, torch
+sys.path[:0] = [%r, %r]
+import gymnasium_planar_robotics_b200 as gpr
+kw = dict(layout_tiles=np.ones((3, 3)), num_movers=4, std_noise=1e-5, seed=5)
+e1 = gpr.BenchmarkPlanningVecEnv(3000, device='cuda:0', **kw)
+e2 = gpr.BenchmarkPlanningVecEnv(3000, device='cuda:0', **kw)
+e1.reset(seed=5); e2.reset(seed=5)
+rng = np.random.default_rng(17)
+for _ in range(6):
+    a = rng.uniform(-10, 10, (3000, 8)).astype(np.float32)
+    o1, r1, t1, tr1, i1 = e1.step(torch.as_tensor(a, device='cuda:0'))
+    o2, r2, t2, tr2, i2 = e2.step_host(a)
+    torch.cuda.synchronize()
+    for k in ('observation', 'achieved_goal', 'desired_goal'):
+        assert np.array_equal(o1[k].cpu().numpy(), o2[k]), k
+    assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(t1.cpu().numpy(), t2) and np.array_equal(tr1.cpu().numpy(), tr2)
+    for k in ('is_success', 'mover_collision', 'wall_collision'):
+        assert np.array_equal(i1[k].cpu().numpy(), i2[k]), k
+    d = t2 | tr2
+    for k in ('observation', 'achieved_goal', 'desired_goal'):
+        assert np.array_equal(i1['final_obs'][k].cpu().numpy()[d], i2['final_obs'][k][d]), 'final ' + k
+print('ok')
+""" % (ROOT, ROOT + '/oracle')
+    import os
+
+    for mode in ('dma', 'zerocopy'):
+        env = dict(os.environ, GPR_HOST_IO=mode)
+        out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
+        assert out.returncode == 0 and 'ok' in out.stdout, (mode, out.stdout[-500:], out.stderr[-1500:])
 
 
 def test_sharding_does_not_change_results():
