@@ -85,7 +85,7 @@ class GprConfig(ctypes.Structure):
         ('solref', ctypes.c_double * 2),
         ('solimp', ctypes.c_double * 5),
         ('contact_iterations', ctypes.c_int32),
-        ('reserved_i32', ctypes.c_int32),
+        ('output_flags', ctypes.c_int32),
     ]
 
 
@@ -358,6 +358,7 @@ def planning_config(
     env_index_base: int = 0,
     seed: int = 0,
     reference_quirks: bool = False,
+    goal_output_on_change: bool = True,
 ) -> tuple[GprConfig, dict[str, Any]]:
     """kwargs of ``BenchmarkPlanningEnv`` (planning:165-185) -> ``gpr_config``."""
     del mover_colors_2D_plot, render_every_cycle, initial_mover_zpos  # visual only / z is not simulated (SURVEY §3.4)
@@ -399,6 +400,8 @@ def planning_config(
     d['obs_dim'] = num_movers * (1 + int(bool(learn_jerk))) * 2
     d['goal_dim'] = num_movers * 2
     d['action_dim'] = num_movers * 2
+    # the env classes hand the same output buffers to every call: desired_goal rows are rewritten only when they change
+    cfg.output_flags = 1 if goal_output_on_change else 0  # GPR_OUT_GOAL_ON_CHANGE
     return cfg, d
 
 
@@ -426,6 +429,7 @@ def pushing_config(
     env_index_base: int = 0,
     seed: int = 0,
     contact_iterations: int = 8,
+    goal_output_on_change: bool = True,
 ) -> tuple[GprConfig, dict[str, Any]]:
     """kwargs of ``BenchmarkPushingEnv`` (pushing:154-169) -> ``gpr_config``.
 
@@ -497,4 +501,6 @@ def pushing_config(
     d['obs_dim'] = (2 + int(bool(learn_jerk))) * 2
     d['goal_dim'] = 2
     d['action_dim'] = 2
+    # the env classes hand the same output buffers to every call: desired_goal rows are rewritten only when they change
+    cfg.output_flags = 1 if goal_output_on_change else 0  # GPR_OUT_GOAL_ON_CHANGE
     return cfg, d

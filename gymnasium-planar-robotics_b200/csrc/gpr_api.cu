@@ -70,6 +70,8 @@ struct gpr_handle {
     double *cx = nullptr, *cy = nullptr, *c_wall = nullptr, *c_mover = nullptr;
     uint16_t* cell = nullptr;
     double quirk_rsum[2] = {0, 0};
+    bool goal_dirty = true;  // desired_goal rows must all be written by the next step (GPR_OUT_GOAL_ON_CHANGE)
+    const void* goal_ptr = nullptr;  // the desired_goal buffer the last step wrote into
     // per-kernel timing (gpr_kernel_times)
     bool timing = false;
     std::vector<cudaEvent_t> tev;  // triples: before step kernel, between, after auto-reset kernel
@@ -484,6 +486,7 @@ extern "C" int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, u
         h->seed = seed;
         CU(cudaMemsetAsync(h->rng, 0, sizeof(uint32_t) * (size_t)h->cfg.num_envs, s));
     }
+    if (!out || out->desired_goal != h->goal_ptr) h->goal_dirty = true;  // new goals the steps' buffer does not see
     if (h->cfg.env_kind == GPR_ENV_PLANNING) {
         if (inject_object) return fail(GPR_ERR_INVALID_ARG, "inject_object is for the pushing env");
         PlanArgs a = plan_args(h, out);
@@ -520,9 +523,14 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
         h->tev_used += 3;
         CU(cudaEventRecord(te[0], s));
     }
+    // GPR_OUT_GOAL_ON_CHANGE: rows of envs that are not reset are skipped — unless this buffer has not seen all of them yet
+    const int write_goal = !(h->cfg.output_flags & GPR_OUT_GOAL_ON_CHANGE) || h->goal_dirty || out->desired_goal != h->goal_ptr;
+    h->goal_dirty = false;
+    h->goal_ptr = out->desired_goal;
     if (h->cfg.env_kind == GPR_ENV_PLANNING) {
         PlanArgs a = plan_args(h, out);
         a.action = reinterpret_cast<const float2*>(action);
+        a.write_goal = write_goal;
         CU(launch_plan(h, PLAN_STEP, a, s));
         if (te) CU(cudaEventRecord(te[1], s));
         if (h->cfg.autoreset_mode != GPR_AUTORESET_OFF) {
@@ -533,6 +541,7 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
     } else {
         PushArgs a = push_args(h, out);
         a.action = reinterpret_cast<const float2*>(action);
+        a.write_goal = write_goal;
         CU(launch_push(false, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, s));
         if (te) CU(cudaEventRecord(te[1], s));
     }
@@ -748,6 +757,7 @@ extern "C" int gpr_get_state(gpr_handle* h, const gpr_state* dst, void* stream) 
 extern "C" int gpr_set_state(gpr_handle* h, const gpr_state* src, void* stream) {
     if (!h || !src) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
     DeviceGuard g(h->device);
+    if (src->goal) h->goal_dirty = true;
     return copy_state(h, src, true, (cudaStream_t)stream);
 }
 

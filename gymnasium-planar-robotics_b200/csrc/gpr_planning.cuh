@@ -70,6 +70,7 @@ struct PlanArgs {
     uint32_t* reset_count;   // [2] double-buffered by step parity
     uint32_t* reset_cursor;  // [2]
     int parity;
+    int write_goal;  // 0: the step kernel leaves desired_goal rows of envs that were not reset alone (GPR_OUT_GOAL_ON_CHANGE)
     // per-call I/O
     const float2* action;
     gpr_outputs out;
@@ -914,7 +915,7 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
         u.y = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
         // desired_goal does not change during a step: store it now, so that (when the output lives in pinned host memory)
         // this part of the result traffic crosses PCIe under the 40-cycle loop instead of in the burst at the end
-        if (!pending_reset && a.out.desired_goal)
+        if (!pending_reset && a.write_goal && a.out.desired_goal)
             reinterpret_cast<float2*>(a.out.desired_goal)[ln.idx] = make_float2((float)goal.x, (float)goal.y);
     }
 

@@ -49,6 +49,7 @@ struct PushArgs {
     float* ep_return;
     double* stats;
     uint32_t* fail_count;
+    int write_goal;  // see PlanArgs
     // per-call I/O
     const float2* action;
     gpr_outputs out;
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(c
         }
     }
     if (!valid) return;
-    push_store_obs(a, e, a.out.observation, a.out.achieved_goal, a.out.desired_goal, obs, ag, s.goal);
+    push_store_obs(a, e, a.out.observation, a.out.achieved_goal, (a.write_goal || need) ? a.out.desired_goal : nullptr, obs, ag, s.goal);
     push_store(a, e, s);
     a.rng[e] = event;
     a.elapsed[e] = elapsed;

@@ -129,8 +129,15 @@ typedef struct gpr_config {
     double solref[2];       /* MuJoCo default (0.02, 1) */
     double solimp[5];       /* MuJoCo default (0.9, 0.95, 0.001, 0.5, 2) */
     int32_t contact_iterations; /* projected Gauss-Seidel sweeps of the planar contact solve */
-    int32_t reserved_i32;
+    int32_t output_flags; /* GPR_OUT_* bits */
 } gpr_config;
+
+/* output_flags bit: a step writes `desired_goal` rows only for environments whose goal changed in that call (they were
+ * reset); the other rows keep what an earlier call wrote.  For callers that pass the SAME desired_goal buffer to every
+ * call (the Python env classes do): it takes a quarter off the result traffic, which is what bounds *_host calls.
+ * gpr_reset always writes the rows of the environments it resets; after gpr_set_state with a goal, the next step writes
+ * every row once. */
+#define GPR_OUT_GOAL_ON_CHANGE 1
 
 /* Per-step results. Device pointers (host pointers for *_host calls), caller-owned, row-major; NULL = do not write.
  * planning: obs_dim = 2*N*(1+learn_jerk) (planning:242-254), goal_dim = 2*N

@@ -439,6 +439,37 @@ print('ok')
         assert out.returncode == 0 and 'ok' in out.stdout, (mode, out.stdout[-500:], out.stderr[-1500:])
 
 
+def test_desired_goal_on_change_survives_route_switches():
+    """GPR_OUT_GOAL_ON_CHANGE (default in the env classes): steps rewrite desired_goal rows only for envs that were reset.
+    Switching between the device-tensor route and the host-array route, masked resets and set_state must never leave a
+    stale row in the buffer that is returned."""
+    rng = np.random.default_rng(23)
+    B = 2048
+    env = gpr.BenchmarkPlanningVecEnv(B, device=DEV, layout_tiles=np.ones((3, 3)), num_movers=4, std_noise=0.0, seed=9, max_episode_steps=5)
+    env.reset(seed=9)
+
+    def goal_now():
+        return env.get_state()['goal'].cpu().numpy().reshape(B, 8).astype(np.float32)
+
+    for t in range(14):
+        a = rng.uniform(-10, 10, (B, 8)).astype(np.float32)
+        if t % 3 == 2:
+            obs = env.step_host(a)[0]
+            got = obs['desired_goal']
+        else:
+            obs = env.step(torch.as_tensor(a, device=DEV))[0]
+            torch.cuda.synchronize()
+            got = obs['desired_goal'].cpu().numpy()
+        assert np.array_equal(got, goal_now()), f'step {t}'
+        if t == 5:  # masked reset through the device route, then a host-route step
+            mask = rng.random(B) < 0.3
+            env.reset(options={'mask': mask})
+        if t == 9:  # goals replaced behind the env's back
+            st = env.get_state()
+            env.set_state({'goal': st['goal'].flip(0)})
+    env.close()
+
+
 def test_sharding_does_not_change_results():
     """Multi-GPU rule: the RNG is keyed by the GLOBAL env index, so one handle with 4096 envs and two
     handles with 2048 each (env_index_base 0 / 2048) produce identical trajectories."""
