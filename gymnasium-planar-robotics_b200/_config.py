@@ -118,6 +118,8 @@ class GprState(ctypes.Structure):
         ('mover_rot', ctypes.c_void_p),
         ('object_pos', ctypes.c_void_p),
         ('object_vel', ctypes.c_void_p),
+        ('needs_reset', ctypes.c_void_p),
+        ('episode_return', ctypes.c_void_p),
     ]
 
 

@@ -31,6 +31,8 @@ EXPORTED_SYMBOLS = (
     'gpr_reset_host',
     'gpr_get_state',
     'gpr_set_state',
+    'gpr_get_seed',
+    'gpr_set_seed',
     'gpr_compute_reward',
     'gpr_episode_stats',
     'gpr_reset_failures',
@@ -71,6 +73,8 @@ def load():
     lib.gpr_reset_host.argtypes = [vp, i32, u64, ctypes.POINTER(GprOutputs)]
     lib.gpr_get_state.argtypes = [vp, ctypes.POINTER(GprState), vp]
     lib.gpr_set_state.argtypes = [vp, ctypes.POINTER(GprState), vp]
+    lib.gpr_get_seed.argtypes = [vp, ctypes.POINTER(u64)]
+    lib.gpr_set_seed.argtypes = [vp, u64]
     lib.gpr_compute_reward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.gpr_episode_stats.argtypes = [vp, vp, i32, vp]
     lib.gpr_reset_failures.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]

@@ -739,6 +739,8 @@ static int copy_state(gpr_handle* h, const gpr_state* st, bool to_handle, cudaSt
         {h->mover_rot, st->mover_rot, 3 * B * sizeof(double)},
         {h->obj_pos, st->object_pos, 4 * B * sizeof(double)},
         {h->obj_vel, st->object_vel, 3 * B * sizeof(double)},
+        {h->needs_reset, st->needs_reset, B * sizeof(uint8_t)},
+        {h->ep_return, st->episode_return, B * sizeof(float)},
     };
     for (const Item& it : items) {
         if (!it.theirs) continue;
@@ -759,6 +761,18 @@ extern "C" int gpr_set_state(gpr_handle* h, const gpr_state* src, void* stream) 
     DeviceGuard g(h->device);
     if (src->goal) h->goal_dirty = true;
     return copy_state(h, src, true, (cudaStream_t)stream);
+}
+
+extern "C" int gpr_get_seed(const gpr_handle* h, uint64_t* seed) {
+    if (!h || !seed) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    *seed = h->seed;
+    return GPR_OK;
+}
+
+extern "C" int gpr_set_seed(gpr_handle* h, uint64_t seed) {
+    if (!h) return fail(GPR_ERR_INVALID_ARG, "handle is NULL");
+    h->seed = seed;
+    return GPR_OK;
 }
 
 extern "C" int gpr_compute_reward(gpr_handle* h, int batch, const float* achieved, const float* desired,

@@ -219,6 +219,8 @@ class BatchedCore:
             'goal': z((B, self.goal_dim // 2, 2)),
             'elapsed_steps': z((B,), torch.int32),
             'rng_counter': z((B,), torch.int32),  # uint32 bit pattern
+            'needs_reset': z((B,), torch.uint8),
+            'episode_return': z((B,), torch.float32),
         }
         if self.kind != ENV_PLANNING:
             st.update(act=z((B, 2)), mover_rot=z((B, 3)), object_pos=z((B, 4)), object_vel=z((B, 3)))
@@ -446,10 +448,19 @@ class _VecEnvBase:
         self.core.set_state(state)
 
     def state_dict(self):
-        """Checkpoint: SoA state tensors + RNG key."""
+        """Checkpoint: the SoA state tensors, the per-env RNG event counters and the RNG key in use.
+        ``load_state_dict`` on an env built with the same kwargs continues the run bit for bit."""
         st = {k: v.cpu() for k, v in self.core.get_state().items()}
-        st['seed'] = int(self.cfg.seed)
+        seed = ctypes.c_uint64()
+        _lib.check(self.core.lib.gpr_get_seed(self.core.handle, ctypes.byref(seed)))
+        st['seed'] = int(seed.value)
         return st
+
+    def load_state_dict(self, state):
+        state = dict(state)
+        seed = state.pop('seed')
+        self.core.set_state(state)
+        _lib.check(self.core.lib.gpr_set_seed(self.core.handle, ctypes.c_uint64(int(seed))))
 
     def episode_stats(self, reset: bool = True, all_reduce: bool = False):
         return self.core.episode_stats(reset, all_reduce)

@@ -16,6 +16,8 @@
  *   gpr_compute_reward <- compute_reward / compute_terminated        planning:459-534, pushing:457-527   (HER relabelling)
  *   gpr_get_state /
  *   gpr_set_state      <- MjData.qpos/qvel/act/qacc access           utils/mujoco_utils.py:23-190 (parity + checkpoint)
+ *   gpr_get_seed /
+ *   gpr_set_seed       <- np_random / rng_noise of reset(seed)       envs/basic_envs.py:1789-1791 (checkpoint)
  *   gpr_destroy        <- Env.close                                  planning:604-608
  *
  * Conventions
@@ -174,6 +176,9 @@ typedef struct gpr_state {
     double* mover_rot;   /* [num_envs, 3] cos(yaw), sin(yaw), yaw rate (orientation kept on the unit circle) */
     double* object_pos;  /* [num_envs, 4] x, y, cos(yaw), sin(yaw) */
     double* object_vel;  /* [num_envs, 3] vx, vy, yaw rate */
+    /* bookkeeping needed to resume an interrupted run exactly (checkpoint / restore) */
+    uint8_t* needs_reset;   /* [num_envs] NEXT_STEP auto-reset: the env finished in the previous step */
+    float* episode_return;  /* [num_envs] return accumulated so far in the running episode (episode statistics) */
 } gpr_state;
 
 typedef struct gpr_handle gpr_handle;
@@ -226,6 +231,11 @@ GPR_API int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_o
 /* Copy state out of / into the handle (device pointers, float64). */
 GPR_API int gpr_get_state(gpr_handle* h, const gpr_state* dst, void* stream);
 GPR_API int gpr_set_state(gpr_handle* h, const gpr_state* src, void* stream);
+
+/* The RNG key in use (gpr_reset with reseed != 0 replaces the one of the config).  gpr_set_seed changes the key WITHOUT
+ * touching the per-env event counters: together with gpr_set_state it restores a checkpoint exactly. */
+GPR_API int gpr_get_seed(const gpr_handle* h, uint64_t* seed);
+GPR_API int gpr_set_seed(gpr_handle* h, uint64_t seed);
 
 /* HER relabelling: batched compute_reward / compute_terminated on device.
  *   achieved, desired : float32 [batch, goal_dim]; mover_collision, wall_collision: [batch] bytes (NULL = all false)

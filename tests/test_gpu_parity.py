@@ -470,6 +470,33 @@ def test_desired_goal_on_change_survives_route_switches():
     env.close()
 
 
+@pytest.mark.parametrize('mode', ['same_step', 'next_step'])
+def test_checkpoint_resume_is_bit_exact(mode):
+    """state_dict() / load_state_dict(): a second env built with the same kwargs continues an interrupted run with
+    identical results (state, RNG event counters, RNG key after reset(seed), TimeLimit counters, NEXT_STEP bookkeeping)."""
+    rng = np.random.default_rng(29)
+    kw = dict(layout_tiles=np.ones((3, 3)), num_movers=4, std_noise=1e-5, seed=1, autoreset_mode=mode, max_episode_steps=6)
+    a_env = gpr.BenchmarkPlanningVecEnv(3000, device=DEV, **kw)
+    a_env.reset(seed=77)  # (not the constructor's seed: the checkpoint must carry the key in use)
+    acts = [torch.as_tensor(rng.uniform(-10, 10, (3000, 8)).astype(np.float32), device=DEV) for _ in range(16)]
+    for t in range(8):
+        a_env.step(acts[t])
+    ckpt = a_env.state_dict()
+    b_env = gpr.BenchmarkPlanningVecEnv(3000, device=DEV, **kw)
+    b_env.load_state_dict(ckpt)
+    for t in range(8, 16):
+        oa, ra, ta, tra, ia = a_env.step(acts[t])
+        ob, rb, tb, trb, ib = b_env.step(acts[t])
+        assert torch.equal(oa['observation'], ob['observation']) and torch.equal(oa['achieved_goal'], ob['achieved_goal'])
+        assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(tra, trb) and torch.equal(ia['is_success'], ib['is_success'])
+    sa, sb = a_env.get_state(), b_env.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert a_env.episode_stats()['episodes'] > 0
+    a_env.close()
+    b_env.close()
+
+
 def test_sharding_does_not_change_results():
     """Multi-GPU rule: the RNG is keyed by the GLOBAL env index, so one handle with 4096 envs and two
     handles with 2048 each (env_index_base 0 / 2048) produce identical trajectories."""
