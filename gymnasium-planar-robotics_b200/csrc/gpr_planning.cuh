@@ -1,22 +1,29 @@
 // gpr_planning.cuh — fused kernels of BenchmarkPlanningEnv's step path.
 //
-//   planning_step_kernel : basic:1835-1950 in one launch — action clip, num_cycles x { plan:420-450 limit control,
-//                          mj_step-equivalent integration, basic:459-788 wall check, basic:355-424 mover check, break on
-//                          collision }, plan:536-573 observation, plan:575-602 info, plan:502-534 reward,
-//                          plan:459-479 terminated, TimeLimit truncation, episode statistics and auto-reset
-//                          (plan:355-418 rejection sampling with the counter-based RNG of include/gpr_rng.h).
-//   planning_reset_kernel: basic:1770-1833 for a masked subset, optionally with injected starts / goals.
+//   planning_step_kernel     : basic:1835-1950 in one launch — action clip, num_cycles x { plan:420-450 limit control,
+//                              mj_step-equivalent integration, basic:459-788 wall check, basic:355-424 mover check, break
+//                              on collision }, plan:536-573 observation, plan:575-602 info, plan:502-534 reward,
+//                              plan:459-479 terminated, TimeLimit truncation, episode statistics; finished envs are
+//                              appended to a compacted reset list.
+//   planning_autoreset_kernel: plan:355-418 + basic:1797-1805 for the envs on that list, one warp per env (rejection
+//                              sampling of starts and goals with the counter-based RNG of include/gpr_rng.h).
+//   planning_reset_kernel    : basic:1770-1833 for a masked subset, optionally with injected starts / goals.
 //
-// Two exact optimisations shape the code (DESIGN.md "Kernels"):
+// Exact optimisations that shape the code (DESIGN.md "Kernels"); every one leaves the oracle's results bit for bit:
 //   * LAZY NOISE.  The sensor noise of the reference (sigma = 1e-5 by default) is drawn three times per mover and cycle
 //     (plan:430, basic:1888-1901) but only ever feeds comparisons.  The portable normal generator is bounded
 //     (|n| <= GPR_NORMAL_ABS_MAX), the RNG is counter-based (skipping a draw changes no other draw), so a comparison whose
-//     noise-free margin exceeds the noise bound has the same outcome with and without the noise.  The kernel evaluates
-//     each check noise-free first and generates the noise only inside the band where it can matter — bit-identical to
-//     always drawing it (which is what the oracle does).
-//   * WARP-COOPERATIVE REJECTION SAMPLING.  Acceptance of "all movers at once" sampling is ~1% for 4 movers on 3x3 tiles.
-//     All 32/G lane groups of the warp test DIFFERENT attempts of ONE environment in parallel (two attempts per Philox
-//     block) and the lowest accepted attempt index wins, which is exactly the sequential loop's result.
+//     noise-free margin exceeds the noise bound has the same outcome with and without the noise.  The kernels evaluate
+//     each check noise-free first and generate the noise only inside the band where it can matter.
+//   * FLOAT32 SCREENS WITH EXACT FALLBACK.  wall_core / pair_circle_fast / pair_box_screen decide a comparison in float32
+//     when its margin exceeds noise bound + rounding slack; only the thin uncertain band re-evaluates in float64.
+//   * TEMPORAL COHERENCE.  A check certifies a clearance; while a mover's accumulated travel stays below it the
+//     reference's check is known to be negative and is skipped (planning_step_kernel).
+//   * WARP-UNIFORM FREE-RUN PATH.  Control + integration without any clip or noise when no lane of the warp needs them.
+//   * REJECTION SAMPLING IN BULK.  Acceptance of "all movers at once" sampling is ~1% for 4 movers on 3x3 tiles.  For
+//     G <= 4 every lane screens two complete attempts (64 per warp iteration, sample_env_lanes); for wider groups all
+//     32/G lane groups test different attempts (sample_env_groups).  The lowest accepted attempt index wins, which is
+//     exactly the sequential loop's result.
 #pragma once
 
 #include "gpr_device.cuh"
