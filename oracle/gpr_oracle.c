@@ -6,7 +6,7 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.  The product
  * (gymnasium-planar-robotics_b200/) never links, imports or falls back to anything in this directory.
  *
- * Pinning (see tests/test_oracle_vs_reference.py, tests/golden/):
+ * Pinning (tests/test_oracle_vs_reference.py live against the mounted reference, tests/test_oracle_golden.py on the committed vectors of tests/golden/):
  *   - gpro_qpos_is_valid, gpro_check_mover_collision, gpro_segments_intersect, gpro_rectangles_intersect,
  *     gpro_ensure_max_dyn_val, gpro_planning_reward are compared against the UNMODIFIED reference functions (imported
  *     from /root/reference with mujoco/gymnasium stubbed, tests/ref_harness.py) on the reference's own 100+34 test
@@ -113,7 +113,7 @@ void gpro_rect_vertices(const double qpos[7], const double size[2], double vx[4]
     for (int k = 0; k < 4; ++k) qf[k] = (float)qpos[3 + k];
     /* np.sum over the last axis of a (n,4) float32 array: out = d0; out += (0 + d1 + d2 + d3) is NOT what numpy does for
        a contiguous inner reduce of 4 elements: it accumulates left to right, ((d0+d1)+d2)+d3 (verified against the
-       reference in tests/test_oracle_vs_reference.py::test_rect_vertices_bit_exact). */
+       reference in tests/test_oracle_golden.py::test_rect_vertices). */
     float s = qf[0] * qf[0];
     s = s + qf[1] * qf[1];
     s = s + qf[2] * qf[2];
