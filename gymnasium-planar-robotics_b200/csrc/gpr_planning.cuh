@@ -1215,42 +1215,63 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
     }
 }
 
-// plan:355-418 + basic:1770-1833 for the envs on the reset list: ONE WARP PER ENVIRONMENT.  All 32/G lane groups test
-// different rejection-sampling attempts; lane group 0 then acts as the env's movers for the reset-time checks, the first
-// observation and the state write.  Warps pull list entries through an atomic cursor (attempt counts are geometric).
+// plan:355-418 + basic:1770-1833 for the envs on the reset list.  A warp pulls a BATCH of 32/G list entries through an
+// atomic cursor (attempt counts are geometric, so work is balanced dynamically).  The rejection sampling of the batch's
+// envs runs one env after the other with the whole warp working on that env (sample_env); lane group g keeps the result
+// of the batch's g-th env.  Everything after the sampling — reset-time checks, first observation, state and output
+// stores — then runs ONCE for the whole batch with every lane group acting as the movers of its own env (instead of
+// once per env with only G of the 32 lanes active).
 template <int G, bool BOX, bool NOISE>
 __global__ void __launch_bounds__(128, GPR_AR_MINB) planning_autoreset_kernel(const __grid_constant__ PlanArgs a) {
     __shared__ Tables tb;
     load_tables(tb, a.L);
     __syncthreads();
+    constexpr unsigned S = 32u / G;  // envs per batch
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned grp = lane / G;
     const uint32_t count = a.reset_count[a.parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the other buffer belongs to the next step: clear it now
         a.reset_count[a.parity ^ 1] = 0u;
         a.reset_cursor[a.parity ^ 1] = 0u;
     }
+    // batch size: as many envs as there are lane groups, but never so many that warps of the grid would stay without work
+    const unsigned warps = gridDim.x * (blockDim.x / 32u);
+    const unsigned bs = min(S, max(1u, (count + warps - 1u) / warps));
     for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(a.reset_cursor + a.parity, 1u);
-        i = __shfl_sync(FULL, i, 0);
-        if (i >= count) break;
+        uint32_t i0 = 0;
+        if (lane == 0) i0 = atomicAdd(a.reset_cursor + a.parity, bs);
+        i0 = __shfl_sync(FULL, i0, 0);
+        if (i0 >= count) break;
+        const unsigned nb = min(bs, count - i0);  // envs in this batch
         Lane<G> ln;
         ln.lane = lane;
         ln.gmask = group_mask<G>(lane);
-        ln.env = a.reset_list[i];
         ln.m = (int)(lane % G);
-        ln.env_ok = true;
-        ln.active = lane < (unsigned)G && ln.m < a.N;  // lane group 0 carries the env
+        ln.env_ok = grp < nb;
+        ln.env = ln.env_ok ? a.reset_list[i0 + grp] : 0;
+        ln.active = ln.env_ok && ln.m < a.N;
         ln.idx = (size_t)ln.env * (size_t)a.N + (size_t)ln.m;
         ln.env_global = a.env_base + (uint32_t)ln.env;
-        const uint32_t event = a.rng[ln.env];
+        const uint32_t event = ln.env_ok ? a.rng[ln.env] : 0u;
         double2 p = make_double2(0, 0), v = p, acc = p, goal = p;
-        bool failed = false, f2 = false;
-        sample_env<G, BOX, 0>(a, tb, lane, ln.gmask, ln.env_global, event, p, failed);
-        sample_env<G, BOX, 1>(a, tb, lane, ln.gmask, ln.env_global, event, goal, f2);
-        failed = failed || f2;
+        bool failed = false;
+#pragma unroll 1
+        for (unsigned b = 0; b < nb; ++b) {  // the whole warp samples for the batch's b-th env
+            const uint32_t eg = __shfl_sync(FULL, ln.env_global, (int)(b * G));
+            const uint32_t ev = __shfl_sync(FULL, event, (int)(b * G));
+            double2 pb = p, gb = p;
+            bool f1 = false, f2 = false;
+            sample_env<G, BOX, 0>(a, tb, lane, ln.gmask, eg, ev, pb, f1);  // every lane: position of mover lane % G
+            sample_env<G, BOX, 1>(a, tb, lane, ln.gmask, eg, ev, gb, f2);
+            if (grp == b) {
+                p = pb;
+                goal = gb;
+                failed = f1 || f2;
+            }
+        }
+        // ---- the rest for all envs of the batch at once: lane group g = the movers of env g
         bool mc = false, wc = false;
-        reset_checks<G, BOX, NOISE>(a, tb, ln, lane < (unsigned)G, event, p, mc, wc);
+        reset_checks<G, BOX, NOISE>(a, tb, ln, ln.env_ok, event, p, mc, wc);
         double2 ag, ov;
         int reached;
         observe<G, NOISE>(a, ln, event, p, v, goal, ag, ov, reached);
@@ -1261,7 +1282,7 @@ __global__ void __launch_bounds__(128, GPR_AR_MINB) planning_autoreset_kernel(co
             a.acc[ln.idx] = acc;
             a.goal[ln.idx] = goal;
         }
-        if (lane == 0) {
+        if (ln.env_ok && ln.m == 0) {
             a.rng[ln.env] = event + 1u;
             a.elapsed[ln.env] = 0;
             if (failed) atomicAdd(a.fail_count, 1u);
