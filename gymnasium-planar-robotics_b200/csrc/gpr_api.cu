@@ -57,8 +57,8 @@ struct gpr_handle {
     float* ep_return = nullptr;
     double* stats = nullptr;
     uint32_t* fail_count = nullptr;
-    int32_t* reset_list = nullptr;    // auto-reset work list (see planning_autoreset_kernel)
-    uint32_t* reset_count = nullptr;  // [2] count, [2] cursor
+    unsigned long long* reset_list = nullptr;  // auto-reset work list (see planning_autoreset_kernel)
+    unsigned long long* reset_count = nullptr;  // [2] control words (reported warps, reserved slots), then [2] uint32 cursors
     int parity = 0;
     int num_sms = 148;
     // pushing state
@@ -236,6 +236,7 @@ extern "C" int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_ha
     TRY(dalloc(&h->stats, 6));
     TRY(dalloc(&h->fail_count, 1));
     TRY(dalloc(&h->reset_list, B));
+    CU(cudaMemset(h->reset_list, 0xFF, std::max<size_t>(B, 1) * sizeof(unsigned long long)));  // all ones: slot not published
     TRY(dalloc(&h->reset_count, 4));
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (cfg->env_kind == GPR_ENV_PUSHING) {
@@ -291,6 +292,15 @@ static LayoutArgs layout_args(const gpr_handle* h) {
     L.cy = h->cy;
     L.cell = h->cell;
     return L;
+}
+
+// GPR_NO_OVERLAP=1: launch the auto-reset kernel the ordinary way (after the step kernel has drained); for A/B timing
+static bool no_overlap() {
+    static const bool v = [] {
+        const char* e = getenv("GPR_NO_OVERLAP");
+        return e && e[0] == '1';
+    }();
+    return v;
 }
 
 static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
@@ -382,8 +392,9 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     a.stats = h->stats;
     a.fail_count = h->fail_count;
     a.reset_list = h->reset_list;
-    a.reset_count = h->reset_count;
-    a.reset_cursor = h->reset_count + 2;
+    a.reset_ctl = h->reset_count;
+    a.reset_cursor = reinterpret_cast<uint32_t*>(h->reset_count + 2);
+    a.overlap = (h->timing || no_overlap()) ? 0 : 1;  // (an event between the two launches would break the pairing)
     a.parity = h->parity;
     if (out) a.out = *out;
     return a;

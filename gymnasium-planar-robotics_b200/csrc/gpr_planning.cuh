@@ -72,10 +72,14 @@ struct PlanArgs {
     float* ep_return;
     double* stats;         // 6 accumulators, see gpr_episode_stats
     uint32_t* fail_count;  // number of resets whose rejection loop hit max_reset_attempts
-    // auto-reset work list: the step kernel appends finished envs, the auto-reset kernel consumes them (one warp per env)
-    int32_t* reset_list;     // [B]
-    uint32_t* reset_count;   // [2] double-buffered by step parity
-    uint32_t* reset_cursor;  // [2]
+    // auto-reset work list: the step kernel appends finished envs, the auto-reset kernel consumes them — WHILE the step
+    // kernel is still running when the two are launched as a programmatic dependent pair (see planning_autoreset_kernel).
+    unsigned long long* reset_list;  // [B]  (RNG event << 32 | env); all ones = slot not published (consumers restore it)
+    unsigned long long* reset_ctl;   // [2]  (warps of the step kernel that have reported << 32 | slots reserved),
+                                     //      double-buffered by step parity
+    uint32_t* reset_cursor;          // [2]  slots claimed by consumers
+    unsigned step_ctas;      // grid size of the step kernel (set by the launcher)
+    int overlap;             // host side: launch the auto-reset kernel as the step kernel's programmatic dependent
     int parity;
     int write_goal;  // 0: the step kernel leaves desired_goal rows of envs that were not reset alone (GPR_OUT_GOAL_ON_CHANGE)
     // per-call I/O
@@ -892,6 +896,9 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
 
 template <int G, bool BOX, bool NOISE>
 __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const __grid_constant__ PlanArgs a) {
+    // the auto-reset kernel that follows in the stream may become resident as soon as every CTA of this grid has started
+    // (programmatic dependent launch): its warps then fill the SM slots the last, partial wave of this grid leaves idle
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ Tables tb;
     load_tables(tb, a.L);
     __syncthreads();
@@ -1105,6 +1112,29 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
     const bool trunc = stepped && a.max_episode_steps > 0 && elapsed >= a.max_episode_steps;  // gymnasium TimeLimit
     const bool done = stepped && (term || trunc);
 
+    // ------------------------------------------------------------------ auto-reset: hand finished envs to the reset kernel
+    // The consumer may already be running (see planning_autoreset_kernel).  An entry carries all the consumer needs of the
+    // env (index and RNG event) in one 64-bit store, the env's state is not written back (the reset rewrites all of it),
+    // and the one store of this kernel that the consumer overwrites — the early desired_goal row — is fenced before the
+    // entry.  Every warp reports exactly once, with the slots it reserves in the same atomic: when all warps of the grid
+    // have reported the count is final.  SAME_STEP publishes here, ahead of this kernel's result stores; NEXT_STEP (the
+    // consumer also rewrites the per-env flags, which other threads of the CTA store) after them, behind a barrier.
+    bool need = false;
+    if (a.autoreset == GPR_AUTORESET_SAME_STEP) need = done;
+    if (a.autoreset == GPR_AUTORESET_NEXT_STEP) need = ln.env_ok && pending_reset;
+    const bool handed = need && a.autoreset == GPR_AUTORESET_SAME_STEP;  // nothing of this env's state is stored below
+    auto publish = [&]() {
+        const unsigned leaders = __ballot_sync(FULL, need && ln.m == 0);
+        if (need && a.write_goal) __threadfence();  // (the early desired_goal store, if there was one)
+        unsigned long long t = 0ull;
+        if (ln.lane == 0) t = atomicAdd(a.reset_ctl + a.parity, (1ull << 32) | (unsigned long long)__popc(leaders));
+        const unsigned slot0 = (unsigned)__shfl_sync(FULL, t, 0);
+        if (need && ln.m == 0)
+            *reinterpret_cast<volatile unsigned long long*>(a.reset_list + slot0 + __popc(leaders & ((1u << ln.lane) - 1u))) =
+                ((unsigned long long)event << 32) | (unsigned long long)(uint32_t)ln.env;
+    };
+    if (a.autoreset == GPR_AUTORESET_SAME_STEP) publish();
+
     // episode statistics (one lane per env accumulates, one atomic per warp and counter)
     {
         const bool lead = ln.env_ok && ln.m == 0;
@@ -1183,44 +1213,51 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
         }
     }
 
-    // ------------------------------------------------------------------ auto-reset: hand finished envs to the reset kernel
-    bool need = false;
-    if (a.autoreset == GPR_AUTORESET_SAME_STEP) need = done;
-    if (a.autoreset == GPR_AUTORESET_NEXT_STEP) need = ln.env_ok && pending_reset;
-    {
-        const unsigned leaders = __ballot_sync(FULL, need && ln.m == 0);
-        if (leaders) {
-            unsigned slot0 = 0;
-            if (ln.lane == 0) slot0 = atomicAdd(a.reset_count + a.parity, (unsigned)__popc(leaders));
-            slot0 = __shfl_sync(FULL, slot0, 0);
-            if (need && ln.m == 0) a.reset_list[slot0 + __popc(leaders & ((1u << ln.lane) - 1u))] = ln.env;
-        }
+    if (a.autoreset == GPR_AUTORESET_NEXT_STEP) {
+        __threadfence();
+        __syncthreads();
+        publish();
     }
-    if (need && a.autoreset == GPR_AUTORESET_SAME_STEP)
+
+    // ------------------------------------------------------------------ final observation / observation rows
+    if (handed)
         store_obs<G>(a, ln, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, ov, acc, ag, goal);
     // (the rows of envs handed to planning_autoreset_kernel are written there: first observation of the new episode)
-    if (stepped && !(need && a.autoreset == GPR_AUTORESET_SAME_STEP))
-        store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, nullptr, ov, acc, ag, goal);
+    if (stepped && !handed) store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, nullptr, ov, acc, ag, goal);
 
     // ------------------------------------------------------------------ state write-back
-    if (ln.active && stepped) {
+    if (ln.active && stepped && !handed) {
         a.pos[ln.idx] = p;
         a.vel[ln.idx] = v;
         a.acc[ln.idx] = acc;
     }
-    if (ln.env_ok && ln.m == 0 && stepped) {
+    if (ln.env_ok && ln.m == 0 && stepped && !handed) {
         a.rng[ln.env] = event;
         a.elapsed[ln.env] = elapsed;
         if (a.autoreset == GPR_AUTORESET_NEXT_STEP) a.needs_reset[ln.env] = done ? 1 : 0;
     }
 }
 
-// plan:355-418 + basic:1770-1833 for the envs on the reset list.  A warp pulls a BATCH of 32/G list entries through an
-// atomic cursor (attempt counts are geometric, so work is balanced dynamically).  The rejection sampling of the batch's
-// envs runs one env after the other with the whole warp working on that env (sample_env); lane group g keeps the result
-// of the batch's g-th env.  Everything after the sampling — reset-time checks, first observation, state and output
-// stores — then runs ONCE for the whole batch with every lane group acting as the movers of its own env (instead of
-// once per env with only G of the 32 lanes active).
+// plan:355-418 + basic:1770-1833 for the envs on the reset list.  A warp claims a BATCH of up to 32/G list entries through an
+// atomic cursor (attempt counts are geometric, so work is balanced dynamically; the batch shrinks with the work that is
+// left).  The rejection sampling of the batch's envs runs one env after the other with the whole warp working on that
+// env (sample_env); lane group g keeps the result of the batch's g-th env.  Everything after the sampling — reset-time
+// checks, first observation, state and output stores — then runs ONCE for the whole batch with every lane group acting
+// as the movers of its own env (instead of once per env with only G of the 32 lanes active).
+//
+// STREAMING.  gpr_step launches this kernel as the programmatic dependent of planning_step_kernel: its CTAs become
+// resident as soon as the last CTA of the step grid has started and consume list entries while the step kernel's last
+// wave is still running (a 65,536-env step is 3.5 waves: the partial wave leaves half of the SM slots idle for a quarter
+// of the kernel).  There is no grid-level dependency: an entry is valid once its slot holds an env index (published by
+// the step kernel after a fence), and a warp leaves when every warp of the step grid has reported (reset_ctl) and the cursor has
+// reached the final count.  Launched the ordinary way (per-kernel timing, profilers) the same code simply finds
+// everything published.
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <int G, bool BOX, bool NOISE>
 __global__ void __launch_bounds__(128, GPR_AR_MINB) planning_autoreset_kernel(const __grid_constant__ PlanArgs a) {
     __shared__ Tables tb;
@@ -1229,30 +1266,74 @@ __global__ void __launch_bounds__(128, GPR_AR_MINB) planning_autoreset_kernel(co
     constexpr unsigned S = 32u / G;  // envs per batch
     const unsigned lane = threadIdx.x & 31u;
     const unsigned grp = lane / G;
-    const uint32_t count = a.reset_count[a.parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the other buffer belongs to the next step: clear it now
-        a.reset_count[a.parity ^ 1] = 0u;
+        a.reset_ctl[a.parity ^ 1] = 0ull;
         a.reset_cursor[a.parity ^ 1] = 0u;
     }
-    // batch size: as many envs as there are lane groups, but never so many that warps of the grid would stay without work
     const unsigned warps = gridDim.x * (blockDim.x / 32u);
-    const unsigned bs = min(S, max(1u, (count + warps - 1u) / warps));
+    const unsigned step_warps = a.step_ctas * 8u;  // (planning_step_kernel: 256 threads per CTA)
+    uint32_t* const cursor = a.reset_cursor + a.parity;
     for (;;) {
-        uint32_t i0 = 0;
-        if (lane == 0) i0 = atomicAdd(a.reset_cursor + a.parity, bs);
+        // ---- claim [i0, i0 + nb) once the cursor is behind the slots reserved so far (a plain atomicAdd: a claim that
+        //      races past the count simply waits until producers have reserved those slots too, or learns that none will);
+        //      nb = 0: the step kernel is done and nothing is left
+        uint32_t i0 = 0, nb = 0;
+        if (lane == 0) {
+            unsigned spins = 0;
+            bool claimed = false;
+            for (;;) {
+                const unsigned long long ctl = ld_acquire_u64(a.reset_ctl + a.parity);
+                const bool done = (unsigned)(ctl >> 32) >= step_warps;  // every warp has reported: the count is final
+                const uint32_t cnt = (uint32_t)ctl;
+                if (!claimed) {
+                    const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(cursor);
+                    if (cur < cnt) {
+                        // as many envs as there are lane groups, but never so many that other warps would stay without work
+                        nb = min(S, max(1u, (cnt - cur + warps - 1u) / warps));
+                        i0 = atomicAdd(cursor, nb);
+                        claimed = true;
+                    }
+                }
+                if (claimed) {
+                    if (cnt >= i0 + nb) break;
+                    if (done) {
+                        nb = cnt > i0 ? cnt - i0 : 0u;
+                        break;
+                    }
+                } else if (done) {
+                    break;
+                }
+                __nanosleep(200);
+                if (++spins > (1u << 24)) {  // (~seconds: a step grid that never reports in must not hang the device)
+                    atomicAdd(a.fail_count, 1u << 20);
+                    nb = 0;
+                    break;
+                }
+            }
+        }
         i0 = __shfl_sync(FULL, i0, 0);
-        if (i0 >= count) break;
-        const unsigned nb = min(bs, count - i0);  // envs in this batch
+        nb = __shfl_sync(FULL, nb, 0);
+        if (nb == 0) break;
         Lane<G> ln;
         ln.lane = lane;
         ln.gmask = group_mask<G>(lane);
         ln.m = (int)(lane % G);
         ln.env_ok = grp < nb;
-        ln.env = ln.env_ok ? a.reset_list[i0 + grp] : 0;
+        unsigned long long entry = 0ull;
+        if (ln.env_ok) {  // the slot is reserved; its entry follows within the producer's next few instructions
+            volatile unsigned long long* slot = a.reset_list + i0 + grp;
+            do {
+                entry = *slot;
+            } while (entry == ~0ull);
+        }
+        __syncwarp();
+        if (ln.env_ok && ln.m == 0) a.reset_list[i0 + grp] = ~0ull;  // leave the list empty for the next step
+        __threadfence();  // (the producer's early desired_goal store is ordered before the row written below)
+        ln.env = (int)(uint32_t)entry;
         ln.active = ln.env_ok && ln.m < a.N;
         ln.idx = (size_t)ln.env * (size_t)a.N + (size_t)ln.m;
         ln.env_global = a.env_base + (uint32_t)ln.env;
-        const uint32_t event = ln.env_ok ? a.rng[ln.env] : 0u;
+        const uint32_t event = (uint32_t)(entry >> 32);
         double2 p = make_double2(0, 0), v = p, acc = p, goal = p;
         bool failed = false;
 #pragma unroll 1

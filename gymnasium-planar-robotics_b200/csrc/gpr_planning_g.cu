@@ -10,10 +10,12 @@
 namespace gpr {
 
 template <int G, bool BOX, bool NOISE>
-static cudaError_t launch_plan_gbn(PlanKernel which, const PlanArgs& a, int num_sms, cudaStream_t s) {
+static cudaError_t launch_plan_gbn(PlanKernel which, const PlanArgs& a_in, int num_sms, cudaStream_t s) {
     const int threads = 256;
-    const long long lanes = (long long)a.B * G;
+    const long long lanes = (long long)a_in.B * G;
     const unsigned blocks = (unsigned)((lanes + threads - 1) / threads);
+    PlanArgs a = a_in;
+    a.step_ctas = blocks;  // planning_autoreset_kernel waits until all of its warps have reported (reset_ctl)
     if (which == PLAN_RESET) {
         planning_reset_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
     } else if (which == PLAN_STEP) {
@@ -21,7 +23,22 @@ static cudaError_t launch_plan_gbn(PlanKernel which, const PlanArgs& a, int num_
     } else {
         // one warp per finished env, pulled through an atomic cursor: a fixed grid of 8 CTAs (4 warps each) per SM
         const unsigned ab = (unsigned)std::min<long long>(((long long)a.B + 3) / 4, (long long)num_sms * 8);
-        planning_autoreset_kernel<G, BOX, NOISE><<<ab, 128, 0, s>>>(a);
+        if (!a.overlap) {
+            planning_autoreset_kernel<G, BOX, NOISE><<<ab, 128, 0, s>>>(a);
+        } else {
+            // programmatic dependent launch: resident as soon as every CTA of the step grid (the previous launch in
+            // this stream) has started; the kernel synchronises with the step kernel through the work list itself
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ab);
+            cfg.blockDim = dim3(128);
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, planning_autoreset_kernel<G, BOX, NOISE>, a);
+        }
     }
     return cudaGetLastError();
 }

@@ -630,3 +630,37 @@ def test_single_env_and_pettingzoo_forms():
     alive = ~term['mover_0']
     assert torch.allclose(obs['mover_1']['observation'][alive, 2:], torch.full((int(alive.sum()), 2), 4.0, device=DEV), atol=1e-5)
     pz.close()
+
+
+@pytest.mark.parametrize('mode', ['same_step', 'next_step'])
+@pytest.mark.parametrize('movers,num_envs', [(4, 65536), (8, 20000), (2, 262144 + 7)])
+def test_streamed_autoreset_equals_serial_launches(mode, movers, num_envs):
+    """gpr_step launches the auto-reset kernel as the step kernel's programmatic dependent: it consumes the work list while
+    the step kernel's last wave is still publishing into it.  With per-kernel timing switched on the two kernels run one
+    after the other (an event sits between them).  Both orders must give identical results, step after step, at batch
+    sizes of several waves (random actions: a third of the envs is reset in every step)."""
+    kw = dict(layout_tiles=np.ones((5, 5)) if movers == 8 else np.ones((3, 3)), num_movers=movers, std_noise=1e-5, seed=5,
+              autoreset_mode=mode, max_episode_steps=7)
+    a_env = gpr.BenchmarkPlanningVecEnv(num_envs, device=DEV, **kw)
+    b_env = gpr.BenchmarkPlanningVecEnv(num_envs, device=DEV, **kw)
+    b_env.core.kernel_times(True)  # serial launches
+    a_env.reset(seed=5)
+    b_env.reset(seed=5)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    for t in range(25):
+        act = (torch.rand((num_envs, 2 * movers), device=DEV, generator=gen) * 2 - 1) * 10
+        oa, ra, ta, tra, ia = a_env.step(act)
+        ob, rb, tb, trb, ib = b_env.step(act)
+        for k in ('observation', 'achieved_goal', 'desired_goal'):
+            assert torch.equal(oa[k], ob[k]), (t, k)
+        assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(tra, trb), t
+        for k in ('is_success', 'mover_collision', 'wall_collision'):
+            assert torch.equal(ia[k], ib[k]), (t, k)
+    sa, sb = a_env.get_state(), b_env.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert a_env.core.reset_failures() == 0 and b_env.core.reset_failures() == 0
+    assert a_env.episode_stats()['episodes'] > num_envs  # the work list really was busy
+    b_env.core.kernel_times(False)
+    a_env.close()
+    b_env.close()
