@@ -888,14 +888,33 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
 #define GPR_PRAGMA_(x) _Pragma(#x)
 #define GPR_UNROLL(n) GPR_PRAGMA_(unroll n)
 #ifndef GPR_STEP_MINB
-#define GPR_STEP_MINB 2
+#define GPR_STEP_MINB 3  // resident threads per SM the step kernel is compiled for, in units of 256 (circle shape)
+#endif
+#ifndef GPR_STEP_MINB_BOX
+#define GPR_STEP_MINB_BOX 2  // same for the box shape (more live state: a tighter register cap spills)
 #endif
 #ifndef GPR_AR_MINB
-#define GPR_AR_MINB 4
+#define GPR_AR_MINB 3  // CTAs of 128 threads per SM the auto-reset kernel is compiled for (circle shape)
 #endif
+#ifndef GPR_AR_MINB_BOX
+#define GPR_AR_MINB_BOX 4
+#endif
+// measured on B200 (planning4 at 65,536 / 1,048,576 envs, planning8box): step kernel 256 threads x 2 CTAs/SM 0.136 / 1.56 ms,
+// 128 x 6 (80 registers) 0.118 / 1.22 ms, 64 x 12 0.116 / 1.21 ms, 128 x 8 (64 registers) 0.121 / 1.25 ms; the box shape
+// spills under any cap below 128 registers (2.14 -> 2.35 ms).  Auto-reset kernel: 3 / 4 / 6 / 8 CTAs per SM 0.108 / 0.112 /
+// 0.112 / 0.122 ms (circle), 0.79 / 0.74 / 0.74 / 0.73 ms (box).
+#ifndef GPR_STEP_THREADS
+#define GPR_STEP_THREADS 128
+#endif
+// threads per CTA of planning_step_kernel: at least 8 envs per CTA (the CTA-gathered flag stores work in 8-byte units)
+template <int G>
+struct StepThreads {
+    static constexpr int value = GPR_STEP_THREADS >= 8 * G ? GPR_STEP_THREADS : 8 * G;
+};
 
 template <int G, bool BOX, bool NOISE>
-__global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const __grid_constant__ PlanArgs a) {
+__global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BOX : GPR_STEP_MINB) * 256 / StepThreads<G>::value)
+    planning_step_kernel(const __grid_constant__ PlanArgs a) {
     // the auto-reset kernel that follows in the stream may become resident as soon as every CTA of this grid has started
     // (programmatic dependent launch): its warps then fill the SM slots the last, partial wave of this grid leaves idle
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -1170,7 +1189,7 @@ __global__ void __launch_bounds__(256, GPR_STEP_MINB) planning_step_kernel(const
     // live in pinned host memory every such fragment is its own PCIe write: measured 47 us per step for 0.3 MB).
     // Envs that did not step (NEXT_STEP mode, pending reset) get zeros here and their real values from the auto-reset kernel.
     {
-        constexpr int EPC = 256 / G;  // envs per CTA (>= 8)
+        constexpr int EPC = StepThreads<G>::value / G;  // envs per CTA (>= 8)
         __shared__ __align__(16) uint8_t s_flag[5][EPC];
         __shared__ __align__(16) float s_rew[EPC];
         const int le = (int)threadIdx.x / G;
@@ -1259,7 +1278,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 }
 
 template <int G, bool BOX, bool NOISE>
-__global__ void __launch_bounds__(128, GPR_AR_MINB) planning_autoreset_kernel(const __grid_constant__ PlanArgs a) {
+__global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) planning_autoreset_kernel(const __grid_constant__ PlanArgs a) {
     __shared__ Tables tb;
     load_tables(tb, a.L);
     __syncthreads();
@@ -1271,7 +1290,7 @@ __global__ void __launch_bounds__(128, GPR_AR_MINB) planning_autoreset_kernel(co
         a.reset_cursor[a.parity ^ 1] = 0u;
     }
     const unsigned warps = gridDim.x * (blockDim.x / 32u);
-    const unsigned step_warps = a.step_ctas * 8u;  // (planning_step_kernel: 256 threads per CTA)
+    const unsigned step_warps = a.step_ctas * (unsigned)(StepThreads<G>::value / 32);
     uint32_t* const cursor = a.reset_cursor + a.parity;
     for (;;) {
         // ---- claim [i0, i0 + nb) once the cursor is behind the slots reserved so far (a plain atomicAdd: a claim that

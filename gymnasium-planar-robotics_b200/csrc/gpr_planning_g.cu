@@ -14,12 +14,13 @@ static cudaError_t launch_plan_gbn(PlanKernel which, const PlanArgs& a_in, int n
     const int threads = 256;
     const long long lanes = (long long)a_in.B * G;
     const unsigned blocks = (unsigned)((lanes + threads - 1) / threads);
+    const unsigned step_blocks = (unsigned)((lanes + StepThreads<G>::value - 1) / StepThreads<G>::value);
     PlanArgs a = a_in;
-    a.step_ctas = blocks;  // planning_autoreset_kernel waits until all of its warps have reported (reset_ctl)
+    a.step_ctas = step_blocks;  // planning_autoreset_kernel waits until all of its warps have reported (reset_ctl)
     if (which == PLAN_RESET) {
         planning_reset_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
     } else if (which == PLAN_STEP) {
-        planning_step_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
+        planning_step_kernel<G, BOX, NOISE><<<step_blocks, StepThreads<G>::value, 0, s>>>(a);
     } else {
         // one warp per finished env, pulled through an atomic cursor: a fixed grid of 8 CTAs (4 warps each) per SM
         const unsigned ab = (unsigned)std::min<long long>(((long long)a.B + 3) / 4, (long long)num_sms * 8);
