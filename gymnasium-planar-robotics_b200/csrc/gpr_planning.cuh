@@ -903,6 +903,10 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
 // 128 x 6 (80 registers) 0.118 / 1.22 ms, 64 x 12 0.116 / 1.21 ms, 128 x 8 (64 registers) 0.121 / 1.25 ms; the box shape
 // spills under any cap below 128 registers (2.14 -> 2.35 ms).  Auto-reset kernel: 3 / 4 / 6 / 8 CTAs per SM 0.108 / 0.112 /
 // 0.112 / 0.122 ms (circle), 0.79 / 0.74 / 0.74 / 0.73 ms (box).
+// Tried on top of that and measured slower (planning4, step kernel 0.111 ms): refreshing the wall budget of EVERY mover of a
+// warp whenever one of them is due (0.117 ms: more lanes reach the exact fallback), and "blind runs" — k cycles of bare
+// integration without per-cycle budget tests, k from a closed-form bound of the travel (0.134 ms: with 32 movers per warp
+// one of them is nearly always within a few cycles of its wall budget, so k is 0 or 1 and its computation is overhead).
 #ifndef GPR_STEP_THREADS
 #define GPR_STEP_THREADS 128
 #endif
@@ -912,7 +916,7 @@ struct StepThreads {
     static constexpr int value = GPR_STEP_THREADS >= 8 * G ? GPR_STEP_THREADS : 8 * G;
 };
 
-template <int G, bool BOX, bool NOISE>
+template <int G, bool BOX, bool NOISE, bool JERK>
 __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BOX : GPR_STEP_MINB) * 256 / StepThreads<G>::value)
     planning_step_kernel(const __grid_constant__ PlanArgs a) {
     // the auto-reset kernel that follows in the stream may become resident as soon as every CTA of this grid has started
@@ -984,11 +988,11 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         // ensure_max_dyn_val passes its inputs through: qacc = a (acc mode) or act + dt*j (jerk mode, integrator actuator
         // with actearly, plan:305-311), qvel += dt*qacc.  The sums below are the very expressions the general path
         // evaluates (same operands, same two roundings), so both paths produce identical bits.
-        const double nax = a.learn_jerk ? dadd(dmul(a.dt, u.x), acc.x) : u.x;
-        const double nay = a.learn_jerk ? dadd(dmul(a.dt, u.y), acc.y) : u.y;
+        const double nax = JERK ? dadd(dmul(a.dt, u.x), acc.x) : u.x;
+        const double nay = JERK ? dadd(dmul(a.dt, u.y), acc.y) : u.y;
         const double tx = dadd(dmul(a.dt, nax), v.x), ty = dadd(dmul(a.dt, nay), v.y);
         bool free_run = dadd(dmul(tx, tx), dmul(ty, ty)) < (NOISE ? a.v_lazy2 : a.v_max2_lo);
-        if (a.learn_jerk) free_run = free_run && dadd(dmul(nax, nax), dmul(nay, nay)) < a.a_max2_lo;
+        if (JERK) free_run = free_run && dadd(dmul(nax, nax), dmul(nay, nay)) < a.a_max2_lo;
         if (!__any_sync(FULL, part && !free_run)) {
             if (part) {
                 acc.x = nax;
@@ -999,7 +1003,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         } else if (part) {
             // general path; d = derivative entering the velocity clip (action or limited acc)
             double dxv = u.x, dyv = u.y, jx = 0.0, jy = 0.0;
-            if (a.learn_jerk) ensure_max(acc.x, acc.y, a.a_max, a.a_max2_lo, u.x, u.y, a.dt, dxv, dyv, jx, jy);  // plan:434
+            if (JERK) ensure_max(acc.x, acc.y, a.a_max, a.a_max2_lo, u.x, u.y, a.dt, dxv, dyv, jx, jy);  // plan:434
             double velx = v.x, vely = v.y;
             if (NOISE) {
                 // the velocity noise can only matter if the un-noised |dt*d + v| is within its bound of v_max
@@ -1013,7 +1017,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
             }
             double t0, t1, ax, ay;
             ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);  // plan:437 / 442
-            if (a.learn_jerk) {
+            if (JERK) {
                 if (dxv != ax || dyv != ay) {  // plan:438
                     jx = ddiv(dsub(ax, acc.x), a.dt);
                     jy = ddiv(dsub(ay, acc.y), a.dt);

@@ -20,7 +20,9 @@ static cudaError_t launch_plan_gbn(PlanKernel which, const PlanArgs& a_in, int n
     if (which == PLAN_RESET) {
         planning_reset_kernel<G, BOX, NOISE><<<blocks, threads, 0, s>>>(a);
     } else if (which == PLAN_STEP) {
-        planning_step_kernel<G, BOX, NOISE><<<step_blocks, StepThreads<G>::value, 0, s>>>(a);
+        // (learn_jerk is a template parameter of the step kernel only: it sits inside the 40-cycle loop)
+        if (a.learn_jerk) planning_step_kernel<G, BOX, NOISE, true><<<step_blocks, StepThreads<G>::value, 0, s>>>(a);
+        else planning_step_kernel<G, BOX, NOISE, false><<<step_blocks, StepThreads<G>::value, 0, s>>>(a);
     } else {
         // one warp per finished env, pulled through an atomic cursor: a fixed grid of 8 CTAs (4 warps each) per SM
         const unsigned ab = (unsigned)std::min<long long>(((long long)a.B + 3) / 4, (long long)num_sms * 8);
