@@ -1165,17 +1165,14 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         if (lead && stepped) ret = a.ep_return[ln.env] + reward;
         const bool fin = lead && done;
         if (__any_sync(FULL, fin)) {
-            double s_ep = fin ? 1.0 : 0.0, s_ret = fin ? (double)ret : 0.0, s_len = fin ? (double)elapsed : 0.0;
-            double s_succ = (fin && succ) ? 1.0 : 0.0, s_mc = (fin && mc) ? 1.0 : 0.0, s_wc = (fin && wc) ? 1.0 : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s_ep += __shfl_xor_sync(FULL, s_ep, o);
-                s_ret += __shfl_xor_sync(FULL, s_ret, o);
-                s_len += __shfl_xor_sync(FULL, s_len, o);
-                s_succ += __shfl_xor_sync(FULL, s_succ, o);
-                s_mc += __shfl_xor_sync(FULL, s_mc, o);
-                s_wc += __shfl_xor_sync(FULL, s_wc, o);
-            }
+            // (planning rewards are whole numbers — -50, +50, -(movers off goal) — so every sum is an exact integer: one
+            //  warp-reduce instruction per counter)
+            const double s_ep = (double)__reduce_add_sync(FULL, fin ? 1 : 0);
+            const double s_ret = (double)__reduce_add_sync(FULL, fin ? (int)ret : 0);
+            const double s_len = (double)__reduce_add_sync(FULL, fin ? elapsed : 0);
+            const double s_succ = (double)__reduce_add_sync(FULL, (fin && succ) ? 1 : 0);
+            const double s_mc = (double)__reduce_add_sync(FULL, (fin && mc) ? 1 : 0);
+            const double s_wc = (double)__reduce_add_sync(FULL, (fin && wc) ? 1 : 0);
             if (ln.lane == 0) {
                 atomicAdd(a.stats + 0, s_ep);
                 atomicAdd(a.stats + 1, s_ret);

@@ -462,6 +462,13 @@ class _VecEnvBase:
         self.core.set_state(state)
         _lib.check(self.core.lib.gpr_set_seed(self.core.handle, ctypes.c_uint64(int(seed))))
 
+    def debug_view(self, env_index: int = 0, ppm: float = 400.0) -> np.ndarray:
+        """(H, W, 3) uint8 picture of ONE env — tiles, movers, collision shapes, goals, velocities (``debug_view.py``; the
+        stand-in for the reference's ``Matplotlib2DViewer``, utils/rendering.py:283-507, off the step path)."""
+        from . import debug_view
+
+        return debug_view.view_of_env(self, env_index, ppm)
+
     def episode_stats(self, reset: bool = True, all_reduce: bool = False):
         return self.core.episode_stats(reset, all_reduce)
 
@@ -550,6 +557,9 @@ class _SingleEnvBase:
     def render(self):
         return None
 
+    def debug_view(self, ppm: float = 400.0) -> np.ndarray:
+        return self._vec.debug_view(0, ppm)
+
     def close(self):
         self._vec.close()
 
@@ -635,6 +645,9 @@ class BenchmarkPlanningParallelEnv:
 
     def state(self):
         return self._vec.get_state()
+
+    def debug_view(self, env_index: int = 0, ppm: float = 400.0) -> np.ndarray:
+        return self._vec.debug_view(env_index, ppm)
 
     def close(self):
         self._vec.close()

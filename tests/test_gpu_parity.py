@@ -664,3 +664,31 @@ def test_streamed_autoreset_equals_serial_launches(mode, movers, num_envs):
     b_env.core.kernel_times(False)
     a_env.close()
     b_env.close()
+
+
+def test_debug_view_draws_the_chosen_env():
+    """env.debug_view(i): the picture is made from the state of env i alone (movers where get_state says they are)."""
+    from gymnasium_planar_robotics_b200 import debug_view as dv
+
+    env = gpr.BenchmarkPlanningVecEnv(300, layout_tiles=np.ones((3, 3)), num_movers=3, device=DEV, seed=2)
+    env.reset(seed=2)
+    st = env.get_state()
+    ppm = 400.0
+    for i in (0, 123, 299):
+        img = env.debug_view(i, ppm=ppm)
+        assert img.shape == (288, 288, 3) and img.dtype == np.uint8
+        pos = st['pos'][i].cpu().numpy()
+        for m in range(3):
+            # a point inside mover m's body, off the velocity arrow and the outlines
+            x, y = pos[m, 0] + 0.04, pos[m, 1] - 0.04
+            assert tuple(int(c) for c in img[img.shape[0] - 1 - int(y * ppm), int(x * ppm)]) == dv.PALETTE[m]
+    push = gpr.BenchmarkPushingVecEnv(50, device=DEV, seed=3)
+    push.reset(seed=3)
+    img = push.debug_view(7, ppm=ppm)
+    ob = push.get_state()['object_pos'][7].cpu().numpy()
+    assert tuple(int(c) for c in img[img.shape[0] - 1 - int(ob[1] * ppm), int(ob[0] * ppm)]) == dv.OBJECT_COLOUR
+    single = gpr.BenchmarkPlanningEnv(layout_tiles=np.ones((3, 3)), num_movers=2)
+    single.reset(seed=1)
+    assert single.debug_view().shape == (288, 288, 3) and single.render() is None
+    for e in (env, push, single):
+        e.close()
