@@ -369,6 +369,32 @@ __device__ __forceinline__ void store_obs(const PlanArgs& a, const Lane<G>& ln, 
     if (DG) reinterpret_cast<float2*>(DG)[ln.idx] = make_float2((float)goal.x, (float)goal.y);
 }
 
+// Instruction-cache footprint of the auto-reset kernel.  With starts and goals each running their own inlined copy of the
+// sampling loop, the kernel's hot code is ~23 KB spread over 64 KB — more than the 32 KB L1.5 instruction cache once the
+// step kernel's warps share the SM (the two kernels overlap, see planning_autoreset_kernel) — and "no instruction" was its
+// top stall reason (profiles/r1b_full_planning4.txt).  GPR_SAMPLER_ONE_COPY: for the circle shape the kind of sample is a
+// run-time argument and both kinds go through ONE copy of the loop.  Measured on B200 (planning4, 65,536 / 1,048,576 envs):
+// two copies 276 M / 449 M env-steps/s; one copy 318 M / 462 M; one copy with the Philox block out of line
+// (GPR_SAMPLER_PHILOX_CALL=1) 303 M / 437 M; out-of-line Philox with two copies 283 M / 441 M.
+#ifndef GPR_SAMPLER_PHILOX_CALL
+#define GPR_SAMPLER_PHILOX_CALL 0
+#endif
+#ifndef GPR_SAMPLER_ONE_COPY
+#define GPR_SAMPLER_ONE_COPY 1
+#endif
+#ifndef GPR_SAMPLER_ROLL_H
+#define GPR_SAMPLER_ROLL_H 0
+#endif
+#if GPR_SAMPLER_PHILOX_CALL
+static __device__ __noinline__ gpr_u32x4 sampler_block(uint64_t seed, uint32_t eg, uint32_t ev, uint32_t stream, uint32_t lane) {
+    return gpr_rng_block(seed, eg, ev, stream, lane);
+}
+#else
+__device__ __forceinline__ gpr_u32x4 sampler_block(uint64_t seed, uint32_t eg, uint32_t ev, uint32_t stream, uint32_t lane) {
+    return gpr_rng_block(seed, eg, ev, stream, lane);
+}
+#endif
+
 // ---- warp-cooperative rejection sampling (plan:369-385 starts / plan:395-413 goals) ----------------------------------
 // For every lane group with `need`, find the FIRST attempt t (t = 0, 1, 2, ...) whose N positions pass the test, exactly as
 // the reference's sequential while-loop would, but with all 32/G groups of the warp testing different attempts of the
@@ -462,7 +488,7 @@ __device__ __forceinline__ void sample_env_groups(const PlanArgs& a, const Table
 #pragma unroll 1
     for (int t0 = 0; t0 < cap && !found; t0 += 2 * S) {
         const uint32_t blk = (uint32_t)(t0 / 2 + slot);
-        const gpr_u32x4 r = gpr_rng_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)KIND, (uint32_t)m);
+        const gpr_u32x4 r = sampler_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)KIND, (uint32_t)m);
         // ---- phase 1, float32: ~99% of the attempts die on a pair that is far inside the rejection band
         unsigned cand_bits = 0u, needx_bits = 0u;
 #pragma unroll
@@ -599,8 +625,12 @@ __device__ __forceinline__ bool confirm_attempt(const PlanArgs& a, const Tables&
 #endif
 template <int G, bool BOX, int KIND>
 __device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables& tb, unsigned lane, uint32_t eg, uint32_t ev,
-                                                 double2& out, bool& failed) {
+                                                 double2& out, bool& failed, int kind_rt = 0) {
+    // KIND < 0 (circle shape only): the kind is a run-time argument, so that starts and goals share ONE copy of this loop
+    // (instruction-cache footprint of the auto-reset kernel); they differ in thresholds and in the exact confirmation only
     static_assert(G <= 8, "one lane draws all movers: register budget");
+    static_assert(KIND >= 0 || !BOX, "run-time kind: circle shape only");
+    const int kind = KIND < 0 ? kind_rt : KIND;
     const int N = a.N;
     const int cap = a.max_reset_attempts > 0 ? a.max_reset_attempts : 1;
     const int m_self = (int)(lane % G);
@@ -613,8 +643,8 @@ __device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables
         sf[m] = (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
     }
     const float mg = a.pair_mgf[0];
-    const bool uni = KIND == 1 || a.uniform_pairs != 0;
-    const float lo2u = KIND == 1 ? a.goal_lo2f : a.pair_lo2f[1][0], hi2u = KIND == 1 ? a.goal_hi2f : a.pair_hi2f[1][0];
+    const bool uni = kind == 1 || a.uniform_pairs != 0;
+    const float lo2u = kind == 1 ? a.goal_lo2f : a.pair_lo2f[1][0], hi2u = kind == 1 ? a.goal_hi2f : a.pair_hi2f[1][0];
     bool found = false;
 #pragma unroll 1
     for (int t0 = 0; t0 < cap && !found; t0 += 64) {
@@ -622,18 +652,23 @@ __device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables
         gpr_u32x4 r[G];
 #pragma unroll
         for (int m = 0; m < G; ++m) {
-            if (m < N) r[m] = gpr_rng_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)KIND, (uint32_t)m);
+            if (m < N) r[m] = sampler_block(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE + 2u * blk + (uint32_t)kind, (uint32_t)m);
             else r[m].v[0] = r[m].v[1] = r[m].v[2] = r[m].v[3] = 0u;
         }
         unsigned accb = 0u, uncb = 0u;  // this lane's pair-screen verdicts for its attempts h = 0, 1
+#if GPR_SAMPLER_ROLL_H
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int h = 0; h < 2; ++h) {
             float xf[G], yf[G];
 #pragma unroll
             for (int m = 0; m < G; ++m) {
                 // (lanes of a group wider than num_movers: park the spare movers far away from everything, no branches)
-                xf[m] = m < N ? fmaf(a.spanxf, (float)r[m].v[2 * h] * 2.3283064365386963e-10f, a.minxf) : 1e8f * (float)(m + 1);
-                yf[m] = m < N ? fmaf(a.spanyf, (float)r[m].v[2 * h + 1] * 2.3283064365386963e-10f, a.minyf) : 0.f;
+                const uint32_t wx = h ? r[m].v[2] : r[m].v[0], wy = h ? r[m].v[3] : r[m].v[1];
+                xf[m] = m < N ? fmaf(a.spanxf, (float)wx * 2.3283064365386963e-10f, a.minxf) : 1e8f * (float)(m + 1);
+                yf[m] = m < N ? fmaf(a.spanyf, (float)wy * 2.3283064365386963e-10f, a.minyf) : 0.f;
             }
             bool rej = false, unc = false;
 #pragma unroll
@@ -641,7 +676,7 @@ __device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables
 #pragma unroll
                 for (int j = i + 1; j < G; ++j) {
                     const float dx = xf[i] - xf[j], dy = yf[i] - yf[j];
-                    if (KIND == 0 && BOX) {
+                    if (BOX && kind == 0) {
                         // axis-aligned rectangles: a gap along x or y is a certain miss, overlap along both axes a certain
                         // hit when all boxes have one size (else containment, which geom:107-138 does not report, is possible)
                         const float tx = rf[i] + rf[j], ty = sf[i] + sf[j];
@@ -685,7 +720,14 @@ __device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables
                     py = dadd(a.min_xy[1], dmul(a.span_xy[1], gpr_uniform32(wy)));
                 }
             }
-            if (confirm_attempt<G, BOX, KIND>(a, tb, lane, px, py, certain, eg, ev)) {
+            bool ok;
+            if constexpr (KIND < 0) {
+                ok = kind == 0 ? confirm_attempt<G, BOX, 0>(a, tb, lane, px, py, certain, eg, ev)
+                               : confirm_attempt<G, BOX, 1>(a, tb, lane, px, py, certain, eg, ev);
+            } else {
+                ok = confirm_attempt<G, BOX, KIND>(a, tb, lane, px, py, certain, eg, ev);
+            }
+            if (ok) {
                 out = make_double2(px, py);
                 found = true;
             } else if (h0 == 0) {
@@ -700,7 +742,7 @@ __device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables
     if (!found) {
         // the reference would loop forever (plan:369); keep the last attempt's sample and report the failure
         double ux, uy;
-        gpr_sample_xy(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE, (uint32_t)KIND, (uint32_t)(cap - 1), (uint32_t)m_self, &ux, &uy);
+        gpr_sample_xy(a.seed, eg, ev, GPR_RNG_RESET_SAMPLE, (uint32_t)kind, (uint32_t)(cap - 1), (uint32_t)m_self, &ux, &uy);
         out = make_double2(dadd(a.min_xy[0], dmul(a.span_xy[0], ux)), dadd(a.min_xy[1], dmul(a.span_xy[1], uy)));
         failed = true;
     }
@@ -1362,8 +1404,24 @@ __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) plan
             const uint32_t ev = __shfl_sync(FULL, event, (int)(b * G));
             double2 pb = p, gb = p;
             bool f1 = false, f2 = false;
-            sample_env<G, BOX, 0>(a, tb, lane, ln.gmask, eg, ev, pb, f1);  // every lane: position of mover lane % G
-            sample_env<G, BOX, 1>(a, tb, lane, ln.gmask, eg, ev, gb, f2);
+            if constexpr (!BOX && G <= GPR_LANES_MAX_G && GPR_SAMPLER_ONE_COPY) {
+#pragma unroll 1
+                for (int kind = 0; kind < 2; ++kind) {  // starts, then goals, through one copy of the sampling loop
+                    double2 r = p;
+                    bool f = false;
+                    sample_env_lanes<G, BOX, -1>(a, tb, lane, eg, ev, r, f, kind);
+                    if (kind == 0) {
+                        pb = r;
+                        f1 = f;
+                    } else {
+                        gb = r;
+                        f2 = f;
+                    }
+                }
+            } else {
+                sample_env<G, BOX, 0>(a, tb, lane, ln.gmask, eg, ev, pb, f1);  // every lane: position of mover lane % G
+                sample_env<G, BOX, 1>(a, tb, lane, ln.gmask, eg, ev, gb, f2);
+            }
             if (grp == b) {
                 p = pb;
                 goal = gb;

@@ -5,7 +5,7 @@
 # tools/ncu_summary.py, tools/sass_hist.py and tools/attribute_lines.py turn the captures into the summaries under profiles/.
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 400 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 timeout 600 python bench.py > gpurun_out/bench_planning4.log 2>&1
 timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.log 2>&1
@@ -16,4 +16,4 @@ CMD="python bench.py --steps 10 --warmup 3 --quick --no-cpu"
 timeout 300 $CMD > gpurun_out/plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 timeout 300 $CMD > gpurun_out/plain.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:planning_ -s 8 -c 2 -o gpurun_out/prof_planning4 $CMD > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:planning_ -s 8 -c 2 -f -o gpurun_out/prof_planning4 $CMD > gpurun_out/ncu_full.log 2>&1
