@@ -16,9 +16,10 @@ from typing import Any
 
 import numpy as np
 
-GPR_ABI_VERSION = 1
+GPR_ABI_VERSION = 2
 GPR_MAX_MOVERS = 32
 GPR_MAX_TILES_1D = 32
+GPR_MAX_OBSTACLES = 8
 
 ENV_PLANNING, ENV_PUSHING = 0, 1
 SHAPE_CIRCLE, SHAPE_BOX = 0, 1
@@ -86,6 +87,10 @@ class GprConfig(ctypes.Structure):
         ('solimp', ctypes.c_double * 5),
         ('contact_iterations', ctypes.c_int32),
         ('output_flags', ctypes.c_int32),
+        ('num_obstacles', ctypes.c_int32),
+        ('reserved0', ctypes.c_int32),
+        ('obstacle_xy', (ctypes.c_double * 2) * GPR_MAX_OBSTACLES),
+        ('obstacle_size', (ctypes.c_double * 2) * GPR_MAX_OBSTACLES),
     ]
 
 
@@ -103,6 +108,7 @@ class GprOutputs(ctypes.Structure):
         ('final_observation', ctypes.c_void_p),
         ('final_achieved_goal', ctypes.c_void_p),
         ('final_desired_goal', ctypes.c_void_p),
+        ('other_collision', ctypes.c_void_p),
     ]
 
 
@@ -361,8 +367,13 @@ def planning_config(
     seed: int = 0,
     reference_quirks: bool = False,
     goal_output_on_change: bool = True,
+    obstacles=None,
 ) -> tuple[GprConfig, dict[str, Any]]:
-    """kwargs of ``BenchmarkPlanningEnv`` (planning:165-185) -> ``gpr_config``."""
+    """kwargs of ``BenchmarkPlanningEnv`` (planning:165-185) -> ``gpr_config``.
+
+    ``obstacles``: static obstacles, the typed form of ``_check_for_other_collisions_callback`` (basic_envs.py:1976-1986):
+    an array (K, 3) of ``[x, y, radius]`` rows for the circle collision shape or (K, 4) of ``[x, y, half_x, half_y]`` rows
+    (axis-aligned) for the box shape, K <= 8.  See ``gpr_config.num_obstacles`` in include/gpr.h for the rules."""
     del mover_colors_2D_plot, render_every_cycle, initial_mover_zpos  # visual only / z is not simulated (SURVEY §3.4)
     _reject_out_of_scope({} if mover_params is None else mover_params, render_mode, show_2D_plot, use_mj_passive_viewer)
     cfg = GprConfig()
@@ -399,6 +410,22 @@ def planning_config(
         min_goal_dist = 2 * np.linalg.norm(cs + d['c_size_offset'], ord=2)
     cfg.min_goal_dist = float(min_goal_dist)
     d['min_goal_dist'] = float(min_goal_dist)
+    obst = np.zeros((0, 4)) if obstacles is None else np.asarray(obstacles, dtype=np.float64)
+    if obst.size:
+        want = 3 if d['c_shape'] == 'circle' else 4
+        if obst.ndim != 2 or obst.shape[1] != want:
+            raise ValueError(f"obstacles must have shape (K, {want}) for collision shape '{d['c_shape']}' "
+                             f"([x, y, radius] / [x, y, half_x, half_y]), got {obst.shape}")
+        if obst.shape[0] > GPR_MAX_OBSTACLES:
+            raise ValueError(f'at most {GPR_MAX_OBSTACLES} obstacles')
+        if not (np.isfinite(obst).all() and (obst[:, 2:] > 0).all()):
+            raise ValueError('obstacle sizes must be finite and > 0')
+        cfg.num_obstacles = int(obst.shape[0])
+        for k in range(obst.shape[0]):
+            cfg.obstacle_xy[k][0], cfg.obstacle_xy[k][1] = float(obst[k, 0]), float(obst[k, 1])
+            cfg.obstacle_size[k][0] = float(obst[k, 2])
+            cfg.obstacle_size[k][1] = float(obst[k, 3]) if want == 4 else float(obst[k, 2])
+    d['obstacles'] = obst
     d['obs_dim'] = num_movers * (1 + int(bool(learn_jerk))) * 2
     d['goal_dim'] = num_movers * 2
     d['action_dim'] = num_movers * 2

@@ -161,6 +161,12 @@ static int validate(const gpr_config* c) {
         return fail(GPR_ERR_INVALID_ARG, "autoreset_mode unknown");
     if (c->env_index_base < 0 || (uint64_t)c->env_index_base + (uint64_t)c->num_envs > (1ull << 32))
         return fail(GPR_ERR_INVALID_ARG, "global env indices must fit 32 bits");
+    if (c->num_obstacles < 0 || c->num_obstacles > GPR_MAX_OBSTACLES) return fail(GPR_ERR_INVALID_ARG, "num_obstacles out of range");
+    if (c->num_obstacles > 0 && c->env_kind != GPR_ENV_PLANNING)
+        return fail(GPR_ERR_UNSUPPORTED, "static obstacles are a planning-env feature");
+    for (int k = 0; k < c->num_obstacles; ++k)
+        if (!(c->obstacle_size[k][0] > 0) || (c->c_shape == GPR_SHAPE_BOX && !(c->obstacle_size[k][1] > 0)))
+            return fail(GPR_ERR_INVALID_ARG, "obstacle sizes must be > 0");
     for (int m = 0; m < c->num_movers; ++m)
         for (int s = 0; s < 2; ++s) {
             if (!(c->c_wall[s][m][0] > 0) || !(c->c_mover[s][m][0] > 0))
@@ -374,6 +380,15 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     // too large for the bound: a huge extent then makes the screen defer to the exact test every time)
     a.rot_extf = !h->noise ? 0.f : (c.std_noise[0] < 5e-3 ? (float)(14.0 * c.std_noise[0]) : 1e3f);
     a.inv_dtf = (float)((1.0 / c.cycle_time) * (1.0 - 1e-6));
+    // static obstacles: float32 screen slack = position-noise bound + float rounding of coordinates up to the layout extent
+    a.n_obst = c.num_obstacles;
+    a.obst_delta = (float)((h->noise ? 6.0 * c.std_noise[0] * 1.01 : 0.0) + 4e-6 * std::max(1.0, extent) + 2e-6);
+    for (int k = 0; k < c.num_obstacles; ++k) {
+        a.obst[k][0] = c.obstacle_xy[k][0];
+        a.obst[k][1] = c.obstacle_xy[k][1];
+        a.obst[k][2] = c.obstacle_size[k][0];
+        a.obst[k][3] = c.obstacle_size[k][1];
+    }
     a.inv_wxf = (float)(1.0 / (2.0 * c.tile_half[0]));
     a.inv_wyf = (float)(1.0 / (2.0 * c.tile_half[1]));
     a.sigma_p = c.std_noise[0];
@@ -586,8 +601,9 @@ extern "C" int gpr_kernel_times(gpr_handle* h, int enable, double* host_ms) {
 // ---------------------------------------------------------------------------------------------------------------------
 // host-buffer entry points (what a user of the reference calls: NumPy in, NumPy out)
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int kOutSlots = 13;  // pointers in gpr_outputs
 struct StageLayout {
-    size_t off_action, off[12], bytes[12], total;
+    size_t off_action, off[kOutSlots], bytes[kOutSlots], total;
 };
 
 static StageLayout stage_layout(const gpr_handle* h) {
@@ -600,10 +616,10 @@ static StageLayout stage_layout(const gpr_handle* h) {
         return o;
     };
     L.off_action = take(B * h->action_dim * sizeof(float));
-    const size_t sz[12] = {B * h->obs_dim * sizeof(float), B * h->goal_dim * sizeof(float), B * h->goal_dim * sizeof(float),
-                           B * sizeof(float), B, B, B, B, B,
-                           B * h->obs_dim * sizeof(float), B * h->goal_dim * sizeof(float), B * h->goal_dim * sizeof(float)};
-    for (int k = 0; k < 12; ++k) {
+    const size_t sz[kOutSlots] = {B * h->obs_dim * sizeof(float), B * h->goal_dim * sizeof(float), B * h->goal_dim * sizeof(float),
+                                  B * sizeof(float), B, B, B, B, B,
+                                  B * h->obs_dim * sizeof(float), B * h->goal_dim * sizeof(float), B * h->goal_dim * sizeof(float), B};
+    for (int k = 0; k < kOutSlots; ++k) {
         L.bytes[k] = sz[k];
         L.off[k] = take(sz[k]);
     }
@@ -623,10 +639,11 @@ static int ensure_stage(gpr_handle* h) {
 }
 
 static void** out_slot(gpr_outputs* o, int k) {
-    void** slots[12] = {(void**)&o->observation,      (void**)&o->achieved_goal,       (void**)&o->desired_goal,
+    void** slots[kOutSlots] = {(void**)&o->observation,      (void**)&o->achieved_goal,       (void**)&o->desired_goal,
                         (void**)&o->reward,           (void**)&o->terminated,          (void**)&o->truncated,
                         (void**)&o->is_success,       (void**)&o->mover_collision,     (void**)&o->wall_collision,
-                        (void**)&o->final_observation, (void**)&o->final_achieved_goal, (void**)&o->final_desired_goal};
+                        (void**)&o->final_observation, (void**)&o->final_achieved_goal, (void**)&o->final_desired_goal,
+                        (void**)&o->other_collision};
     return slots[k];
 }
 
@@ -647,8 +664,8 @@ static void* device_alias(const void* p) {
 //   pageable destination    -> device staging, then one async copy into the handle's pinned mirror and a memcpy
 struct HostRoute {
     gpr_outputs dev;   // pointers handed to the kernels
-    bool staged[12];   // field k goes through d_stage (copy engine afterwards)
-    void* pinned[12];  // staged field whose destination is page-locked: the copy engine writes it directly
+    bool staged[kOutSlots];   // field k goes through d_stage (copy engine afterwards)
+    void* pinned[kOutSlots];  // staged field whose destination is page-locked: the copy engine writes it directly
 };
 
 // GPR_HOST_IO=dma: results of *_host calls always go through device staging and the copy engine (into the caller's buffer
@@ -665,7 +682,7 @@ static HostRoute route_outputs(gpr_handle* h, const StageLayout& L, const gpr_ou
     HostRoute r;
     gpr_outputs ho = *host_out;
     memset(&r, 0, sizeof(r));
-    for (int k = 0; k < 12; ++k) {
+    for (int k = 0; k < kOutSlots; ++k) {
         void* dst = *out_slot(&ho, k);
         if (!dst) continue;
         void* alias = device_alias(dst);
@@ -681,12 +698,12 @@ static int finish_host_call(gpr_handle* h, const StageLayout& L, const HostRoute
     gpr_outputs ho = *host_out;
     char* hs = (char*)h->h_stage;
     char* ds = (char*)h->d_stage;
-    for (int k = 0; k < 12; ++k)
+    for (int k = 0; k < kOutSlots; ++k)
         if (r.staged[k])
             CU(cudaMemcpyAsync(r.pinned[k] ? r.pinned[k] : (void*)(hs + L.off[k]), ds + L.off[k], L.bytes[k], cudaMemcpyDeviceToHost,
                                h->host_stream));
     CU(cudaStreamSynchronize(h->host_stream));  // results (zero-copy stores included) are visible to the host after this
-    for (int k = 0; k < 12; ++k)
+    for (int k = 0; k < kOutSlots; ++k)
         if (r.staged[k] && !r.pinned[k]) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
     return GPR_OK;
 }

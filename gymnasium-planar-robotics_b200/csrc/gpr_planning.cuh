@@ -59,6 +59,10 @@ struct PlanArgs {
     float goal_lo2f, goal_hi2f;              // min_goal_dist bands
     float minxf, minyf, spanxf, spanyf;      // spawn box as float
     LayoutArgs L;
+    // static obstacles (gpr_config.num_obstacles): x, y, size0, size1 — circle radius / box half sizes
+    int n_obst;
+    float obst_delta;  // float32 screen slack: position-noise bound + float rounding
+    double obst[GPR_MAX_OBSTACLES][4];
     const double* c_wall;   // [2][GPR_MAX_MOVERS][2] device
     const double* c_mover;  // [2][GPR_MAX_MOVERS][2] device
     // state (SoA, float64)
@@ -336,6 +340,55 @@ __device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part,
     }
 }
 
+// ---- static obstacles (the typed form of basic:1976-1986, see gpr_config.num_obstacles) -------------------------------
+// Exact test of ONE mover against every obstacle, on the position (x, y) the caller has made noisy or not; (s0, s1) are the
+// mover's collision sizes, rm its rectangle (box shape).  Mirrors gpro_check_obstacle_collision of the oracle.
+template <bool BOX>
+static __device__ __noinline__ bool obstacle_hit_exact(const PlanArgs& a, double x, double y, double s0, const Rect& rm) {
+#pragma unroll 1
+    for (int k = 0; k < a.n_obst; ++k) {
+        const double ox = a.obst[k][0], oy = a.obst[k][1];
+        if (!BOX) {
+            const double dx = dsub(x, ox), dy = dsub(y, oy);
+            if (dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))) <= dadd(s0, a.obst[k][2])) return true;
+        } else {
+            const double h0 = a.obst[k][2], h1 = a.obst[k][3];
+            if (fabs(dsub(x, ox)) <= h0 && fabs(dsub(y, oy)) <= h1) return true;  // centre inside: the edge test is blind to it
+            Rect ro;
+            rect_vertices_axis(ox, oy, h0, h1, ro);
+            if (rects_intersect(rm, ro)) return true;
+        }
+    }
+    return false;
+}
+// float32 screen: 0 = certain miss (clear = distance the mover may still travel before that can change), 1 = certain hit
+// (circle only), 2 = too close to call.  (e0, e1): circle radius / bounding half extents of the (noise-rotated) box.
+template <bool BOX>
+__device__ __forceinline__ int obstacle_screen(const PlanArgs& a, double x, double y, float e0, float e1, float& clear) {
+    clear = 3.0e38f;
+    int verdict = 0;
+#pragma unroll 1
+    for (int k = 0; k < a.n_obst; ++k) {
+        const float dx = fabsf((float)dsub(x, a.obst[k][0])), dy = fabsf((float)dsub(y, a.obst[k][1]));
+        float gap;
+        if (!BOX) {
+            const float t = e0 + (float)a.obst[k][2];
+            const float d = sqrtf(dx * dx + dy * dy);
+            gap = d * 0.999999f - t * 1.000001f - a.obst_delta;
+            if (d * 1.000001f + a.obst_delta < t * 0.999999f) verdict = max(verdict, 1);
+            else if (!(gap > 0.f)) verdict = 2;
+        } else {
+            const float gx = dx * 0.999999f - (e0 + (float)a.obst[k][2]) * 1.000001f - a.obst_delta;
+            const float gy = dy * 0.999999f - (e1 + (float)a.obst[k][3]) * 1.000001f - a.obst_delta;
+            gap = fmaxf(gx, gy);
+            if (!(gap > 0.f)) verdict = 2;
+        }
+        clear = fminf(clear, fmaxf(gap, 0.f));
+    }
+    if (verdict != 0) clear = 0.f;
+    return verdict;
+}
+
 // One observation row (plan:536-573) + the per-env reductions the reward needs.
 template <int G, bool NOISE>
 __device__ __forceinline__ void observe(const PlanArgs& a, const Lane<G>& ln, uint32_t event, double2 p, double2 v,
@@ -456,6 +509,11 @@ GPR_COLD(GPR_INL_CONFIRM) bool sample_confirm(const PlanArgs& a, const Tables& t
             Rect rw;
             if (BOX) rect_vertices_axis(x, y, cw0, cw1, rw);
             bad = !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);
+            if (a.n_obst > 0 && !bad) {  // starts and goals clear every obstacle by the safety offset
+                Rect rm;
+                if (BOX) rect_vertices_axis(x, y, cs0, cs1, rm);
+                bad = obstacle_hit_exact<BOX>(a, x, y, cs0, rm);
+            }
         }
         const unsigned badm = __ballot_sync(FULL, bad);
         okmask[h] = __ballot_sync(FULL, alive_grp && (badm & gmask) == 0u && m == 0);
@@ -614,6 +672,13 @@ __device__ __forceinline__ bool confirm_attempt(const PlanArgs& a, const Tables&
             bad = !wall_valid<BOX>(tb, a.L, x, y, cw0, rw);
         } else {
             bad = f == 0;
+        }
+        // starts and goals clear every obstacle by the safety offset (exact, no noise inside the sampling loop)
+        if (a.n_obst > 0 && !bad) {
+            const double cs0 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0], cs1 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
+            Rect rm;
+            if (BOX) rect_vertices_axis(x, y, cs0, cs1, rm);
+            bad = obstacle_hit_exact<BOX>(a, x, y, cs0, rm);
         }
     }
     return __ballot_sync(FULL, hit || bad) == 0u;
@@ -783,7 +848,7 @@ __device__ __forceinline__ void sample_positions(const PlanArgs& a, const Tables
 // basic:1799-1805: wall check WITH the safety offset, mover check WITHOUT, on independently noisy qpos (warp-collective)
 template <int G, bool BOX, bool NOISE>
 __device__ __forceinline__ void reset_checks(const PlanArgs& a, const Tables& tb, const Lane<G>& ln, bool need,
-                                             uint32_t event, double2 p, bool& mc, bool& wc) {
+                                             uint32_t event, double2 p, bool& mc, bool& wc, bool& oc) {
     const int mm = ln.active ? ln.m : 0;
     const double cw0 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 0], cw1 = a.c_wall[(GPR_MAX_MOVERS + mm) * 2 + 1];
     const double cm0 = a.c_mover[mm * 2 + 0], cm1 = a.c_mover[mm * 2 + 1];
@@ -885,11 +950,42 @@ __device__ __forceinline__ void reset_checks(const PlanArgs& a, const Tables& tb
             if (pany) hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0, kmask);
         }
     }
+    // basic:1807 the hook: static obstacles on the wall check's noisy qpos, with the safety offset like that wall check
+    bool obad = false;
+    if (a.n_obst > 0 && part) {
+        const double cs0 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 0], cs1 = a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
+        const float ext = BOX ? a.rot_extf * (float)(cs0 + cs1) : 0.f;
+        float clear_o;
+        const int f = obstacle_screen<BOX>(a, p.x, p.y, (float)cs0 + ext, (float)cs1 + ext, clear_o);
+        if (f == 2) {
+            double wx = p.x, wy = p.y;
+            Rect rm;
+            if (NOISE) {
+                float w4[4];
+                normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK, (uint32_t)ln.m, w4);
+                wx = noisy(p.x, w4[0], a.sigma_p);
+                wy = noisy(p.y, w4[1], a.sigma_p);
+                if (BOX) {
+                    float q[4];
+                    normal4_cold(a.seed, ln.env_global, event, GPR_RNG_RESET_CHECK_WQUAT, (uint32_t)ln.m, q);
+                    rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                                  dmul((double)q[3], a.sigma_p), cs0, cs1, rm);
+                }
+            } else if (BOX) {
+                rect_vertices_axis(wx, wy, cs0, cs1, rm);
+            }
+            obad = obstacle_hit_exact<BOX>(a, wx, wy, cs0, rm);
+        } else {
+            obad = f == 1;
+        }
+    }
     const bool wnow = (__ballot_sync(FULL, bad) & ln.gmask) != 0u;
     const bool mnow = (__ballot_sync(FULL, hit) & ln.gmask) != 0u;
+    const bool onow = (__ballot_sync(FULL, obad) & ln.gmask) != 0u;
     if (need) {
         wc = wnow;
         mc = mnow;
+        oc = onow;
     }
 }
 
@@ -898,7 +994,7 @@ template <int G, bool BOX, bool NOISE>
 __device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb, const Lane<G>& ln, bool need,
                                             uint32_t event, const double2* inj_start, const double2* inj_goal,
                                             double2& p, double2& v, double2& acc, double2& goal, bool& mc, bool& wc,
-                                            bool& failed) {
+                                            bool& oc, bool& failed) {
     failed = false;
     if (need && inj_start != nullptr && ln.active) p = inj_start[ln.idx];
     if (need && inj_goal != nullptr && ln.active) goal = inj_goal[ln.idx];
@@ -911,7 +1007,7 @@ __device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb,
         v = make_double2(0.0, 0.0);
         acc = make_double2(0.0, 0.0);
     }
-    reset_checks<G, BOX, NOISE>(a, tb, ln, need, event, p, mc, wc);
+    reset_checks<G, BOX, NOISE>(a, tb, ln, need, event, p, mc, wc, oc);
 }
 
 // reward / terminated / is_success for one env from the group reductions (plan:502-534, 459-479, 596-601)
@@ -1006,7 +1102,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
     // check is lane-local and runs for the lanes whose wall budget is used up; the pair check is warp-collective and
     // runs for the warp as soon as one of its envs has used up its pair budget.
     bool alive = ln.env_ok && !pending_reset;
-    bool mc = false, wc = false;
+    bool mc = false, wc = false, oc = false;
     int gi = 0, gj = 0;  // tile cell under the mover, tracked across cycles (movement per cycle is ~mm)
     guess_cell(a, p.x, p.y, gi, gj);
     // bounding rectangle / circle used by the float32 screens of the box shape (planning movers never rotate: the only
@@ -1085,7 +1181,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         if (!__any_sync(FULL, due_w || due_p)) continue;  // every mover of this warp is certified clear
 
         // ---- wall check (basic:1888-1894) of the lanes that are due: lane-local
-        bool bad = false;
+        bool bad = false, obad = false;
         if (due_w) {
             float clear_w;
             if (!BOX) {
@@ -1113,6 +1209,33 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
                     bad = !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
                     guess_cell(a, p.x, p.y, gi, gj);  // refresh the tracked cell
                 }
+            }
+            // ---- static obstacles (the hook of basic:1903), checked with the walls on the wall check's noisy qpos
+            if (a.n_obst > 0) {
+                float clear_o;
+                const int f = obstacle_screen<BOX>(a, p.x, p.y, BOX ? pxf : (float)cm0, pyf, clear_o);
+                if (f == 2) {
+                    double wx = p.x, wy = p.y;
+                    Rect rm;
+                    if (NOISE) {
+                        float w4[4];
+                        normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, w4);
+                        wx = noisy(p.x, w4[2], a.sigma_p);
+                        wy = noisy(p.y, w4[3], a.sigma_p);
+                        if (BOX) {
+                            float q[4];
+                            normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT, (uint32_t)ln.m, q);
+                            rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                                          dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
+                        }
+                    } else if (BOX) {
+                        rect_vertices_axis(wx, wy, cm0, cm1, rm);
+                    }
+                    obad = obstacle_hit_exact<BOX>(a, wx, wy, cm0, rm);
+                } else {
+                    obad = f == 1;
+                }
+                clear_w = fminf(clear_w, clear_o);
             }
             lim_w = (travel + clear_w * a.inv_dtf) * 0.999999f;
         }
@@ -1152,11 +1275,13 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
             lim_p = (travel + 0.5f * clear_p * a.inv_dtf) * 0.999999f;
         }
         const unsigned badm = __ballot_sync(FULL, bad), hitm = __ballot_sync(FULL, hit);
-        if (badm | hitm) {
+        const unsigned obm = a.n_obst > 0 ? __ballot_sync(FULL, obad) : 0u;
+        if (badm | hitm | obm) {
             if (alive) {
                 wc = (badm & ln.gmask) != 0u;
                 mc = (hitm & ln.gmask) != 0u;
-                if (wc || mc) alive = false;  // basic:1904 break
+                oc = (obm & ln.gmask) != 0u;
+                if (wc || mc || oc) alive = false;  // basic:1904 break
             }
             any_alive = __any_sync(FULL, alive);
         }
@@ -1169,7 +1294,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
     observe<G, NOISE>(a, ln, event, p, v, goal, ag, ov, reached);
     float reward;
     bool term, succ;
-    planning_reward(a.N, reached, mc, wc, reward, term, succ);
+    planning_reward(a.N, reached, mc || oc, wc, reward, term, succ);  // (an obstacle hit counts as a collision)
     if (stepped) {
         event += 1u;
         elapsed += 1;
@@ -1233,7 +1358,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
     // Envs that did not step (NEXT_STEP mode, pending reset) get zeros here and their real values from the auto-reset kernel.
     {
         constexpr int EPC = StepThreads<G>::value / G;  // envs per CTA (>= 8)
-        __shared__ __align__(16) uint8_t s_flag[5][EPC];
+        __shared__ __align__(16) uint8_t s_flag[6][EPC];
         __shared__ __align__(16) float s_rew[EPC];
         const int le = (int)threadIdx.x / G;
         const int env0 = (int)blockIdx.x * EPC;
@@ -1244,13 +1369,15 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
             s_flag[2][le] = stepped && succ;
             s_flag[3][le] = stepped && mc;
             s_flag[4][le] = stepped && wc;
+            s_flag[5][le] = stepped && oc;
         }
         __syncthreads();
-        uint8_t* const fo[5] = {a.out.terminated, a.out.truncated, a.out.is_success, a.out.mover_collision, a.out.wall_collision};
+        uint8_t* const fo[6] = {a.out.terminated, a.out.truncated, a.out.is_success, a.out.mover_collision, a.out.wall_collision,
+                                a.out.other_collision};
         const bool whole = env0 + EPC <= a.B;  // (the last CTA may be partial)
         constexpr int FU = EPC / 8, RU = EPC / 2;  // 8-byte units per flag array / of the reward array
         const int t = (int)threadIdx.x;
-        if (t < 5 * FU) {
+        if (t < 6 * FU) {
             const int f = t / FU, k = t % FU;
             uint8_t* dst = fo[f];
             if (dst) {
@@ -1429,8 +1556,8 @@ __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) plan
             }
         }
         // ---- the rest for all envs of the batch at once: lane group g = the movers of env g
-        bool mc = false, wc = false;
-        reset_checks<G, BOX, NOISE>(a, tb, ln, ln.env_ok, event, p, mc, wc);
+        bool mc = false, wc = false, oc = false;
+        reset_checks<G, BOX, NOISE>(a, tb, ln, ln.env_ok, event, p, mc, wc, oc);
         double2 ag, ov;
         int reached;
         observe<G, NOISE>(a, ln, event, p, v, goal, ag, ov, reached);
@@ -1449,7 +1576,7 @@ __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) plan
                 // gymnasium NEXT_STEP: this call only resets; reward 0, not done; info of the fresh episode
                 float r2;
                 bool t2, s2;
-                planning_reward(a.N, reached, mc, wc, r2, t2, s2);
+                planning_reward(a.N, reached, mc || oc, wc, r2, t2, s2);
                 a.needs_reset[ln.env] = 0;
                 if (a.out.reward) a.out.reward[ln.env] = 0.f;
                 if (a.out.terminated) a.out.terminated[ln.env] = 0;
@@ -1457,6 +1584,7 @@ __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) plan
                 if (a.out.is_success) a.out.is_success[ln.env] = s2;
                 if (a.out.mover_collision) a.out.mover_collision[ln.env] = mc;
                 if (a.out.wall_collision) a.out.wall_collision[ln.env] = wc;
+                if (a.out.other_collision) a.out.other_collision[ln.env] = oc;
             }
         }
     }
@@ -1476,8 +1604,8 @@ __global__ void __launch_bounds__(256) planning_reset_kernel(const __grid_consta
         p = a.pos[ln.idx];
         goal = a.goal[ln.idx];
     }
-    bool mc = false, wc = false, failed = false;
-    reset_group<G, BOX, NOISE>(a, tb, ln, need, event, a.inject_start, a.inject_goal, p, v, acc, goal, mc, wc, failed);
+    bool mc = false, wc = false, oc = false, failed = false;
+    reset_group<G, BOX, NOISE>(a, tb, ln, need, event, a.inject_start, a.inject_goal, p, v, acc, goal, mc, wc, oc, failed);
     double2 ag, ov;
     int reached;
     observe<G, NOISE>(a, ln, event, p, v, goal, ag, ov, reached);
@@ -1492,10 +1620,11 @@ __global__ void __launch_bounds__(256) planning_reset_kernel(const __grid_consta
     if (ln.m == 0) {
         float r;
         bool t, s;
-        planning_reward(a.N, reached, mc, wc, r, t, s);
+        planning_reward(a.N, reached, mc || oc, wc, r, t, s);
         if (a.out.is_success) a.out.is_success[ln.env] = s;
         if (a.out.mover_collision) a.out.mover_collision[ln.env] = mc;
         if (a.out.wall_collision) a.out.wall_collision[ln.env] = wc;
+        if (a.out.other_collision) a.out.other_collision[ln.env] = oc;
         a.rng[ln.env] = event + 1u;
         a.elapsed[ln.env] = 0;
         a.ep_return[ln.env] = 0.f;

@@ -115,6 +115,8 @@ class BatchedCore:
             'mover_collision': z((B,), u8),
             'wall_collision': z((B,), u8),
         }
+        if int(getattr(cfg, 'num_obstacles', 0)) > 0:  # (the reference's info has no such key: only present with obstacles)
+            self.buf['other_collision'] = z((B,), u8)
         if int(cfg.autoreset_mode) == AUTORESET_SAME_STEP:
             self.buf['final_observation'] = z((B, self.obs_dim), f32)
             self.buf['final_achieved_goal'] = z((B, self.goal_dim), f32)
@@ -379,6 +381,8 @@ class _VecEnvBase:
             'mover_collision': b['mover_collision'].bool(),
             'wall_collision': b['wall_collision'].bool(),
         }
+        if 'other_collision' in b:
+            info['other_collision'] = b['other_collision'].bool()
         if with_final and 'final_observation' in b:
             # SAME_STEP autoreset: rows are valid where terminated | truncated
             info['final_obs'] = {
@@ -412,7 +416,7 @@ class _VecEnvBase:
             # the result arrays are persistent (rewritten in place every step), so the returned structure is built once;
             # the flag arrays hold 0/1 bytes and are viewed as bool instead of converted
             obs = {'observation': h['observation'], 'achieved_goal': h['achieved_goal'], 'desired_goal': h['desired_goal']}
-            info = {k: h[k].view(np.bool_) for k in ('is_success', 'mover_collision', 'wall_collision')}
+            info = {k: h[k].view(np.bool_) for k in ('is_success', 'mover_collision', 'wall_collision', 'other_collision') if k in h}
             if 'final_observation' in h:
                 info['final_obs'] = {k: h['final_' + k] for k in ('observation', 'achieved_goal', 'desired_goal')}
             self._host_ret = (obs, h['reward'], h['terminated'].view(np.bool_), h['truncated'].view(np.bool_), info)
@@ -435,9 +439,13 @@ class _VecEnvBase:
         if info is None:
             return None, None
         if isinstance(info, dict):
-            return info.get('mover_collision'), info.get('wall_collision')
+            mc = info.get('mover_collision')
+            if info.get('other_collision') is not None:  # an obstacle hit counts like a mover collision in the reward
+                oc = info['other_collision']
+                mc = oc if mc is None else (torch.as_tensor(mc).bool() | torch.as_tensor(oc).bool().to(torch.as_tensor(mc).device))
+            return mc, info.get('wall_collision')
         # array of per-transition dicts, as the reference accepts (planning:666-688)
-        mc = np.array([bool(i['mover_collision']) for i in info], dtype=np.uint8)
+        mc = np.array([bool(i['mover_collision']) or bool(i.get('other_collision', False)) for i in info], dtype=np.uint8)
         wc = np.array([bool(i['wall_collision']) for i in info], dtype=np.uint8)
         return mc, wc
 
@@ -522,7 +530,7 @@ class _SingleEnvBase:
 
     @staticmethod
     def _np_info(info):
-        return {k: bool(info[k][0]) for k in ('is_success', 'mover_collision', 'wall_collision')}
+        return {k: bool(info[k][0]) for k in ('is_success', 'mover_collision', 'wall_collision', 'other_collision') if k in info}
 
     def reset(self, seed: int | None = None, options: dict[str, Any] | None = None):
         if seed is not None:

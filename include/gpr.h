@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GPR_ABI_VERSION 1
+#define GPR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GPR_API __attribute__((visibility("default")))
@@ -52,6 +52,7 @@ extern "C" {
 
 #define GPR_MAX_MOVERS 32   /* one lane per mover, one lane group (<= one warp) per environment */
 #define GPR_MAX_TILES_1D 32 /* tiles per axis */
+#define GPR_MAX_OBSTACLES 8 /* static obstacles per layout (planning env) */
 
 enum gpr_env_kind { GPR_ENV_PLANNING = 0, GPR_ENV_PUSHING = 1 };
 enum gpr_collision_shape { GPR_SHAPE_CIRCLE = 0, GPR_SHAPE_BOX = 1 };
@@ -132,6 +133,21 @@ typedef struct gpr_config {
     double solimp[5];       /* MuJoCo default (0.9, 0.95, 0.001, 0.5, 2) */
     int32_t contact_iterations; /* projected Gauss-Seidel sweeps of the planar contact solve */
     int32_t output_flags; /* GPR_OUT_* bits */
+
+    /* --- static obstacles, planning env only: the typed form of the reference's extension point
+     * `_check_for_other_collisions_callback` (basic_envs.py:1976-1986; called at basic_envs.py:1807 and 1903).  The
+     * reference's hook returns False in both benchmark envs; a custom env overrides it in Python.  Here an obstacle is a
+     * fixed shape of the env's own collision kind (c_shape): a circle (centre, radius) or an axis-aligned box (centre,
+     * half sizes), the same in every environment.  A mover touches an obstacle under the rules of the mover-mover check
+     * (basic_envs.py:390-424: circle  ||p - o|| <= r_mover + r_obstacle;  box  geom.check_rectangles_intersect, or the
+     * mover's centre inside the obstacle), evaluated on the noisy qpos of the WALL check (static geometry is checked
+     * together: no additional random draws).  The flag is reported as `other_collision`, ends the 40-cycle loop like the
+     * other two (basic_envs.py:1904) and counts as a collision in reward / termination; starts and goals are re-sampled
+     * until they clear every obstacle by the safety offset.  num_obstacles = 0 reproduces the reference exactly. */
+    int32_t num_obstacles;
+    int32_t reserved0;
+    double obstacle_xy[GPR_MAX_OBSTACLES][2];
+    double obstacle_size[GPR_MAX_OBSTACLES][2]; /* circle: radius in [0]; box: half sizes */
 } gpr_config;
 
 /* output_flags bit: a step writes `desired_goal` rows only for environments whose goal changed in that call (they were
@@ -159,6 +175,7 @@ typedef struct gpr_outputs {
     float* final_observation;
     float* final_achieved_goal;
     float* final_desired_goal;
+    uint8_t* other_collision; /* [num_envs] a mover touches a static obstacle (see gpr_config.num_obstacles); all 0 without obstacles */
 } gpr_outputs;
 
 /* Structure-of-arrays state, float64. Device pointers, caller-owned copies; NULL = skip that field.

@@ -331,6 +331,30 @@ int gpro_check_mover_collision(const gpr_config* c, int n, const double* qpos, c
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* plan:502-534 compute_reward, plan:459-479 compute_terminated, plan:575-602 _get_info (one env)                       */
+/* Static obstacles — the typed form of the reference's extension point _check_for_other_collisions_callback
+ * (basic:1976-1986, called at basic:1807 and basic:1903; see gpr_config.num_obstacles in include/gpr.h).  Rules of the
+ * mover-mover check (basic:390-424) between every mover and every obstacle: circle  ||p - o|| <= r_mover + r_obstacle
+ * (inclusive like basic:409);  box  geom.check_rectangles_intersect (geom:107-138) or the mover's centre inside the
+ * obstacle (the edge test alone does not see containment).  qpos: [n][7] (noisy) mover poses; csize: [n][2] sizes. */
+int gpro_check_obstacle_collision(const gpr_config* c, int n, const double* qpos, const double* csize) {
+    for (int k = 0; k < c->num_obstacles; ++k) {
+        const double ox = c->obstacle_xy[k][0], oy = c->obstacle_xy[k][1];
+        for (int m = 0; m < n; ++m) {
+            const double* q = qpos + 7 * m;
+            if (c->c_shape == GPR_SHAPE_CIRCLE) {
+                const double dx = q[0] - ox, dy = q[1] - oy;
+                if (sqrt(dx * dx + dy * dy) <= csize[2 * m] + c->obstacle_size[k][0]) return 1;
+            } else {
+                const double qo[7] = {ox, oy, 0.0, 1.0, 0.0, 0.0, 0.0};
+                const double so[2] = {c->obstacle_size[k][0], c->obstacle_size[k][1]};
+                if (fabs(q[0] - ox) <= so[0] && fabs(q[1] - oy) <= so[1]) return 1;
+                if (gpro_rectangles_intersect(q, qo, csize + 2 * m, so)) return 1;
+            }
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------------------------ */
 void gpro_planning_reward(const gpr_config* c, const double* achieved, const double* desired, int mover_collision,
                           int wall_collision, double* reward, int* terminated, int* is_success) {
@@ -396,6 +420,7 @@ typedef struct gpro_outputs {
     double* final_achieved_goal;
     double* final_desired_goal;
     uint8_t* reset_failed; /* [B] 1 if a rejection loop hit max_reset_attempts */
+    uint8_t* other_collision; /* [B] a mover touches a static obstacle */
 } gpro_outputs;
 
 static void noisy_qpos(const gpr_config* c, const double* p, int N, const float (*nxy)[2], const float (*nq)[4],
@@ -459,7 +484,7 @@ static void planning_obs(const gpr_config* c, const double* p, const double* v, 
 /* plan:355-418 + basic:1770-1833 for one env.  Returns 1 if a rejection loop ran out of attempts. */
 static int planning_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_global, uint32_t event, double* p,
                               double* v, double* a, double* g, const double* inj_start, const double* inj_goal,
-                              int* mover_collision, int* wall_collision) {
+                              int* mover_collision, int* wall_collision, int* other_collision) {
     const int N = c->num_movers;
     double qpos[7 * NMAX], cw[2 * NMAX], cm[2 * NMAX];
     int32_t valid[NMAX];
@@ -486,6 +511,7 @@ static int planning_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_g
             int allv = 1;
             for (int m = 0; m < N; ++m) allv &= valid[m] != 0;
             ok = allv && !gpro_check_mover_collision(c, N, qpos, cm);
+            if (ok && c->num_obstacles > 0) ok = !gpro_check_obstacle_collision(c, N, qpos, cm); /* starts clear the obstacles */
         }
         failed |= !ok;
     }
@@ -515,6 +541,10 @@ static int planning_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_g
                     double dx = g[2 * i] - g[2 * j], dy = g[2 * i + 1] - g[2 * j + 1];
                     if (sqrt(dx * dx + dy * dy) < c->min_goal_dist) ok = 0; /* plan:410 */
                 }
+            if (ok && c->num_obstacles > 0) { /* a goal must be reachable: the mover's shape there clears the obstacles */
+                csize_rows(c, c->c_mover[1], cm);
+                ok = !gpro_check_obstacle_collision(c, N, qpos, cm);
+            }
         }
         failed |= !ok;
     }
@@ -544,6 +574,13 @@ static int planning_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_g
     gpro_qpos_is_valid(c, N, qpos, cw, valid);
     int wc = 0;
     for (int m = 0; m < N; ++m) wc |= !valid[m];
+    /* basic:1807: the hook, on the wall check's noisy qpos, with the safety offset like the wall check of reset() */
+    *other_collision = 0;
+    if (c->num_obstacles > 0) {
+        double cs[2 * NMAX];
+        csize_rows(c, c->c_mover[1], cs);
+        *other_collision = gpro_check_obstacle_collision(c, N, qpos, cs);
+    }
     noisy_qpos(c, p, N, (noisy && N > 1) ? nxy_m : NULL, (noisy && box && N > 1) ? nq_m : NULL, qpos);
     *wall_collision = wc;
     *mover_collision = gpro_check_mover_collision(c, N, qpos, cm);
@@ -552,7 +589,8 @@ static int planning_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_g
 
 /* basic:1835-1950 step for one planning env (state updated in place). */
 static void planning_step_one(const gpr_config* c, uint64_t seed, uint32_t env_global, uint32_t event, double* p,
-                              double* v, double* a, const float* action, int* mover_collision, int* wall_collision) {
+                              double* v, double* a, const float* action, int* mover_collision, int* wall_collision,
+                              int* other_collision) {
     const int N = c->num_movers;
     const double dt = c->cycle_time;
     const double lim = c->learn_jerk ? c->j_max : c->a_max;
@@ -568,7 +606,7 @@ static void planning_step_one(const gpr_config* c, uint64_t seed, uint32_t env_g
     int32_t valid[NMAX];
     csize_rows(c, c->c_wall[0], cw);
     csize_rows(c, c->c_mover[0], cm);
-    int mc = 0, wc = 0;
+    int mc = 0, wc = 0, oc = 0;
     for (int cyc = 0; cyc < c->num_cycles; ++cyc) { /* basic:1879 */
         float nxy_w[NMAX][2], nxy_m[NMAX][2], nq_w[NMAX][4], nq_m[NMAX][4];
         for (int m = 0; m < N; ++m) {
@@ -629,13 +667,16 @@ static void planning_step_one(const gpr_config* c, uint64_t seed, uint32_t env_g
         gpro_qpos_is_valid(c, N, qpos, cw, valid);
         wc = 0;
         for (int m = 0; m < N; ++m) wc |= !valid[m];
+        /* basic:1903 the hook: static obstacles, on the wall check's noisy qpos, no safety offset */
+        oc = c->num_obstacles > 0 ? gpro_check_obstacle_collision(c, N, qpos, cm) : 0;
         /* basic:1895-1901 mover check on an independent noisy qpos */
         noisy_qpos(c, p, N, (noisy_p && N > 1) ? nxy_m : NULL, (noisy_p && box && N > 1) ? nq_m : NULL, qpos);
         mc = gpro_check_mover_collision(c, N, qpos, cm);
-        if (mc || wc) break; /* basic:1904 */
+        if (mc || wc || oc) break; /* basic:1904 */
     }
     *mover_collision = mc;
     *wall_collision = wc;
+    *other_collision = oc;
 }
 
 static void write_obs(const gpr_config* c, int obs_dim, int goal_dim, const double* o, const double* ag,
@@ -662,10 +703,10 @@ void gpro_planning_reset(const gpr_config* c, uint64_t seed, gpro_state* s, cons
         double* g = s->goal + e * 2 * N;
         uint32_t env_global = (uint32_t)(c->env_index_base + e);
         uint32_t event = s->rng_counter[e];
-        int mc, wc;
+        int mc, wc, oc;
         int failed = planning_reset_one(c, seed, env_global, event, p, v, a, g,
                                         inject_start ? inject_start + e * 2 * N : NULL,
-                                        inject_goal ? inject_goal + e * 2 * N : NULL, &mc, &wc);
+                                        inject_goal ? inject_goal + e * 2 * N : NULL, &mc, &wc, &oc);
         double o[4 * NMAX], ag[2 * NMAX], dg[2 * NMAX];
         planning_obs(c, p, v, a, g, seed, env_global, event, o, ag, dg);
         s->rng_counter[e] = event + 1u;
@@ -675,10 +716,11 @@ void gpro_planning_reset(const gpr_config* c, uint64_t seed, gpro_state* s, cons
             write_obs(c, obs_dim, goal_dim, o, ag, dg, e, out->observation, out->achieved_goal, out->desired_goal);
             double r;
             int term, succ;
-            gpro_planning_reward(c, ag, dg, mc, wc, &r, &term, &succ);
+            gpro_planning_reward(c, ag, dg, mc || oc, wc, &r, &term, &succ); /* an obstacle hit counts as a collision */
             if (out->is_success) out->is_success[e] = (uint8_t)succ;
             if (out->mover_collision) out->mover_collision[e] = (uint8_t)mc;
             if (out->wall_collision) out->wall_collision[e] = (uint8_t)wc;
+            if (out->other_collision) out->other_collision[e] = (uint8_t)oc;
             if (out->reset_failed) out->reset_failed[e] = (uint8_t)failed;
         }
     }
@@ -700,11 +742,11 @@ void gpro_planning_step(const gpr_config* c, uint64_t seed, gpro_state* s, const
         double* g = s->goal + e * 2 * N;
         uint32_t env_global = (uint32_t)(c->env_index_base + e);
         double o[4 * NMAX], ag[2 * NMAX], dg[2 * NMAX];
-        int mc = 0, wc = 0;
+        int mc = 0, wc = 0, oc = 0;
         if (c->autoreset_mode == GPR_AUTORESET_NEXT_STEP && s->needs_reset && s->needs_reset[e]) {
             /* gymnasium vector NEXT_STEP: this call resets instead of stepping; reward 0, not done */
             uint32_t event = s->rng_counter[e];
-            planning_reset_one(c, seed, env_global, event, p, v, a, g, NULL, NULL, &mc, &wc);
+            planning_reset_one(c, seed, env_global, event, p, v, a, g, NULL, NULL, &mc, &wc, &oc);
             planning_obs(c, p, v, a, g, seed, env_global, event, o, ag, dg);
             s->rng_counter[e] = event + 1u;
             s->elapsed_steps[e] = 0;
@@ -712,22 +754,23 @@ void gpro_planning_step(const gpr_config* c, uint64_t seed, gpro_state* s, const
             write_obs(c, obs_dim, goal_dim, o, ag, dg, e, out->observation, out->achieved_goal, out->desired_goal);
             double r;
             int term, succ;
-            gpro_planning_reward(c, ag, dg, mc, wc, &r, &term, &succ);
+            gpro_planning_reward(c, ag, dg, mc || oc, wc, &r, &term, &succ);
             if (out->reward) out->reward[e] = 0.0;
             if (out->terminated) out->terminated[e] = 0;
             if (out->truncated) out->truncated[e] = 0;
             if (out->is_success) out->is_success[e] = (uint8_t)succ;
             if (out->mover_collision) out->mover_collision[e] = (uint8_t)mc;
             if (out->wall_collision) out->wall_collision[e] = (uint8_t)wc;
+            if (out->other_collision) out->other_collision[e] = (uint8_t)oc;
             continue;
         }
         uint32_t event = s->rng_counter[e];
-        planning_step_one(c, seed, env_global, event, p, v, a, action + e * 2 * N, &mc, &wc);
+        planning_step_one(c, seed, env_global, event, p, v, a, action + e * 2 * N, &mc, &wc, &oc);
         planning_obs(c, p, v, a, g, seed, env_global, event, o, ag, dg);
         s->rng_counter[e] = event + 1u;
         double r;
         int term, succ;
-        gpro_planning_reward(c, ag, dg, mc, wc, &r, &term, &succ);
+        gpro_planning_reward(c, ag, dg, mc || oc, wc, &r, &term, &succ); /* an obstacle hit counts as a collision */
         int steps = s->elapsed_steps[e] + 1;
         s->elapsed_steps[e] = steps;
         int trunc = (c->max_episode_steps > 0) && (steps >= c->max_episode_steps); /* gymnasium TimeLimit */
@@ -737,13 +780,14 @@ void gpro_planning_step(const gpr_config* c, uint64_t seed, gpro_state* s, const
         if (out->is_success) out->is_success[e] = (uint8_t)succ;
         if (out->mover_collision) out->mover_collision[e] = (uint8_t)mc;
         if (out->wall_collision) out->wall_collision[e] = (uint8_t)wc;
+        if (out->other_collision) out->other_collision[e] = (uint8_t)oc;
         const int done = term || trunc;
         if (done && c->autoreset_mode == GPR_AUTORESET_SAME_STEP) {
             write_obs(c, obs_dim, goal_dim, o, ag, dg, e, out->final_observation, out->final_achieved_goal,
                       out->final_desired_goal);
             uint32_t ev2 = s->rng_counter[e];
-            int mc2, wc2;
-            int failed = planning_reset_one(c, seed, env_global, ev2, p, v, a, g, NULL, NULL, &mc2, &wc2);
+            int mc2, wc2, oc2;
+            int failed = planning_reset_one(c, seed, env_global, ev2, p, v, a, g, NULL, NULL, &mc2, &wc2, &oc2);
             planning_obs(c, p, v, a, g, seed, env_global, ev2, o, ag, dg);
             s->rng_counter[e] = ev2 + 1u;
             s->elapsed_steps[e] = 0;

@@ -78,6 +78,7 @@ class OOutputs(ctypes.Structure):
         ('final_achieved_goal', ctypes.c_void_p),
         ('final_desired_goal', ctypes.c_void_p),
         ('reset_failed', ctypes.c_void_p),
+        ('other_collision', ctypes.c_void_p),
     ]
 
 
@@ -122,6 +123,16 @@ def check_mover_collision(cfg, qpos, csize) -> bool:
     n = qpos.shape[0]
     csize = np.ascontiguousarray(np.broadcast_to(np.asarray(csize, dtype=np.float64).reshape(n, -1), (n, 2)))
     return bool(lib().gpro_check_mover_collision(ctypes.byref(cfg), n, _p(qpos, _D), _p(csize, _D)))
+
+
+def check_obstacle_collision(cfg, qpos, csize) -> bool:
+    """gpro_check_obstacle_collision: any mover of `qpos` (n, 7) touching a static obstacle of `cfg`."""
+    qpos = np.ascontiguousarray(qpos, dtype=np.float64)
+    n = qpos.shape[0]
+    cs = np.asarray(csize, dtype=np.float64)
+    cs = cs.reshape(1, -1) if cs.size <= 2 else cs.reshape(n, -1)  # one size for all movers, or one row per mover
+    csize = np.ascontiguousarray(np.broadcast_to(cs, (n, 2)))
+    return bool(lib().gpro_check_obstacle_collision(ctypes.byref(cfg), n, _p(qpos, _D), _p(csize, _D)))
 
 
 def compute_reward(cfg, achieved, desired, mover_collision=None, wall_collision=None):
@@ -198,6 +209,7 @@ class OracleEnv:
         self.final_achieved_goal = np.zeros((B, self.goal_dim))
         self.final_desired_goal = np.zeros((B, self.goal_dim))
         self.reset_failed = np.zeros(B, dtype=np.uint8)
+        self.other_collision = np.zeros(B, dtype=np.uint8)
 
     def _state(self) -> OState:
         s = OState()

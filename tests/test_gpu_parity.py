@@ -42,7 +42,9 @@ def sample_starts(rng, ora, spread=1.0):
 def assert_outputs_equal(env, ora, what):
     b = env.core.buf
     torch.cuda.synchronize()
-    for k in ('terminated', 'truncated', 'is_success', 'mover_collision', 'wall_collision'):
+    for k in ('terminated', 'truncated', 'is_success', 'mover_collision', 'wall_collision', 'other_collision'):
+        if k not in b:
+            continue  # (other_collision exists only with static obstacles)
         got, ref = b[k].cpu().numpy(), getattr(ora, k)
         assert np.array_equal(got, ref), f'{what}: {k} differs in {np.count_nonzero(got != ref)} envs'
     assert np.array_equal(b['reward'].cpu().numpy(), ora.reward.astype(np.float32)), f'{what}: reward'
@@ -72,8 +74,9 @@ def run_lockstep(env, ora, steps, rng, scale, inject=True, seed=3):
     torch.cuda.synchronize()
     for k in ('observation', 'achieved_goal', 'desired_goal'):
         assert np.array_equal(env.core.buf[k].cpu().numpy(), getattr(ora, k).astype(np.float32)), f'reset {k}'
-    for k in ('is_success', 'mover_collision', 'wall_collision'):
-        assert np.array_equal(env.core.buf[k].cpu().numpy(), getattr(ora, k)), f'reset {k}'
+    for k in ('is_success', 'mover_collision', 'wall_collision', 'other_collision'):
+        if k in env.core.buf:
+            assert np.array_equal(env.core.buf[k].cpu().numpy(), getattr(ora, k)), f'reset {k}'
     assert_state_equal(env, ora, 'reset')
     events = 0
     for t in range(steps):
@@ -692,3 +695,70 @@ def test_debug_view_draws_the_chosen_env():
     assert single.debug_view().shape == (288, 288, 3) and single.render() is None
     for e in (env, push, single):
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# static obstacles (rules fixed on the oracle in tests/test_oracle_obstacles.py)
+OBST_CIRCLE = np.array([[0.36, 0.36, 0.05], [0.62, 0.2, 0.03], [0.15, 0.8, 0.04]])
+OBST_BOX = np.array([[0.36, 0.36, 0.05, 0.08], [0.62, 0.2, 0.03, 0.03], [0.15, 0.8, 0.06, 0.02]])
+
+
+@pytest.mark.parametrize('noise', [0.0, 1e-5], ids=['exact', 'noisy'])
+@pytest.mark.parametrize('shape,movers,jerk', [('circle', 1, False), ('circle', 3, False), ('circle', 4, True), ('box', 2, False), ('box', 8, True)])
+def test_obstacles_injected_starts(shape, movers, jerk, noise):
+    """Movers started anywhere (also on top of obstacles): other_collision, the loop break, reward and state must equal
+    the oracle's bit for bit, with and without sensor noise, for lane groups of 1 to 8."""
+    rng = np.random.default_rng(300 + movers + (7 if noise else 0))
+    cp = {'shape': 'circle', 'size': 0.08} if shape == 'circle' else {'shape': 'box', 'size': np.array([0.07, 0.05])}
+    env, ora = make_pair(1500, layout_tiles=np.ones((4, 4)), num_movers=movers, std_noise=noise, learn_jerk=jerk, collision_params=cp,
+                         obstacles=OBST_CIRCLE if shape == 'circle' else OBST_BOX, autoreset_mode='off', max_episode_steps=50)
+    ev = run_lockstep(env, ora, 25, rng, 130.0 if jerk else 13.0)
+    assert ev > 0
+    assert ora.other_collision.any()
+    env.close()
+
+
+@pytest.mark.parametrize('mode', ['same_step', 'next_step'])
+@pytest.mark.parametrize('shape,movers', [('circle', 2), ('circle', 4), ('box', 3), ('box', 8)])
+def test_obstacles_with_autoreset_sampling(shape, movers, mode):
+    """Sampled starts / goals avoid the obstacles (rejection loops of both samplers), auto-reset in both modes."""
+    rng = np.random.default_rng(400 + movers)
+    cp = {'shape': 'circle', 'size': 0.08, 'offset': 0.005} if shape == 'circle' else {'shape': 'box', 'size': np.array([0.07, 0.05]), 'offset': 0.005}
+    layout = np.ones((5, 5)) if movers == 8 else np.ones((4, 4))
+    env, ora = make_pair(1200, layout_tiles=layout, num_movers=movers, std_noise=1e-5, collision_params=cp,
+                         obstacles=OBST_CIRCLE if shape == 'circle' else OBST_BOX, autoreset_mode=mode, max_episode_steps=6, seed=11)
+    run_lockstep(env, ora, 30, rng, 12.0, inject=False, seed=11)
+    assert env.core.reset_failures() == 0 and not ora.reset_failed.any()
+    st = env.get_state()
+    for arr in (st['pos'].cpu().numpy(), st['goal'].cpu().numpy()):
+        assert np.isfinite(arr).all()
+    info = env._info(False)
+    assert 'other_collision' in info and info['other_collision'].dtype == torch.bool
+    env.close()
+
+
+def test_obstacles_through_the_host_path_and_her():
+    """step_host delivers other_collision like the other flags; compute_reward treats it as a collision."""
+    cp = {'shape': 'circle', 'size': 0.08}
+    kw = dict(layout_tiles=np.ones((4, 4)), num_movers=2, collision_params=cp, obstacles=OBST_CIRCLE, seed=5, std_noise=1e-5)
+    a_env = gpr.BenchmarkPlanningVecEnv(3000, device=DEV, **kw)
+    b_env = gpr.BenchmarkPlanningVecEnv(3000, device=DEV, **kw)
+    a_env.reset(seed=5)
+    b_env.reset(seed=5)
+    rng = np.random.default_rng(6)
+    seen = 0
+    for _ in range(20):
+        act = rng.uniform(-10, 10, (3000, 4)).astype(np.float32)
+        obs, r, term, trunc, info = a_env.step(torch.as_tensor(act, device=DEV))
+        hobs, hr, hterm, htrunc, hinfo = b_env.step_host(act)
+        assert np.array_equal(info['other_collision'].cpu().numpy(), hinfo['other_collision'])
+        assert np.array_equal(r.cpu().numpy(), hr) and np.array_equal(term.cpu().numpy(), hterm)
+        oc = info['other_collision']
+        seen += int(oc.sum())
+        assert bool((r[oc] == -50.0).all()) and bool(term[oc].all())
+        fin = info['final_obs']
+        rr = a_env.compute_reward(fin['achieved_goal'][oc], fin['desired_goal'][oc], {k: info[k][oc] for k in ('mover_collision', 'wall_collision', 'other_collision')})
+        assert bool((rr == -50.0).all())
+    assert seen > 0
+    a_env.close()
+    b_env.close()
