@@ -23,6 +23,7 @@ BLACK = (0, 0, 0)
 PALETTE = [(31, 119, 180), (255, 127, 14), (44, 160, 44), (214, 39, 40), (148, 103, 189), (140, 86, 75), (227, 119, 194),
            (127, 127, 127), (188, 189, 34), (23, 190, 207)]
 OBJECT_COLOUR = (80, 80, 80)
+OBSTACLE_COLOUR = (120, 40, 40)
 
 
 class _Canvas:
@@ -82,14 +83,15 @@ class _Canvas:
 
 def rasterize_scene(layout_tiles, tile_half, mover_pos, mover_half, c_shape, c_size, c_offset=0.0, goals=None, mover_vel=None,
                     mover_yaw=None, object_pose=None, object_half=None, object_goal=None, goal_radius=None, ppm=400.0,
-                    colours=None, velocity_scale=0.1):
+                    colours=None, velocity_scale=0.1, obstacles=None):
     """Draw one environment.
 
     layout_tiles (nx, ny) 0/1; tile_half (2,) half tile size in m; mover_pos (N, 2); mover_half (N, 2) or (2,) half sizes of
     the mover bodies; c_shape 'circle' | 'box'; c_size scalar / (2,) / per-mover like ``collision_params['size']``;
     c_offset the safety offset (outline drawn when > 0); goals (N, 2) or None; mover_vel (N, 2) or None (arrow of length
     ``velocity_scale`` s * v); mover_yaw (N,) or None; object_pose (x, y, cos, sin) + object_half for the pushing env;
-    object_goal (2,); goal_radius: radius of the goal ring (``threshold_pos``).  Returns (H, W, 3) uint8.
+    object_goal (2,); goal_radius: radius of the goal ring (``threshold_pos``); obstacles: the ``obstacles`` kwarg of the
+    planning env ((K, 3) circles / (K, 4) boxes).  Returns (H, W, 3) uint8.
     """
     layout = np.asarray(layout_tiles)
     nx, ny = layout.shape
@@ -101,6 +103,12 @@ def rasterize_scene(layout_tiles, tile_half, mover_pos, mover_half, c_shape, c_s
                 cx, cy = (i + 0.5) * 2 * hx, (j + 0.5) * 2 * hy
                 cv.rect(cx, cy, hx, hy, SILVER)
                 cv.rect(cx, cy, hx, hy, BACKGROUND, outline=True, width_px=1.0)  # tile joints
+    if obstacles is not None:
+        for o in np.asarray(obstacles, dtype=np.float64).reshape(-1, 3 if c_shape == 'circle' else 4):
+            if c_shape == 'circle':
+                cv.circle(o[0], o[1], o[2], OBSTACLE_COLOUR)
+            else:
+                cv.rect(o[0], o[1], o[2], o[3], OBSTACLE_COLOUR)
     pos = np.asarray(mover_pos, dtype=np.float64).reshape(-1, 2)
     N = pos.shape[0]
     mh = np.broadcast_to(np.asarray(mover_half, dtype=np.float64).reshape(-1, 2), (N, 2))
@@ -171,5 +179,5 @@ def view_of_env(env, env_index: int = 0, ppm: float = 400.0) -> np.ndarray:
         kw.update(object_pose=one['object_pos'], object_half=float(cfg.object_half_xy), object_goal=one['goal'].reshape(-1)[:2],
                   mover_yaw=np.array([np.arctan2(rot[1], rot[0])]))
     else:
-        kw.update(goals=one['goal'])
+        kw.update(goals=one['goal'], obstacles=d.get('obstacles') if d.get('obstacles') is not None and len(d['obstacles']) else None)
     return rasterize_scene(**kw)

@@ -55,3 +55,12 @@ def test_rotated_object_and_ppm_file(tmp_path):
     dv.save_ppm(str(path), img)
     raw = path.read_bytes()
     assert raw.startswith(b'P6\n240 240\n255\n') and len(raw) == len(b'P6\n240 240\n255\n') + 240 * 240 * 3
+
+
+def test_obstacles_are_drawn():
+    img = dv.rasterize_scene(np.ones((2, 2)), (0.12, 0.12), np.array([[0.1, 0.1]]), (0.05, 0.05), 'circle', 0.06,
+                             obstacles=[[0.3, 0.3, 0.05]], ppm=500.0)
+    assert px(img, 0.3, 0.3, 500.0) == dv.OBSTACLE_COLOUR and px(img, 0.3 + 0.07, 0.3, 500.0) == dv.SILVER
+    img = dv.rasterize_scene(np.ones((2, 2)), (0.12, 0.12), np.array([[0.1, 0.1]]), (0.05, 0.05), 'box', (0.06, 0.06),
+                             obstacles=[[0.3, 0.3, 0.08, 0.02]], ppm=500.0)
+    assert px(img, 0.3 + 0.07, 0.3, 500.0) == dv.OBSTACLE_COLOUR and px(img, 0.3, 0.3 + 0.04, 500.0) == dv.SILVER
