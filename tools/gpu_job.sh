@@ -17,3 +17,10 @@ timeout 300 $CMD > gpurun_out/plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 timeout 300 $CMD > gpurun_out/plain.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:planning_ -s 8 -c 2 -f -o gpurun_out/prof_planning4 $CMD > gpurun_out/ncu_full.log 2>&1
+# batch-size sweep on one GPU (BASELINE configs[4]): GPR_SWEEP=1 bash tools/gpu_job.sh
+if [ "${GPR_SWEEP:-0}" = "1" ]; then
+for n in 262144 1048576 4194304 8388608; do
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --quick --num-envs $n > gpurun_out/sweep_planning4_$n.log 2>&1
+timeout 300 python bench.py --workload pushing --steps 10 --warmup 3 --no-cpu --quick --num-envs $n > gpurun_out/sweep_pushing_$n.log 2>&1
+done
+fi
