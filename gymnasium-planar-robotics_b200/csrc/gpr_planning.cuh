@@ -1045,6 +1045,9 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
 // warp whenever one of them is due (0.117 ms: more lanes reach the exact fallback), and "blind runs" — k cycles of bare
 // integration without per-cycle budget tests, k from a closed-form bound of the travel (0.134 ms: with 32 movers per warp
 // one of them is nearly always within a few cycles of its wall budget, so k is 0 or 1 and its computation is overhead).
+#ifndef GPR_STEP_STASH
+#define GPR_STEP_STASH 1
+#endif
 #ifndef GPR_STEP_THREADS
 #define GPR_STEP_THREADS 128
 #endif
@@ -1114,10 +1117,18 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
     float travel = 0.f;                  // sum over cycles of an upper bound of |v|  (distance / dt)
     float lim_w = -1.f, lim_p = -1.f;    // `travel` values up to which the wall / pair check is certified negative
     bool any_alive = __any_sync(FULL, alive);
+    // `part`: this lane integrates a mover of a live env.  GPR_STEP_STASH: a lane whose env has collided parks its final
+    // (p, v, acc) in shared memory and the common path below then runs UNPREDICATED for every lane (a parked lane computes
+    // garbage that nothing reads: it takes part in no check and is restored after the loop) — the integration writes
+    // straight into the loop-carried registers instead of into temporaries that are copied under a predicate.
+    // (measured on B200: circle shape +1 %, box shape -4 % — the box kernel is register-bound — so circle only)
+    constexpr bool STASH = GPR_STEP_STASH && !BOX;
+    bool part = alive && ln.active;
+    bool died = false;
+    __shared__ double s_stash[STASH ? 6 : 1][STASH ? StepThreads<G>::value : 1];
     GPR_UNROLL(GPR_STEP_UNROLL)
     for (int cyc = 0; cyc < a.num_cycles && any_alive; ++cyc) {
         const uint32_t s0 = (uint32_t)cyc * 4u;
-        const bool part = alive && ln.active;
         float n4[4] = {0.f, 0.f, 0.f, 0.f};
         bool have0 = false;  // block 0 of this cycle generated?
         // ---- plan:420-450 _mujoco_step_callback + mj_step
@@ -1132,7 +1143,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         bool free_run = dadd(dmul(tx, tx), dmul(ty, ty)) < (NOISE ? a.v_lazy2 : a.v_max2_lo);
         if (JERK) free_run = free_run && dadd(dmul(nax, nax), dmul(nay, nay)) < a.a_max2_lo;
         if (!__any_sync(FULL, part && !free_run)) {
-            if (part) {
+            if (STASH || part) {
                 acc.x = nax;
                 acc.y = nay;
                 v.x = tx;
@@ -1169,7 +1180,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
             v.x = dadd(v.x, dmul(a.dt, acc.x));  // semi-implicit Euler (MuJoCo): qvel += dt*qacc
             v.y = dadd(v.y, dmul(a.dt, acc.y));
         }
-        if (part) {
+        if (STASH || part) {
             p.x = dadd(p.x, dmul(a.dt, v.x));  // qpos += dt*qvel
             p.y = dadd(p.y, dmul(a.dt, v.y));
             // |v| <= max + min/2 of the absolute components; 1e-4 covers the float roundings of the running sum
@@ -1281,10 +1292,30 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
                 wc = (badm & ln.gmask) != 0u;
                 mc = (hitm & ln.gmask) != 0u;
                 oc = (obm & ln.gmask) != 0u;
-                if (wc || mc || oc) alive = false;  // basic:1904 break
+                if (wc || mc || oc) {  // basic:1904 break
+                    alive = false;
+                    if (STASH && part) {
+                        const int t = (int)threadIdx.x;
+                        s_stash[0][t] = p.x;
+                        s_stash[1][t] = p.y;
+                        s_stash[2][t] = v.x;
+                        s_stash[3][t] = v.y;
+                        s_stash[4][t] = acc.x;
+                        s_stash[5][t] = acc.y;
+                        died = true;
+                    }
+                    part = false;
+                }
             }
             any_alive = __any_sync(FULL, alive);
         }
+    }
+
+    if (STASH && died) {
+        const int t = (int)threadIdx.x;
+        p = make_double2(s_stash[0][t], s_stash[1][t]);
+        v = make_double2(s_stash[2][t], s_stash[3][t]);
+        acc = make_double2(s_stash[4][t], s_stash[5][t]);
     }
 
     // ------------------------------------------------------------------ observation, info, reward (basic:1910-1929)
