@@ -268,8 +268,10 @@ __device__ __forceinline__ bool wall_bad_circle(const PlanArgs& a, const Tables&
 // Circle pair check with a float32 prefilter (warp-collective).  xf/yf are this lane's float coordinates (1e30f when the
 // lane does not take part); a pair is decided in float32 when its squared distance is outside the band, and only if some
 // lane of the warp meets an undecided pair does the whole warp run the exact float64 check.
-// `margin`: min over the pairs this lane looked at of (distance - upper band edge), 0 when a pair was hit or undecided —
-// as long as the two movers of every pair have together travelled less than that, no pair can start to collide.
+// `margin`: min over ALL pairs this mover is part of of (distance - upper band edge), 0 when a pair was hit or undecided.
+// A pair cannot start to collide while its two movers have together travelled less than the pair's margin; each mover may
+// therefore use up HALF of its own `margin` (which is <= the margin of each of its pairs) — a mover far from everything
+// keeps a large budget even when two other movers of its env are about to touch.
 template <int G, bool NOISY>
 __device__ __forceinline__ bool pair_circle_fast(const PlanArgs& a, unsigned lane, int m, bool part, double x, double y,
                                                  double r, int safety, uint32_t env_global, uint32_t event,
@@ -303,7 +305,11 @@ __device__ __forceinline__ bool pair_circle_fast(const PlanArgs& a, unsigned lan
             if (d2 < lo2) hit = true;
             else if (!(d2 > hi2)) unc = true;
         }
-        if (both) margin = fminf(margin, fmaxf(sqrtf(d2) * 0.999999f - thi, 0.f));
+        // this pair's margin, and — for the mover on the other side of the lane group — the margin of the pair (m-k, m) that
+        // lane m-k has just computed: `margin` ends up as the minimum over ALL pairs this mover is part of
+        const float mk = both ? fmaxf(sqrtf(d2) * 0.999999f - thi, 0.f) : 3.0e38f;
+        margin = fminf(margin, mk);
+        if (k < G / 2) margin = fminf(margin, __shfl_sync(FULL, mk, (int)(base | (unsigned)((m - k) & (G - 1)))));
     }
     if (__any_sync(FULL, unc)) hit = pair_circle<G, NOISY>(a, lane, m, part, x, y, r, safety, env_global, event, stream);
     return hit;
@@ -335,8 +341,11 @@ __device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part,
         if (both) {
             near = near || !(mgn > 0.f);
             kmask |= !(mgn > 0.f) ? (1u << k) : 0u;
-            margin = fminf(margin, fmaxf(mgn, 0.f));
         }
+        // (own pairs on both sides of the lane group, see pair_circle_fast)
+        const float mk = both ? fmaxf(mgn, 0.f) : 3.0e38f;
+        margin = fminf(margin, mk);
+        if (k < G / 2) margin = fminf(margin, __shfl_sync(FULL, mk, (int)(base | (unsigned)((m - k) & (G - 1)))));
     }
 }
 
@@ -1045,6 +1054,9 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
 // warp whenever one of them is due (0.117 ms: more lanes reach the exact fallback), and "blind runs" — k cycles of bare
 // integration without per-cycle budget tests, k from a closed-form bound of the travel (0.134 ms: with 32 movers per warp
 // one of them is nearly always within a few cycles of its wall budget, so k is 0 or 1 and its computation is overhead).
+#ifndef GPR_PAIR_ENV_MARGIN
+#define GPR_PAIR_ENV_MARGIN 0  // 1: one pair budget per env (the smallest margin of any of its pairs) instead of per mover
+#endif
 #ifndef GPR_STEP_STASH
 #define GPR_STEP_STASH 1
 #endif
@@ -1280,9 +1292,11 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
                     hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0, kmask);
                 }
             }
-            // an env's pair clearance is the smallest one any of its lanes saw; each mover may use up half of it
+            // each mover may use up half of the smallest margin among its own pairs
+#if GPR_PAIR_ENV_MARGIN
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) clear_p = fminf(clear_p, __shfl_xor_sync(FULL, clear_p, o));
+#endif
             lim_p = (travel + 0.5f * clear_p * a.inv_dtf) * 0.999999f;
         }
         const unsigned badm = __ballot_sync(FULL, bad), hitm = __ballot_sync(FULL, hit);
