@@ -273,7 +273,48 @@ def reference_random_vectors(seed=20240607):
     return out
 
 
+OBSTACLES_BOX = np.array([[0.5, 0.5, 0.2, 0.1], [0.9, 0.3, 0.05, 0.05]])
+OBSTACLES_CIRCLE = np.array([[0.5, 0.5, 0.07], [0.3, 0.9, 0.02]])
+
+
+def reference_obstacle_vectors(seed=20241018, n=3000):
+    """Verdicts of the REFERENCE's own functions for a mover against fixed shapes — what the static-obstacle rules of
+    include/gpr.h (gpr_config.num_obstacles) are built from: box  ``geom.check_rectangles_intersect`` (geom:107-138) or the
+    mover's centre inside the obstacle; circle  ``check_mover_collision`` (basic:355-424) on the pair (mover, obstacle)."""
+    ref_harness.install()
+    geom = ref_harness.geometry()
+    rng = np.random.default_rng(seed)
+    out = {'obst_box': OBSTACLES_BOX, 'obst_circle': OBSTACLES_CIRCLE}
+    q = np.zeros((n, 7))
+    q[:, :2] = rng.uniform(0.1, 1.1, (n, 2))
+    yaw = rng.uniform(-np.pi, np.pi, n)
+    q[:, 3], q[:, 6] = np.cos(yaw / 2), np.sin(yaw / 2)
+    s = rng.uniform(0.03, 0.1, (n, 2))
+    want = np.zeros(n, dtype=bool)
+    for o in OBSTACLES_BOX:
+        qo = np.tile(np.array([[o[0], o[1], 0.0, 1.0, 0.0, 0.0, 0.0]]), (n, 1))
+        want |= geom.check_rectangles_intersect(q, qo, s, np.tile(o[None, 2:], (n, 1)))
+        want |= (np.abs(q[:, 0] - o[0]) <= o[2]) & (np.abs(q[:, 1] - o[1]) <= o[3])
+    out['box_qpos'], out['box_size'], out['box_hit'] = q, s, want
+    env = ref_harness.make_planning_env(layout_tiles=np.ones((5, 5)), num_movers=2, collision_params={'shape': 'circle', 'size': 0.1})
+    xy = rng.uniform(0.2, 1.0, (n, 2))
+    r = rng.uniform(0.03, 0.12, n)
+    hit = np.zeros(n, dtype=bool)
+    for i in range(n):
+        for o in OBSTACLES_CIRCLE:
+            pair = np.zeros((2, 7))
+            pair[:, 3] = 1.0
+            pair[0, :2], pair[1, :2] = xy[i], o[:2]
+            hit[i] |= bool(env.check_mover_collision(mover_names=['m0', 'm1'], c_size=np.array([r[i], o[2]]), add_safety_offset=False,
+                                                     mover_qpos=pair))
+    out['circle_xy'], out['circle_r'], out['circle_hit'] = xy, r, hit
+    return out
+
+
 if __name__ == '__main__':
+    ov = reference_obstacle_vectors()
+    np.savez_compressed(os.path.join(HERE, 'reference_obstacle_vectors.npz'), **ov)
+    print('obstacle vectors: box hits', int(ov['box_hit'].sum()), 'circle hits', int(ov['circle_hit'].sum()))
     tv = reference_test_vectors()
     with open(os.path.join(HERE, 'reference_test_vectors.json'), 'w') as f:
         json.dump(tv, f)

@@ -154,6 +154,27 @@ def test_pushing_reward(rv):
     assert np.array_equal(t[safe], rv['rew_push_term'][safe])
 
 
+def check_obstacle_vectors(ov):
+    """The oracle's static-obstacle test against verdicts of the reference's own geometry / mover-check functions."""
+    cfg_b, _ = gpr.planning_config(num_envs=1, layout_tiles=np.ones((5, 5)), num_movers=1, obstacles=ov['obst_box'], std_noise=0.0,
+                                   collision_params={'shape': 'box', 'size': np.array([0.08, 0.06])})
+    got = np.array([oracle.check_obstacle_collision(cfg_b, ov['box_qpos'][i:i + 1], ov['box_size'][i:i + 1]) for i in range(len(ov['box_hit']))])
+    assert np.array_equal(got, ov['box_hit'])
+    cfg_c, _ = gpr.planning_config(num_envs=1, layout_tiles=np.ones((5, 5)), num_movers=1, obstacles=ov['obst_circle'], std_noise=0.0)
+    q = np.zeros((1, 7))
+    q[0, 3] = 1.0
+    got = []
+    for xy, r in zip(ov['circle_xy'], ov['circle_r']):
+        q[0, :2] = xy
+        got.append(oracle.check_obstacle_collision(cfg_c, q, r))
+    assert np.array_equal(np.array(got), ov['circle_hit'])
+    assert 100 < ov['box_hit'].sum() < len(ov['box_hit']) - 100 and 100 < ov['circle_hit'].sum() < len(ov['circle_hit']) - 100
+
+
+def test_obstacle_rules_against_reference_vectors():
+    check_obstacle_vectors(np.load(os.path.join(GOLDEN, 'reference_obstacle_vectors.npz')))
+
+
 def test_philox_known_answers():
     """Random123 kat_vectors for philox4x32-10."""
     assert oracle.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
