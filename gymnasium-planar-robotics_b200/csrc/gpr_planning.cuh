@@ -1,12 +1,14 @@
 // gpr_planning.cuh — fused kernels of BenchmarkPlanningEnv's step path.
 //
 //   planning_step_kernel     : basic:1835-1950 in one launch — action clip, num_cycles x { plan:420-450 limit control,
-//                              mj_step-equivalent integration, basic:459-788 wall check, basic:355-424 mover check, break
-//                              on collision }, plan:536-573 observation, plan:575-602 info, plan:502-534 reward,
-//                              plan:459-479 terminated, TimeLimit truncation, episode statistics; finished envs are
-//                              appended to a compacted reset list.
-//   planning_autoreset_kernel: plan:355-418 + basic:1797-1805 for the envs on that list, one warp per env (rejection
-//                              sampling of starts and goals with the counter-based RNG of include/gpr_rng.h).
+//                              mj_step-equivalent integration, basic:459-788 wall check (+ static obstacles, the typed
+//                              form of the basic:1976-1986 hook), basic:355-424 mover check, break on collision },
+//                              plan:536-573 observation, plan:575-602 info, plan:502-534 reward, plan:459-479 terminated,
+//                              TimeLimit truncation, episode statistics; finished envs are PUBLISHED on a work list.
+//   planning_autoreset_kernel: plan:355-418 + basic:1797-1805 for the envs on that list, launched as the step kernel's
+//                              programmatic dependent: it consumes entries while the step kernel's last wave still runs
+//                              (rejection sampling of starts and goals with the counter-based RNG of include/gpr_rng.h,
+//                              the whole warp per env; checks / observation / stores per batch of 32/G envs).
 //   planning_reset_kernel    : basic:1770-1833 for a masked subset, optionally with injected starts / goals.
 //
 // Exact optimisations that shape the code (DESIGN.md "Kernels"); every one leaves the oracle's results bit for bit:
