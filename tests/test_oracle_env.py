@@ -119,3 +119,33 @@ def test_oracle_sharding_invariance():
         assert np.array_equal(whole.observation, np.concatenate([p.observation for p in parts]))
         assert np.array_equal(whole.desired_goal, np.concatenate([p.desired_goal for p in parts]))
         assert np.array_equal(whole.reward, np.concatenate([p.reward for p in parts]))
+
+
+def test_baseline_config0_shape_single_env_1000_steps():
+    """BASELINE.json configs[0]: BenchmarkPlanningEnv-v0, 2 movers, ONE env, random actions, 1000 steps with a reset whenever
+    an episode ends (the reference's own CPU-runnable case) — run on the oracle with reference-default kwargs.
+    Invariants of the reference's step contract: rewards in {-50, +50, -2, -1}, terminated <=> |reward| == 50, TimeLimit(50),
+    a collision flag with every -50, state inside the layout while no wall collision is reported."""
+    cfg, _ = gpr.planning_config(num_envs=1, layout_tiles=np.ones((3, 3)), num_movers=2, autoreset_mode='same_step', seed=0)
+    env = oracle.OracleEnv(cfg)
+    env.reset(seed=0)
+    rng = np.random.default_rng(0)
+    episodes, lengths, length = 0, [], 0
+    for _ in range(1000):
+        act = rng.uniform(-10.0, 10.0, (1, 4)).astype(np.float32)
+        env.step(act)
+        r, term, trunc = float(env.reward[0]), bool(env.terminated[0]), bool(env.truncated[0])
+        length += 1
+        assert r in (-50.0, 50.0, -2.0, -1.0)
+        assert term == (abs(r) == 50.0)
+        assert (r == -50.0) == bool(env.mover_collision[0] or env.wall_collision[0])
+        if term or trunc:
+            assert length <= 50 and (trunc == (length == 50) or term)
+            episodes += 1
+            lengths.append(length)
+            length = 0
+            assert env.elapsed_steps[0] == 0 and not np.any(env.vel[0])  # SAME_STEP: the new episode has already begun
+            assert np.all(env.pos[0] >= 0.11) and np.all(env.pos[0] <= 0.55)  # spawn box incl. the plan:264-267 quirk
+        else:
+            assert np.all(env.pos[0] > 0.0) and np.all(env.pos[0] < 0.72)
+    assert episodes > 50 and max(lengths) <= 50
