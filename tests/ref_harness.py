@@ -3,7 +3,8 @@
 The reference (``/root/reference``) needs ``mujoco``, ``gymnasium``, ``pettingzoo`` and ``matplotlib``, none of which are
 installed here.  Every pure-NumPy function on the step path (``qpos_is_valid``, ``check_mover_collision``,
 ``geometry_2D_utils.*``, ``ensure_max_dyn_val``, ``compute_reward`` ...) takes its numeric inputs as arguments, so it runs
-unmodified once those four imports are stubbed in ``sys.modules`` (recipe: SURVEY.md appendix A).
+unmodified once those four imports are stubbed in ``sys.modules`` (recipe: SURVEY.md appendix A).  ``mujoco`` itself is replaced by
+the closed-form stand-in of ``tests/mujoco_standin.py``, so the reference's ``reset()`` / ``step()`` run unmodified too.
 
 This module is used ONLY by ``tests/`` and by ``tests/golden/make_golden.py`` (the script that generated the committed
 fixtures).  It never runs on the GPU box (``/root/reference`` does not exist there): ``available()`` is False there and the
@@ -43,7 +44,11 @@ def install() -> None:
         sys.modules[name] = m
         return m
 
-    mj = MagicMock(name='mujoco')
+    # `mujoco`: the closed-form stand-in (tests/mujoco_standin.py) — parses the XML the reference generates and integrates
+    # the movers with the recurrence the reference's own tests assert against real MuJoCo
+    import mujoco_standin
+
+    mj = mujoco_standin.as_module()
     sys.modules['mujoco'] = mj
     sys.modules['mujoco.viewer'] = mj.viewer
 
@@ -54,10 +59,14 @@ def install() -> None:
 
     class _Box:
         def __init__(self, low, high, shape=None, dtype=None):
-            self.low, self.high, self.shape = low, high, shape
+            shape = tuple(shape) if shape is not None else np.asarray(low).shape
+            self.shape, self.dtype = shape, np.dtype(dtype or np.float64)
+            self.low = np.broadcast_to(np.asarray(low, dtype=np.float64), shape).copy()
+            self.high = np.broadcast_to(np.asarray(high, dtype=np.float64), shape).copy()
 
         def contains(self, x):
-            return True
+            x = np.asarray(x)
+            return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
 
     class _Dict(dict):
         pass
@@ -83,25 +92,29 @@ def install() -> None:
     sys.path.insert(0, REFERENCE_ROOT)
     sys.dont_write_bytecode = True
 
-    from gymnasium_planar_robotics.envs import basic_envs
-    from gymnasium_planar_robotics.utils import mujoco_utils
+    import gymnasium_planar_robotics.envs.basic_envs  # noqa: F401  (nothing of the reference is patched)
 
-    # the only MuJoCo-name-dependent bits on the construction path
-    mujoco_utils.get_mujoco_type_names = lambda model, obj_type, name_pattern='': []
-    basic_envs.BasicPlanarRoboticsEnv._check_mujoco_name_order = lambda self: None
     _installed = True
 
 
 def make_planning_env(**kwargs):
-    """Construct the reference's BenchmarkPlanningEnv (MuJoCo mocked). Only argument-taking NumPy methods are meaningful."""
+    """Construct the reference's unmodified BenchmarkPlanningEnv on the closed-form MuJoCo stand-in."""
     install()
     from gymnasium_planar_robotics.envs.planning.benchmark_planning_env import BenchmarkPlanningEnv
 
     kwargs.setdefault('show_2D_plot', False)
     kwargs.setdefault('render_mode', None)
-    env = BenchmarkPlanningEnv(**kwargs)
-    env.cycle_time = 0.001
-    return env
+    return BenchmarkPlanningEnv(**kwargs)
+
+
+def make_pushing_env(**kwargs):
+    """The reference's BenchmarkPushingEnv on the stand-in (contact-free trajectories only: the stand-in raises
+    ``mujoco.ContactError`` when the mover reaches the object)."""
+    install()
+    from gymnasium_planar_robotics.envs.manipulation.benchmark_pushing_env import BenchmarkPushingEnv
+
+    kwargs.setdefault('render_mode', None)
+    return BenchmarkPushingEnv(**kwargs)
 
 
 def geometry():
