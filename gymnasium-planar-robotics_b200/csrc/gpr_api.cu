@@ -78,6 +78,12 @@ struct gpr_handle {
     size_t tev_used = 0;
     // staging for the *_host entry points
     cudaStream_t host_stream = nullptr;
+    // ordering between the caller's stream(s) and the private host_stream (a non-blocking stream: it does not even order
+    // with the legacy default stream): every call that enqueues work on a caller stream records `order_ev` there, and a
+    // *_host call waits for it on host_stream before launching.  The other direction needs no event: *_host calls
+    // synchronise host_stream before they return.
+    cudaEvent_t order_ev = nullptr;
+    bool order_pending = false;
     void* d_stage = nullptr;  // device: action + all outputs
     void* h_stage = nullptr;  // pinned mirror
     size_t stage_bytes = 0;
@@ -190,6 +196,7 @@ extern "C" void gpr_destroy(gpr_handle* h) {
         if (p) cudaFree(p);
     for (cudaEvent_t ev : h->tev) cudaEventDestroy(ev);
     if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->order_ev) cudaEventDestroy(h->order_ev);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     cudaSetDevice(prev);
     delete h;
@@ -499,6 +506,16 @@ struct DeviceGuard {
     }
 };
 
+// Work was enqueued on caller stream `s`: the next *_host call (private stream) must run after it.
+static int note_caller_work(gpr_handle* h, cudaStream_t s) {
+    // (no *_host call yet: nothing to order — the first one synchronises the device when it creates host_stream)
+    if (!h->host_stream || s == h->host_stream) return GPR_OK;
+    if (!h->order_ev) CU(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->order_ev, s));
+    h->order_pending = true;
+    return GPR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // reset / step
 // ---------------------------------------------------------------------------------------------------------------------
@@ -529,7 +546,7 @@ extern "C" int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, u
         CU(launch_push(true, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, s));
     }
     h->launches += 1;
-    return GPR_OK;
+    return note_caller_work(h, s);
 }
 
 extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* out, void* stream) {
@@ -573,7 +590,7 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
     }
     if (te) CU(cudaEventRecord(te[2], s));
     h->launches += 1;
-    return GPR_OK;
+    return note_caller_work(h, s);
 }
 
 extern "C" int gpr_kernel_times(gpr_handle* h, int enable, double* host_ms) {
@@ -630,6 +647,7 @@ static StageLayout stage_layout(const gpr_handle* h) {
 static int ensure_stage(gpr_handle* h) {
     if (h->d_stage) return GPR_OK;
     const StageLayout L = stage_layout(h);
+    CU(cudaDeviceSynchronize());  // work enqueued on caller streams before the private stream existed
     CU(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&h->d_stage, L.total));
     CU(cudaMemset(h->d_stage, 0, L.total));
@@ -708,6 +726,15 @@ static int finish_host_call(gpr_handle* h, const StageLayout& L, const HostRoute
     return GPR_OK;
 }
 
+// gpr_reset / gpr_step / gpr_set_state on a caller stream, then a *_host call: host_stream waits for the caller's work
+static int order_host_stream(gpr_handle* h) {
+    if (h->order_pending) {
+        CU(cudaStreamWaitEvent(h->host_stream, h->order_ev, 0));
+        h->order_pending = false;
+    }
+    return GPR_OK;
+}
+
 extern "C" int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out) {
     if (!h || !host_action || !host_out) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
     DeviceGuard g(h->device);
@@ -729,6 +756,8 @@ extern "C" int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_
     // host-I/O step pays for is the result traffic: SM stores to pinned memory sustain ~25 GB/s (the copy engine: 55),
     // and sub-sector stores are charged like full ones — hence the CTA-coalesced flag / reward stores of the step kernel.
     const HostRoute r = route_outputs(h, L, host_out);
+    rc = order_host_stream(h);
+    if (rc != GPR_OK) return rc;
     rc = gpr_step(h, dev_action, &r.dev, h->host_stream);
     if (rc != GPR_OK) return rc;
     return finish_host_call(h, L, r, host_out);
@@ -741,6 +770,8 @@ extern "C" int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gp
     if (rc != GPR_OK) return rc;
     const StageLayout L = stage_layout(h);
     const HostRoute r = route_outputs(h, L, host_out);
+    rc = order_host_stream(h);
+    if (rc != GPR_OK) return rc;
     rc = gpr_reset(h, nullptr, reseed, seed, nullptr, nullptr, nullptr, &r.dev, h->host_stream);
     if (rc != GPR_OK) return rc;
     return finish_host_call(h, L, r, host_out);
@@ -788,7 +819,8 @@ extern "C" int gpr_set_state(gpr_handle* h, const gpr_state* src, void* stream) 
     if (!h || !src) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
     DeviceGuard g(h->device);
     if (src->goal) h->goal_dirty = true;
-    return copy_state(h, src, true, (cudaStream_t)stream);
+    int rc = copy_state(h, src, true, (cudaStream_t)stream);
+    return rc != GPR_OK ? rc : note_caller_work(h, (cudaStream_t)stream);
 }
 
 extern "C" int gpr_get_seed(const gpr_handle* h, uint64_t* seed) {

@@ -1645,6 +1645,12 @@ __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) plan
             }
         }
     }
+    // Launched as the step kernel's programmatic dependent, this grid may run out of work while the step grid's last
+    // CTAs are still writing their results (every step warp reports BEFORE its trailing stores).  griddepcontrol.wait
+    // returns once the prerequisite grid has completed and its memory operations are visible: whatever follows this
+    // kernel in the stream — the next step, a copy, cudaStreamSynchronize — is then ordered after BOTH grids, as PTX
+    // requires of a dependent of a grid that executed launch_dependents.  (An ordinary launch: returns at once.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 template <int G, bool BOX, bool NOISE>

@@ -404,6 +404,43 @@ def test_step_host_matches_device_step():
     e2.close()
 
 
+def test_host_calls_are_ordered_after_caller_stream_work():
+    """gpr_step_host runs on the handle's private non-blocking stream.  A large gpr_reset / gpr_set_state on the
+    caller's stream immediately followed by step_host — no synchronize in between — must still see the reset state."""
+    B = 262144
+    kw = dict(layout_tiles=np.ones((3, 3)), num_movers=4, std_noise=1e-5, seed=5)
+    env, ora = make_pair(B, **kw)
+    rng = np.random.default_rng(23)
+    a0 = rng.uniform(-10, 10, (B, 8)).astype(np.float32)
+    a1 = rng.uniform(-10, 10, (B, 8)).astype(np.float32)
+    env.reset(seed=1)
+    env.step_host(a0)  # (creates the private stream)
+    side = torch.cuda.Stream(device=DEV)
+    with torch.cuda.stream(side):
+        for _ in range(4):  # keep the caller's stream busy: the reset below queues behind these
+            torch.empty(1 << 28, dtype=torch.uint8, device=DEV).zero_()
+        env.reset(seed=5)  # a full re-sample of 262,144 envs on a caller stream ...
+    out = env.step_host(a1)  # ... immediately followed by a host-buffer step
+    ora.reset(seed=5)
+    ora.step(a1)
+    assert np.array_equal(out[0]['achieved_goal'], ora.achieved_goal.astype(np.float32))
+    assert np.array_equal(out[1], ora.reward.astype(np.float32)) and np.array_equal(out[2], ora.terminated.astype(bool))
+    # same for gpr_set_state
+    st = {k: v.clone() for k, v in env.get_state().items()}
+    torch.cuda.synchronize()
+    env.step_host(a0)
+    with torch.cuda.stream(side):
+        torch.empty(1 << 28, dtype=torch.uint8, device=DEV).zero_()
+        env.set_state(st)
+    o2 = env.step_host(a0)
+    r_first = o2[1].copy()
+    env.set_state(st)
+    torch.cuda.synchronize()
+    o3 = env.step_host(a0)
+    assert np.array_equal(r_first, o3[1])
+    env.close()
+
+
 def test_step_host_copy_engine_route_matches(tmp_path):
     """GPR_HOST_IO=dma (results through device staging + copy engine instead of zero-copy stores; read once per process,
     hence the subprocess) and pageable caller buffers give the same results as the default route."""
