@@ -7,6 +7,8 @@ MORE than the bar: the float64 state is compared for exact equality, and the flo
 float64 values rounded once.
 """
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -280,31 +282,27 @@ def test_reference_wall_vectors_directly_on_the_gpu():
 
 
 def test_sampled_starts_follow_the_reference_distribution():
-    """Reset sampling cannot be compared draw for draw (NumPy's PCG64 vs Philox), so it is compared in distribution: the
-    reference's loop (planning:369-385: draw all movers uniformly, redraw everything until no pair is closer than 2r)
-    restated in NumPy against the on-device sampler, two-sample Kolmogorov-Smirnov on coordinates and pair distances."""
+    """Reset sampling cannot be compared draw for draw (NumPy's PCG64 vs Philox), so it is compared in distribution
+    against 4,096 resets drawn by the reference's OWN ``_reset_callback`` loop (planning:355-418, run unmodified through
+    the harness; committed as tests/golden/reference_reset_samples.npz by tests/golden/make_reset_samples.py):
+    two-sample Kolmogorov-Smirnov on coordinates and pair distances of starts and goals."""
     from scipy import stats
 
     B, N = 16384, 4
+    ref = np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_reset_samples.npz'))
     env = gpr.BenchmarkPlanningVecEnv(B, layout_tiles=np.ones((3, 3)), num_movers=N, device=DEV, std_noise=0.0, seed=11)
     env.reset(seed=11)
     p = env.get_state()['pos'].cpu().numpy()
     g = env.get_state()['goal'].cpu().numpy()
     env.close()
-    rng = np.random.default_rng(0)
-    ref = np.zeros((0, N, 2))
-    while ref.shape[0] < B:
-        c = rng.uniform(0.11, 0.55, (400000, N, 2))
-        d = np.linalg.norm(c[:, :, None] - c[:, None], axis=-1) + 9 * np.eye(N)
-        ref = np.concatenate([ref, c[(d > 0.22).all(axis=(1, 2))]])
-    ref = ref[:B]
 
     def feats(x):
         d = np.linalg.norm(x[:, :, None] - x[:, None], axis=-1)[:, np.triu_indices(N, 1)[0], np.triu_indices(N, 1)[1]]
         return {'x': x[..., 0].ravel(), 'y': x[..., 1].ravel(), 'min_pair': d.min(axis=1), 'max_pair': d.max(axis=1), 'x0': x[:, 0, 0]}
 
     for name, arr in (('start', p), ('goal', g)):
-        fa, fb = feats(arr), feats(ref)
+        fa, fb = feats(arr), feats(ref[name])
+        assert (fb['min_pair'] >= 0.22).all() and ref[name].min() >= 0.11 and ref[name].max() <= 0.55  # the reference's own sample
         for k in fa:
             pv = stats.ks_2samp(fa[k], fb[k]).pvalue
             assert pv > 1e-4, f'{name} {k}: KS p-value {pv}'
@@ -600,6 +598,48 @@ def test_full_size_properties():
     assert env.core.reset_failures() == 0
     env.close()
     env2.close()
+
+
+@pytest.mark.parametrize('config', ['configs1_planning4', 'configs3_planning8box', 'configs2_pushing'])
+def test_oracle_lockstep_at_baseline_sizes(config):
+    """the oracle in lock-step with CUDA at BASELINE's FULL sizes — configs[1] 65,536 envs x 50 steps,
+    configs[3] 262,144 x 10, configs[2] 65,536 x 20 — reference-default kwargs (std_noise = 1e-5), SAME_STEP auto-reset with
+    on-device sampling, uniform random actions: flags, rewards and the float64 state must be bit-identical every step."""
+    if config == 'configs1_planning4':
+        B, steps, kw, cls, cfn = 65536, 50, dict(layout_tiles=np.ones((3, 3)), num_movers=4), gpr.BenchmarkPlanningVecEnv, gpr.planning_config
+    elif config == 'configs3_planning8box':
+        B, steps, cls, cfn = 262144, 10, gpr.BenchmarkPlanningVecEnv, gpr.planning_config
+        kw = dict(layout_tiles=np.ones((5, 5)), num_movers=8, learn_jerk=True, collision_params={'shape': 'box', 'size': np.array([0.08, 0.08])})
+    else:
+        B, steps, kw, cls, cfn = 65536, 20, dict(), gpr.BenchmarkPushingVecEnv, gpr.pushing_config
+    env = cls(B, device=DEV, seed=77, **kw)
+    cfg, _ = cfn(num_envs=B, seed=77, **kw)
+    ora = oracle.OracleEnv(cfg, nthreads=oracle.max_threads())
+    env.reset(seed=77)
+    ora.reset(seed=77)
+    lim = cfg.j_max if cfg.learn_jerk else cfg.a_max
+    rng = np.random.default_rng(5)
+    keys = ('pos', 'vel', 'acc', 'goal') + (('act', 'mover_rot', 'object_pos', 'object_vel') if config == 'configs2_pushing' else ())
+    resets = 0
+    for t in range(steps):
+        a = rng.uniform(-lim, lim, (B, ora.action_dim)).astype(np.float32)
+        obs, r, term, trunc, info = env.step(torch.as_tensor(a, device=DEV))
+        ora.step(a)
+        torch.cuda.synchronize()
+        for k in ('terminated', 'truncated', 'is_success', 'mover_collision', 'wall_collision'):
+            assert np.array_equal(env.core.buf[k].cpu().numpy(), getattr(ora, k)), f'step {t}: {k}'
+        assert np.array_equal(r.cpu().numpy(), ora.reward.astype(np.float32)), f'step {t}: reward'
+        assert np.array_equal(obs['achieved_goal'].cpu().numpy(), ora.achieved_goal.astype(np.float32)), f'step {t}: achieved_goal'
+        resets += int(ora.terminated.sum() + ora.truncated.sum())
+        if t % 5 == 4 or t == steps - 1:
+            st = env.get_state()
+            torch.cuda.synchronize()
+            for k in keys:
+                assert np.array_equal(st[k].cpu().numpy(), getattr(ora, k)), f'step {t}: state {k}'
+            assert np.array_equal(st['rng_counter'].cpu().numpy().view(np.uint32), ora.rng_counter)
+    assert resets > B // 4  # the on-device rejection sampling really ran at this size
+    assert config == 'configs2_pushing' or env.core.reset_failures() == 0
+    env.close()
 
 
 def test_full_size_pettingzoo_eight_movers_box_jerk():
