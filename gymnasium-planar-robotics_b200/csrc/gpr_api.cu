@@ -490,6 +490,10 @@ static PushArgs push_args(const gpr_handle* h, const gpr_outputs* out) {
     a.ep_return = h->ep_return;
     a.stats = h->stats;
     a.fail_count = h->fail_count;
+    a.queue = h->reset_list;  // (the planning env's auto-reset work list: same size, unused by the pushing env)
+    a.queue_ctl = h->reset_count;
+    a.queue_cursor = reinterpret_cast<uint32_t*>(h->reset_count + 2);
+    a.parity = h->parity;
     if (out) a.out = *out;
     return a;
 }
@@ -543,7 +547,7 @@ extern "C" int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, u
         a.inject_start = reinterpret_cast<const double2*>(inject_start);
         a.inject_goal = reinterpret_cast<const double2*>(inject_goal);
         a.inject_object = reinterpret_cast<const double2*>(inject_object);
-        CU(launch_push(true, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, s));
+        CU(launch_push(PUSH_RESET, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, h->num_sms, s));
     }
     h->launches += 1;
     return note_caller_work(h, s);
@@ -585,8 +589,11 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
         PushArgs a = push_args(h, out);
         a.action = reinterpret_cast<const float2*>(action);
         a.write_goal = write_goal;
-        CU(launch_push(false, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, s));
+        CU(launch_push(PUSH_STEP, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, h->num_sms, s));
         if (te) CU(cudaEventRecord(te[1], s));
+        CU(launch_push(PUSH_CONTACT, h->cfg.c_shape == GPR_SHAPE_BOX, h->noise, a, h->num_sms, s));
+        h->parity ^= 1;
+        h->launches += 1;
     }
     if (te) CU(cudaEventRecord(te[2], s));
     h->launches += 1;

@@ -16,7 +16,8 @@ template <int G>
 cudaError_t launch_plan_g(PlanKernel which, bool box, bool noise, const PlanArgs& a, int num_sms, cudaStream_t s);
 
 // gpr_pushing_kernels.cu
-cudaError_t launch_push(bool reset, bool box, bool noise, const PushArgs& a, cudaStream_t s);
+enum PushKernel { PUSH_STEP = 0, PUSH_RESET = 1, PUSH_CONTACT = 2 };
+cudaError_t launch_push(PushKernel which, bool box, bool noise, const PushArgs& a, int num_sms, cudaStream_t s);
 
 // gpr_misc_kernels.cu
 cudaError_t launch_compute_reward(int kind, int N, int batch, double threshold, const float* achieved, const float* desired,

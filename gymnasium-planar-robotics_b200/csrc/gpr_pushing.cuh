@@ -50,6 +50,11 @@ struct PushArgs {
     double* stats;
     uint32_t* fail_count;
     int write_goal;  // see PlanArgs
+    // work queue of the envs that entered the contact regime (see pushing_step_kernel), double-buffered by step parity
+    unsigned long long* queue;      // [B] (cycle << 32 | env)
+    unsigned long long* queue_ctl;  // [2] entries appended
+    uint32_t* queue_cursor;         // [2] entries claimed by pushing_contact_kernel
+    int parity;
     // per-call I/O
     const float2* action;
     gpr_outputs out;
@@ -286,174 +291,104 @@ __device__ __forceinline__ void push_reward(bool reached, bool wc, float& reward
     succ = reached && !wc;                          // push:602
 }
 
-// ---- the env-step kernel -------------------------------------------------------------------------------------------------
-// Per cycle a lane is either FREE (object at rest and out of the mover's reach: gpr_push_substep reduces to integrating the
-// mover, ~60 instructions) or in the CONTACT regime (manifold + 8 projected Gauss-Seidel sweeps, thousands of float64
-// instructions).  With random actions ~20% of the envs are in the contact regime at any time, i.e. nearly every warp would
-// execute the long path with a handful of active lanes.  The kernel therefore COMPACTS them: contact lanes queue their
-// inputs in shared memory, the first `count` threads of the CTA run gpr_push_substep on the queue with full warps, and the
-// owners read their results back.  gpr_push_substep is a pure function of its inputs, so this changes no result bit.
+// ---- the env-step kernels -------------------------------------------------------------------------------------------------
+// Per cycle an environment is either FREE (object at rest and out of the mover's reach: gpr_push_substep_free, ~60
+// instructions) or in the CONTACT regime (manifold + projected Gauss-Seidel sweeps: thousands of dependent float64
+// instructions), and an object that has been touched keeps sliding for the rest of its episode.  With random actions about a
+// fifth of the environments are in the contact regime at any time — nearly every warp would run the long path with a handful
+// of active lanes.  The step is therefore split BY POPULATION into two launches (no CTA barrier anywhere):
+//
+//   pushing_step_kernel     one lane per env.  Runs the cycles of the free regime; an env that meets the contact condition
+//                           at the top of cycle c (gpr_push_is_free, the very test gpr_push_substep makes) is parked: its
+//                           state as of that cycle goes back to the state arrays and (c, env) is appended to a work queue.
+//                           Every other env finishes here: observation, reward, flags, statistics, auto-reset.
+//   pushing_contact_kernel  persistent warps pull queued envs 32 at a time and run their remaining cycles with the general
+//                           substep, every lane in the long path, then finish them with the same code.
+//
+// Both kernels evaluate the same functions on the same values in the same order as the one-kernel formulation (and as the
+// oracle): which kernel runs a cycle changes no result bit.
 constexpr int kPushCta = 128;
-constexpr int kPushFields = 16;  // mover (7) + object (7) + commanded acceleration (2); results reuse the slots
-
-__device__ __forceinline__ void push_q_put(double (*q)[kPushCta], int slot, const gpr_body2& M, const gpr_body2& O, double a0,
-                                           double a1) {
-    q[0][slot] = M.x;  q[1][slot] = M.y;  q[2][slot] = M.c;  q[3][slot] = M.s;  q[4][slot] = M.vx;  q[5][slot] = M.vy;  q[6][slot] = M.w;
-    q[7][slot] = O.x;  q[8][slot] = O.y;  q[9][slot] = O.c;  q[10][slot] = O.s; q[11][slot] = O.vx; q[12][slot] = O.vy; q[13][slot] = O.w;
-    q[14][slot] = a0;  q[15][slot] = a1;
-}
-__device__ __forceinline__ void push_q_get(double (*q)[kPushCta], int slot, gpr_body2& M, gpr_body2& O, double& a0, double& a1) {
-    M.x = q[0][slot];  M.y = q[1][slot];  M.c = q[2][slot];  M.s = q[3][slot];  M.vx = q[4][slot];  M.vy = q[5][slot];  M.w = q[6][slot];
-    O.x = q[7][slot];  O.y = q[8][slot];  O.c = q[9][slot];  O.s = q[10][slot]; O.vx = q[11][slot]; O.vy = q[12][slot]; O.w = q[13][slot];
-    a0 = q[14][slot];  a1 = q[15][slot];
-}
 
 #ifndef GPR_PUSH_MINB
 #define GPR_PUSH_MINB 4
 #endif
-#ifndef GPR_PUSH_SPREAD
-#define GPR_PUSH_SPREAD 0
-#endif
+
+// push:419-455 _mujoco_step_callback for one cycle: returns the commanded acceleration (cx, cy) — the limited acceleration, or
+// the integrator state `act` in jerk mode — and updates s.act.  n4/have0: this cycle's noise block 0, generated on demand.
 template <bool BOX, bool NOISE>
-__global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(const __grid_constant__ PushArgs a) {
-    __shared__ Tables tb;
-    __shared__ double q[kPushFields][kPushCta];
-    __shared__ int q_count;
-    load_tables(tb, a.L);
-    if (threadIdx.x == 0) q_count = 0;
-    __syncthreads();
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = e < a.B;  // (no early return: barriers and the reset's stage B are collective)
-    const uint32_t env_global = a.env_base + (uint32_t)e;
-    PushState s;
-    memset(&s, 0, sizeof(s));
-    uint32_t event = 0;
-    int elapsed = 0;
-    bool pending = false;
-    if (valid) {
-        push_load(a, e, s);
-        event = a.rng[e];
-        elapsed = a.elapsed[e];
-        pending = a.autoreset == GPR_AUTORESET_NEXT_STEP && a.needs_reset[e] != 0;
+__device__ __forceinline__ void push_control(const PushArgs& a, PushState& s, double ux, double uy, uint32_t env_global,
+                                             uint32_t event, uint32_t s0, float (&n4)[4], bool& have0, double& cx, double& cy) {
+    double dxv = ux, dyv = uy, jx = 0.0, jy = 0.0;
+    if (a.learn_jerk) ensure_max(s.acc.x, s.acc.y, a.a_max, a.a_max2_lo, ux, uy, a.dt, dxv, dyv, jx, jy);  // push:432 (real qacc)
+    double velx = s.M.vx, vely = s.M.vy;
+    if (NOISE) {
+        // the velocity noise (push:428) is generated only where it can matter
+        const double sx = dadd(dmul(a.dt, dxv), s.M.vx), sy = dadd(dmul(a.dt, dyv), s.M.vy);
+        if (BOX || !(dadd(dmul(sx, sx), dmul(sy, sy)) < a.v_lazy2)) {
+            normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
+            have0 = true;
+            velx = dadd(velx, dmul((double)n4[0], a.sigma_v));
+            vely = dadd(vely, dmul((double)n4[1], a.sigma_v));
+        }
     }
+    double t0, t1, ax, ay;
+    ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);  // push:435 / 440
+    if (a.learn_jerk) {
+        if (dxv != ax || dyv != ay) {  // push:436
+            jx = ddiv(dsub(ax, s.acc.x), a.dt);
+            jy = ddiv(dsub(ay, s.acc.y), a.dt);
+        }
+        // integrator actuator with actearly (push:305-311): act += dt*ctrl, force uses the new act
+        s.act.x = dadd(s.act.x, dmul(a.dt, jx));
+        s.act.y = dadd(s.act.y, dmul(a.dt, jy));
+        cx = s.act.x;
+        cy = s.act.y;
+    } else {
+        cx = ax;
+        cy = ay;
+    }
+}
+
+// basic:1888-1894 wall check of one cycle (no mover-mover check with one mover; push:607 asserts no mover collision).
+// Circle shape: with a travel budget exactly as in planning_step_kernel (certified clearance, wall_core).
+template <bool BOX, bool NOISE>
+__device__ __forceinline__ bool push_wall_cycle(const PushArgs& a, const Tables& tb, const PushState& s, uint32_t env_global,
+                                                uint32_t event, uint32_t s0, float (&n4)[4], bool have0, float cwf, int& gi,
+                                                int& gj, float& travel, float& lim_w) {
+    bool wc = false;
+    if (BOX) {
+        if (NOISE && !have0) normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
+        wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 0, n4[2], n4[3], env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT);
+    } else {
+        const float avx = fabsf((float)s.M.vx), avy = fabsf((float)s.M.vy);
+        travel += (fmaxf(avx, avy) + 0.5f * fminf(avx, avy)) * 1.0001f;
+        if (!(travel < lim_w)) {
+            float clear_w;
+            const int f = wall_fast(a, tb, s.M.x, s.M.y, cwf, cwf, gi, gj, clear_w);
+            if (f == 2) {  // too close to call in float32: the exact check on the noisy position
+                if (NOISE && !have0) normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
+                wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 0, n4[2], n4[3], env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT);
+                guess_cell(a, s.M.x, s.M.y, gi, gj);
+            } else {
+                wc = f == 0;
+            }
+            lim_w = (travel + clear_w * a.inv_dtf) * 0.999999f;
+        }
+    }
+    return wc;
+}
+
+// Everything after the cycle loop for one lane's env (warp-collective: EVERY lane of the warp calls it; `live` = this lane
+// holds an env that has finished its cycles here): observation, reward, flags, statistics, auto-reset, state write-back.
+template <bool BOX, bool NOISE>
+__device__ __forceinline__ void push_finish(const PushArgs& a, const Tables& tb, int e, bool live, bool pending, PushState& s,
+                                            uint32_t env_global, uint32_t event, int elapsed, bool wc) {
     double obs[6] = {0, 0, 0, 0, 0, 0};
     double2 ag = make_double2(0, 0);
     bool reached = false;
     float reward = 0.f;
-    bool term = false, succ = false, wc = false;
-    const bool stepped = valid && !pending;
-    double ux = 0.0, uy = 0.0;
-    if (stepped) {
-        const float2 af = a.action[e];
-        ux = fmin(fmax((double)af.x, -a.act_lim), a.act_lim);  // basic:1869-1873
-        uy = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
-    }
-    // circle shape: wall check with a travel budget exactly as in planning_step_kernel (certified clearance, wall_core)
-    int gi = 0, gj = 0;
-    guess_cell(a, s.M.x, s.M.y, gi, gj);
-    const float cwf = (float)a.c_wall[0][0];
-    float travel = 0.f, lim_w = -1.f;
-    bool active = stepped;
-    for (int cyc = 0; cyc < a.num_cycles; ++cyc) {  // basic:1879
-        if (!__syncthreads_or(active)) break;        // (also separates the queue uses of consecutive cycles)
-        const uint32_t s0 = (uint32_t)cyc * 4u;
-        float n4[4] = {0.f, 0.f, 0.f, 0.f};
-        bool have0 = false;
-        bool queued = false;
-        int slot = 0;
-        if (active) {
-            // push:419-455 _mujoco_step_callback; the velocity noise (push:428) is generated only where it can matter
-            double cx, cy;
-            {
-                double dxv = ux, dyv = uy, jx = 0.0, jy = 0.0;
-                if (a.learn_jerk) ensure_max(s.acc.x, s.acc.y, a.a_max, a.a_max2_lo, ux, uy, a.dt, dxv, dyv, jx, jy);  // push:432 (real qacc)
-                double velx = s.M.vx, vely = s.M.vy;
-                if (NOISE) {
-                    const double sx = dadd(dmul(a.dt, dxv), s.M.vx), sy = dadd(dmul(a.dt, dyv), s.M.vy);
-                    if (BOX || !(dadd(dmul(sx, sx), dmul(sy, sy)) < a.v_lazy2)) {
-                        normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
-                        have0 = true;
-                        velx = dadd(velx, dmul((double)n4[0], a.sigma_v));
-                        vely = dadd(vely, dmul((double)n4[1], a.sigma_v));
-                    }
-                }
-                double t0, t1, ax, ay;
-                ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);  // push:435 / 440
-                if (a.learn_jerk) {
-                    if (dxv != ax || dyv != ay) {  // push:436
-                        jx = ddiv(dsub(ax, s.acc.x), a.dt);
-                        jy = ddiv(dsub(ay, s.acc.y), a.dt);
-                    }
-                    // integrator actuator with actearly (push:305-311): act += dt*ctrl, force uses the new act
-                    s.act.x = dadd(s.act.x, dmul(a.dt, jx));
-                    s.act.y = dadd(s.act.y, dmul(a.dt, jy));
-                    cx = s.act.x;
-                    cy = s.act.y;
-                } else {
-                    cx = ax;
-                    cy = ay;
-                }
-            }
-            // mj_step (basic:1882): contact regime -> queue, free regime -> in place
-            const double ddx = s.O.x - s.M.x, ddy = s.O.y - s.M.y;
-            const bool contact = !(ddx * ddx + ddy * ddy > a.P.contact_r2) || s.O.vx != 0.0 || s.O.vy != 0.0 || s.O.w != 0.0;
-            if (contact) {
-                slot = atomicAdd(&q_count, 1);
-                push_q_put(q, slot, s.M, s.O, cx, cy);
-                queued = true;
-            } else {
-                double qax, qay;
-                gpr_push_substep(&a.P, &s.M, &s.O, cx, cy, &qax, &qay);
-                s.acc = make_double2(qax, qay);
-            }
-        }
-        __syncthreads();
-        {
-            // queue item i -> lane i / W of warp i % W (W warps per CTA): the items fill the low lanes of ALL warps, so the
-            // long dependent float64 chains of the contact solve overlap across W warps per CTA instead of one
-            // (GPR_PUSH_SPREAD=0: item i -> thread i, the densest packing)
-            const int n = q_count;
-            constexpr int W = kPushCta / 32;
-            const int item = GPR_PUSH_SPREAD ? (int)(threadIdx.x & 31u) * W + (int)(threadIdx.x >> 5) : (int)threadIdx.x;
-            if (item < n) {
-                gpr_body2 M, O;
-                double a0, a1, qax, qay;
-                push_q_get(q, item, M, O, a0, a1);
-                gpr_push_substep(&a.P, &M, &O, a0, a1, &qax, &qay);
-                push_q_put(q, item, M, O, qax, qay);
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) q_count = 0;
-        if (queued) {
-            double qax, qay;
-            push_q_get(q, slot, s.M, s.O, qax, qay);
-            s.acc = make_double2(qax, qay);
-        }
-        if (active) {
-            // basic:1888-1894 wall check; no mover-mover check with one mover; push:607 asserts no mover collision
-            if (BOX) {
-                if (NOISE && !have0) normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
-                wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 0, n4[2], n4[3], env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT);
-            } else {
-                const float avx = fabsf((float)s.M.vx), avy = fabsf((float)s.M.vy);
-                travel += (fmaxf(avx, avy) + 0.5f * fminf(avx, avy)) * 1.0001f;
-                if (!(travel < lim_w)) {
-                    float clear_w;
-                    const int f = wall_fast(a, tb, s.M.x, s.M.y, cwf, cwf, gi, gj, clear_w);
-                    if (f == 2) {  // too close to call in float32: the exact check on the noisy position
-                        if (NOISE && !have0) normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, 0u, n4);
-                        wc = push_wall_bad<BOX, NOISE>(a, tb, s.M, 0, n4[2], n4[3], env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT);
-                        guess_cell(a, s.M.x, s.M.y, gi, gj);
-                    } else {
-                        wc = f == 0;
-                    }
-                    lim_w = (travel + clear_w * a.inv_dtf) * 0.999999f;
-                }
-            }
-            if (wc) active = false;  // basic:1904
-        }
-    }
+    bool term = false, succ = false;
+    const bool stepped = live && !pending;
     if (stepped) {
         push_observe<NOISE>(a, s, env_global, event, obs, ag, reached);
         push_reward(reached, wc, reward, term, succ);
@@ -480,7 +415,7 @@ __global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(c
         if (a.out.wall_collision) a.out.wall_collision[e] = wc;
     }
     // ---- auto-reset (push:373-417), stages A / B / C
-    const bool need = valid && ((a.autoreset == GPR_AUTORESET_SAME_STEP && done) || pending);
+    const bool need = live && ((a.autoreset == GPR_AUTORESET_SAME_STEP && done) || pending);
     bool settled = true;
     if (need) {
         if (a.autoreset == GPR_AUTORESET_SAME_STEP)
@@ -507,12 +442,140 @@ __global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(c
             if (a.out.wall_collision) a.out.wall_collision[e] = rwc;
         }
     }
-    if (!valid) return;
+    if (!live) return;
     push_store_obs(a, e, a.out.observation, a.out.achieved_goal, (a.write_goal || need) ? a.out.desired_goal : nullptr, obs, ag, s.goal);
     push_store(a, e, s);
     a.rng[e] = event;
     a.elapsed[e] = elapsed;
     if (a.autoreset == GPR_AUTORESET_NEXT_STEP) a.needs_reset[e] = (done && !need) ? 1 : 0;
+}
+
+template <bool BOX, bool NOISE>
+__global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(const __grid_constant__ PushArgs a) {
+    __shared__ Tables tb;
+    load_tables(tb, a.L);
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the other buffer belongs to the next step: clear it now
+        a.queue_ctl[a.parity ^ 1] = 0ull;
+        a.queue_cursor[a.parity ^ 1] = 0u;
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e < a.B;  // (no early return: the reset's stage B is warp-collective)
+    const uint32_t env_global = a.env_base + (uint32_t)e;
+    PushState s;
+    memset(&s, 0, sizeof(s));
+    uint32_t event = 0;
+    int elapsed = 0;
+    bool pending = false;
+    if (valid) {
+        push_load(a, e, s);
+        event = a.rng[e];
+        elapsed = a.elapsed[e];
+        pending = a.autoreset == GPR_AUTORESET_NEXT_STEP && a.needs_reset[e] != 0;
+    }
+    const bool stepped = valid && !pending;
+    double ux = 0.0, uy = 0.0;
+    if (stepped) {
+        const float2 af = a.action[e];
+        ux = fmin(fmax((double)af.x, -a.act_lim), a.act_lim);  // basic:1869-1873
+        uy = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
+    }
+    int gi = 0, gj = 0;
+    guess_cell(a, s.M.x, s.M.y, gi, gj);
+    const float cwf = (float)a.c_wall[0][0];
+    float travel = 0.f, lim_w = -1.f;
+    bool active = stepped, wc = false;
+    int parked_at = -1;
+    for (int cyc = 0; cyc < a.num_cycles; ++cyc) {  // basic:1879
+        if (!__any_sync(FULL, active)) break;
+        if (!active) continue;
+        if (!gpr_push_is_free(&a.P, &s.M, &s.O)) {  // contact regime from this cycle on: hand the env over
+            parked_at = cyc;
+            active = false;
+            continue;
+        }
+        const uint32_t s0 = (uint32_t)cyc * 4u;
+        float n4[4] = {0.f, 0.f, 0.f, 0.f};
+        bool have0 = false;
+        double cx, cy, qax, qay;
+        push_control<BOX, NOISE>(a, s, ux, uy, env_global, event, s0, n4, have0, cx, cy);
+        gpr_push_substep_free(&a.P, &s.M, &s.O, cx, cy, &qax, &qay);  // mj_step (basic:1882), free regime
+        s.acc = make_double2(qax, qay);
+        wc = push_wall_cycle<BOX, NOISE>(a, tb, s, env_global, event, s0, n4, have0, cwf, gi, gj, travel, lim_w);
+        if (wc) active = false;  // basic:1904
+    }
+    // ---- parked envs: state as of the top of cycle `parked_at` + a queue entry (slots reserved with one atomic per warp)
+    const bool parked = parked_at >= 0;
+    const unsigned pm = __ballot_sync(FULL, parked);
+    if (pm) {
+        unsigned long long t = 0ull;
+        if (lane == 0) t = atomicAdd(a.queue_ctl + a.parity, (unsigned long long)__popc(pm));
+        const unsigned slot0 = (unsigned)__shfl_sync(FULL, t, 0);
+        if (parked) {
+            push_store(a, e, s);
+            a.queue[slot0 + __popc(pm & ((1u << lane) - 1u))] = ((unsigned long long)(unsigned)parked_at << 32) | (unsigned long long)(uint32_t)e;
+        }
+    }
+    push_finish<BOX, NOISE>(a, tb, e, valid && !parked, pending, s, env_global, event, elapsed, wc);
+}
+
+#ifndef GPR_PUSH_CONTACT_MINB
+#define GPR_PUSH_CONTACT_MINB 6
+#endif
+constexpr int kPushContactCta = 64;
+
+template <bool BOX, bool NOISE>
+__global__ void __launch_bounds__(kPushContactCta, GPR_PUSH_CONTACT_MINB) pushing_contact_kernel(const __grid_constant__ PushArgs a) {
+    __shared__ Tables tb;
+    load_tables(tb, a.L);
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t count = (uint32_t)a.queue_ctl[a.parity];  // final: pushing_step_kernel has completed
+    uint32_t* const cursor = a.queue_cursor + a.parity;
+    const float cwf = (float)a.c_wall[0][0];
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= count) break;
+        const bool live = base + lane < count;
+        int e = 0, cyc0 = a.num_cycles;
+        PushState s;
+        memset(&s, 0, sizeof(s));
+        uint32_t event = 0;
+        int elapsed = 0;
+        double ux = 0.0, uy = 0.0;
+        if (live) {
+            const unsigned long long entry = a.queue[base + lane];
+            e = (int)(uint32_t)entry;
+            cyc0 = (int)(entry >> 32);
+            push_load(a, e, s);
+            event = a.rng[e];
+            elapsed = a.elapsed[e];
+            const float2 af = a.action[e];
+            ux = fmin(fmax((double)af.x, -a.act_lim), a.act_lim);  // basic:1869-1873
+            uy = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
+        }
+        const uint32_t env_global = a.env_base + (uint32_t)e;
+        int gi = 0, gj = 0;
+        guess_cell(a, s.M.x, s.M.y, gi, gj);
+        float travel = 0.f, lim_w = -1.f;
+        bool wc = false;
+        for (int cyc = cyc0; cyc < a.num_cycles; ++cyc) {
+            const uint32_t s0 = (uint32_t)cyc * 4u;
+            float n4[4] = {0.f, 0.f, 0.f, 0.f};
+            bool have0 = false;
+            double cx, cy, qax, qay;
+            push_control<BOX, NOISE>(a, s, ux, uy, env_global, event, s0, n4, have0, cx, cy);
+            gpr_push_substep(&a.P, &s.M, &s.O, cx, cy, &qax, &qay);  // mj_step (basic:1882), general
+            s.acc = make_double2(qax, qay);
+            wc = push_wall_cycle<BOX, NOISE>(a, tb, s, env_global, event, s0, n4, have0, cwf, gi, gj, travel, lim_w);
+            if (wc) break;  // basic:1904
+        }
+        __syncwarp();
+        push_finish<BOX, NOISE>(a, tb, e, live, false, s, env_global, event, elapsed, wc);
+    }
 }
 
 template <bool BOX, bool NOISE>

@@ -17,6 +17,12 @@
  *                         46-47 uses the body MASS for the rotational damping too); z / roll / pitch are dropped
  *            object     : joint damping (implicit, as MuJoCo's Euler integrator does), ground friction at the four bottom
  *                         corners (each carries m g / 4, friction coefficient mu), mover-object box-box contact
+ *   precision body states, smooth forces and the integrator are float64.  The CONSTRAINT SOLVE (contact manifold in the
+ *            mover's frame, constraint rows, projected Gauss-Seidel sweeps) is float32, like MuJoCo's own GPU port (MJX):
+ *            constraint forces come out of a truncated iterative solver with ~1e-3 relative accuracy, float32 rounding
+ *            (6e-8) is far below that, and the dependent float32 chain is what bounds the kernel's latency.  Every float32
+ *            operation is an explicitly rounded IEEE operation (GPR_FMUL / GPR_FFMA / GPR_FDIV / GPR_FSQRT of gpr_rng.h),
+ *            so the CPU oracle and the CUDA kernels still produce bit-identical trajectories.
  *   contacts MuJoCo-style soft constraints solved by projected Gauss-Seidel in acceleration space:
  *            a_ref = -B v - K d(r) r,  B = 2/(dmax tc),  K = 1/(dmax^2 tc^2 dr^2),  R = (1 - d)/d * A_ii,
  *            solref = (tc, dr) = (0.02, 1), solimp = (0.9, 0.95, 0.001, 0.5, 2) (MuJoCo defaults), friction cone
@@ -33,6 +39,7 @@
 #include <math.h>
 
 #include "gpr.h"
+#include "gpr_rng.h" /* the explicitly rounded float32 primitives */
 
 #if defined(__CUDACC__)
 #define GPR_PHD __host__ __device__ __forceinline__
@@ -53,6 +60,9 @@ typedef struct gpr_push_params {
     double g_lim;      /* friction limit per corner: mu * m g / 4 */
     double o_inv_lin, o_inv_rot; /* 1 / (m + dt D), 1 / (I + dt D): implicit joint damping of the object */
     int iterations;
+    /* float32 copies for the constraint solve (each the float64 value rounded once) */
+    float f_hxM, f_hyM, f_hO, f_imM, f_iIM, f_imO, f_iIO, f_mu, f_B, f_K;
+    float f_d0, f_dw, f_width, f_mid, f_power, f_gR, f_ginv, f_glim, f_glim2, f_D;
 } gpr_push_params;
 
 /* Derived physics parameters from the config — ONE definition shared by the CUDA host code and the CPU oracle so both
@@ -94,6 +104,26 @@ static inline void gpr_push_params_from_config(const gpr_config* c, gpr_push_par
     }
     P->o_inv_lin = 1.0 / (P->obj_mass + P->dt * P->obj_damping);
     P->o_inv_rot = 1.0 / (P->obj_inertia + P->dt * P->obj_damping);
+    P->f_hxM = (float)P->mover_hx;
+    P->f_hyM = (float)P->mover_hy;
+    P->f_hO = (float)P->obj_h;
+    P->f_imM = (float)(1.0 / P->mover_mass);
+    P->f_iIM = (float)(1.0 / P->mover_inertia);
+    P->f_imO = (float)(1.0 / P->obj_mass);
+    P->f_iIO = (float)(1.0 / P->obj_inertia);
+    P->f_mu = (float)P->mu;
+    P->f_B = (float)P->sol_B;
+    P->f_K = (float)P->sol_K;
+    P->f_d0 = (float)P->imp_d0;
+    P->f_dw = (float)P->imp_dw;
+    P->f_width = (float)P->imp_width;
+    P->f_mid = (float)P->imp_mid;
+    P->f_power = (float)P->imp_power;
+    P->f_gR = (float)P->g_R;
+    P->f_ginv = (float)P->g_inv;
+    P->f_glim = (float)P->g_lim;
+    P->f_glim2 = (float)P->g_lim * (float)P->g_lim;
+    P->f_D = (float)P->obj_damping;
 }
 
 typedef struct gpr_body2 {
@@ -101,23 +131,23 @@ typedef struct gpr_body2 {
     double vx, vy, w;   /* linear velocity, yaw rate */
 } gpr_body2;
 
-/* MuJoCo's impedance d(r): d0 -> dw over `width` of penetration, smooth power-law sigmoid (solimp). */
-GPR_PHD double gpr_push_impedance(const gpr_push_params* P, double r) {
-    double x = fabs(r) / P->imp_width;
-    if (x >= 1.0) return P->imp_dw;
-    if (x <= 0.0) return P->imp_d0;
-    double y;
-    if (P->imp_power == 2.0) { /* the default: avoids pow() */
-        if (x <= P->imp_mid) {
-            y = (x * x) / P->imp_mid;
+/* MuJoCo's impedance d(r): d0 -> dw over `width` of penetration, smooth power-law sigmoid (solimp).  float32. */
+GPR_PHD float gpr_push_impedance(const gpr_push_params* P, float r) {
+    const float x = GPR_FDIV(fabsf(r), P->f_width);
+    if (x >= 1.0f) return P->f_dw;
+    if (x <= 0.0f) return P->f_d0;
+    float y;
+    if (P->f_power == 2.0f) { /* the default: avoids pow() */
+        if (x <= P->f_mid) {
+            y = GPR_FDIV(GPR_FMUL(x, x), P->f_mid);
         } else {
-            double u = 1.0 - x;
-            y = 1.0 - (u * u) / (1.0 - P->imp_mid);
+            const float u = GPR_FSUB(1.0f, x);
+            y = GPR_FSUB(1.0f, GPR_FDIV(GPR_FMUL(u, u), GPR_FSUB(1.0f, P->f_mid)));
         }
     } else {
         y = x; /* other powers fall back to a linear ramp (documented deviation; MuJoCo's default power is 2) */
     }
-    return P->imp_d0 + y * (P->imp_dw - P->imp_d0);
+    return GPR_FFMA(y, GPR_FSUB(P->f_dw, P->f_d0), P->f_d0);
 }
 
 /* advance (c, s) by angle a = dt * w: second-order rotation + renormalisation (no sin/cos call) */
@@ -139,47 +169,44 @@ GPR_PHD double gpr_push_small_yaw(double c, double s) {
     return s * (1.0 + s2 * ((1.0 / 6.0) + s2 * (3.0 / 40.0)));
 }
 
+/* ---- contact manifold, float32, in the MOVER-CENTRED frame (the mover's centre is the origin; its axes are (cM, sM)) ---- */
 typedef struct gpr_contact2 {
-    double px, py; /* contact point (world) */
-    double nx, ny; /* normal, from mover to object */
-    double depth;  /* penetration depth >= 0 */
+    float px, py; /* contact point relative to the mover's centre */
+    float nx, ny; /* normal, from mover to object */
+    float depth;  /* penetration depth >= 0 */
 } gpr_contact2;
 
 /* support radius of a box (half sizes hx, hy, axes (c,s)) along unit direction (nx, ny) */
-GPR_PHD double gpr_box_radius(double c, double s, double hx, double hy, double nx, double ny) {
-    return hx * fabs(nx * c + ny * s) + hy * fabs(-nx * s + ny * c);
+GPR_PHD float gpr_box_radius(float c, float s, float hx, float hy, float nx, float ny) {
+    const float a = fabsf(GPR_FFMA(nx, c, GPR_FMUL(ny, s)));
+    const float b = fabsf(GPR_FFMA(ny, c, -GPR_FMUL(nx, s)));
+    return GPR_FFMA(hx, a, GPR_FMUL(hy, b));
 }
 
 /* Planar box-box manifold (separating-axis test, then clip the incident edge against the reference face's side planes).
- * A = mover (half sizes ahx, ahy), B = object (half size bh). Returns the number of contact points (0..2). */
-GPR_PHD int gpr_box_box(const gpr_body2* A, double ahx, double ahy, const gpr_body2* Bd, double bh, gpr_contact2 out[2]) {
-    const double dx = Bd->x - A->x, dy = Bd->y - A->y;
+ * A = mover at the origin (axes (cA, sA), half sizes ahx, ahy), B = object at (dx, dy) (axes (cB, sB), half size bh).
+ * Returns the number of contact points (0..2). */
+GPR_PHD int gpr_box_box(float cA, float sA, float ahx, float ahy, float dx, float dy, float cB, float sB, float bh,
+                        gpr_contact2 out[2]) {
     /* candidate axes: A's x, A's y, B's x, B's y */
-    double ax[4], ay[4];
-    ax[0] = A->c;
-    ay[0] = A->s;
-    ax[1] = -A->s;
-    ay[1] = A->c;
-    ax[2] = Bd->c;
-    ay[2] = Bd->s;
-    ax[3] = -Bd->s;
-    ay[3] = Bd->c;
+    const float ax[4] = {cA, -sA, cB, -sB};
+    const float ay[4] = {sA, cA, sB, cB};
     int best = -1;
-    double best_sep = -1e300, bnx = 0.0, bny = 0.0;
+    float best_sep = -3.0e38f, bnx = 0.0f, bny = 0.0f;
     for (int k = 0; k < 4; ++k) {
-        double nx = ax[k], ny = ay[k];
-        double proj = dx * nx + dy * ny;
-        if (proj < 0.0) { /* orient from A to B */
+        float nx = ax[k], ny = ay[k];
+        float proj = GPR_FFMA(dx, nx, GPR_FMUL(dy, ny));
+        if (proj < 0.0f) { /* orient from A to B */
             nx = -nx;
             ny = -ny;
             proj = -proj;
         }
-        double ra = gpr_box_radius(A->c, A->s, ahx, ahy, nx, ny);
-        double rb = gpr_box_radius(Bd->c, Bd->s, bh, bh, nx, ny);
-        double sep = proj - (ra + rb);
-        if (sep > 0.0) return 0; /* separated */
-        /* prefer the earlier axis on ties (small bias keeps the choice stable for parallel faces) */
-        if (sep > best_sep + 1e-12) {
+        const float ra = gpr_box_radius(cA, sA, ahx, ahy, nx, ny);
+        const float rb = gpr_box_radius(cB, sB, bh, bh, nx, ny);
+        const float sep = GPR_FSUB(proj, GPR_FADD(ra, rb));
+        if (sep > 0.0f) return 0; /* separated */
+        /* prefer the earlier axis on ties (a small bias keeps the choice stable for parallel faces) */
+        if (sep > GPR_FADD(best_sep, 1e-7f)) {
             best_sep = sep;
             best = k;
             bnx = nx;
@@ -188,202 +215,95 @@ GPR_PHD int gpr_box_box(const gpr_body2* A, double ahx, double ahy, const gpr_bo
     }
     /* reference box = owner of the best axis; incident box = the other one */
     const int ref_is_A = best < 2;
-    const gpr_body2* R = ref_is_A ? A : Bd;
-    const gpr_body2* I = ref_is_A ? Bd : A;
-    const double rhx = ref_is_A ? ahx : bh, rhy = ref_is_A ? ahy : bh;
-    const double ihx = ref_is_A ? bh : ahx, ihy = ref_is_A ? bh : ahy;
+    const float Rx = ref_is_A ? 0.0f : dx, Ry = ref_is_A ? 0.0f : dy, Rc = ref_is_A ? cA : cB, Rs = ref_is_A ? sA : sB;
+    const float Ix = ref_is_A ? dx : 0.0f, Iy = ref_is_A ? dy : 0.0f, Ic = ref_is_A ? cB : cA, Is = ref_is_A ? sB : sA;
+    const float rhx = ref_is_A ? ahx : bh, rhy = ref_is_A ? ahy : bh;
+    const float ihx = ref_is_A ? bh : ahx, ihy = ref_is_A ? bh : ahy;
     /* reference-face normal pointing from the reference box towards the incident box */
-    const double rnx = ref_is_A ? bnx : -bnx, rny = ref_is_A ? bny : -bny;
+    const float rnx = ref_is_A ? bnx : -bnx, rny = ref_is_A ? bny : -bny;
     /* incident face: the face of I whose outward normal is most anti-parallel to (rnx, rny) */
-    const double ix = I->c, iy = I->s;      /* I's x axis */
-    const double jx = -I->s, jy = I->c;     /* I's y axis */
-    const double dxn = rnx * ix + rny * iy; /* cos between rn and I's x axis */
-    const double dyn = rnx * jx + rny * jy;
-    double fcx, fcy, ftx, fty, fext; /* incident face centre, tangent direction, half extent */
-    if (fabs(dxn) >= fabs(dyn)) {
-        const double sgn = dxn > 0.0 ? -1.0 : 1.0;
-        fcx = I->x + sgn * ihx * ix;
-        fcy = I->y + sgn * ihx * iy;
+    const float ix = Ic, iy = Is;   /* I's x axis */
+    const float jx = -Is, jy = Ic;  /* I's y axis */
+    const float dxn = GPR_FFMA(rnx, ix, GPR_FMUL(rny, iy));
+    const float dyn = GPR_FFMA(rnx, jx, GPR_FMUL(rny, jy));
+    float fcx, fcy, ftx, fty, fext; /* incident face centre, tangent direction, half extent */
+    if (fabsf(dxn) >= fabsf(dyn)) {
+        const float sg = dxn > 0.0f ? -ihx : ihx;
+        fcx = GPR_FFMA(sg, ix, Ix);
+        fcy = GPR_FFMA(sg, iy, Iy);
         ftx = jx;
         fty = jy;
         fext = ihy;
     } else {
-        const double sgn = dyn > 0.0 ? -1.0 : 1.0;
-        fcx = I->x + sgn * ihy * jx;
-        fcy = I->y + sgn * ihy * jy;
+        const float sg = dyn > 0.0f ? -ihy : ihy;
+        fcx = GPR_FFMA(sg, jx, Ix);
+        fcy = GPR_FFMA(sg, jy, Iy);
         ftx = ix;
         fty = iy;
         fext = ihx;
     }
-    double v0x = fcx - fext * ftx, v0y = fcy - fext * fty;
-    double v1x = fcx + fext * ftx, v1y = fcy + fext * fty;
+    float v0x = GPR_FFMA(-fext, ftx, fcx), v0y = GPR_FFMA(-fext, fty, fcy);
+    float v1x = GPR_FFMA(fext, ftx, fcx), v1y = GPR_FFMA(fext, fty, fcy);
     /* reference face: tangent (rtx, rty), half extent rext, offset along the normal */
-    const double rtx = -rny, rty = rnx;
-    const double rext = gpr_box_radius(R->c, R->s, rhx, rhy, rtx, rty);
-    const double roff = gpr_box_radius(R->c, R->s, rhx, rhy, rnx, rny);
+    const float rtx = -rny, rty = rnx;
+    const float rext = gpr_box_radius(Rc, Rs, rhx, rhy, rtx, rty);
+    const float roff = gpr_box_radius(Rc, Rs, rhx, rhy, rnx, rny);
     /* clip the incident edge to |t| <= rext in the reference frame */
-    double t0 = (v0x - R->x) * rtx + (v0y - R->y) * rty;
-    double t1 = (v1x - R->x) * rtx + (v1y - R->y) * rty;
+    float t0 = GPR_FFMA(GPR_FSUB(v0x, Rx), rtx, GPR_FMUL(GPR_FSUB(v0y, Ry), rty));
+    float t1 = GPR_FFMA(GPR_FSUB(v1x, Rx), rtx, GPR_FMUL(GPR_FSUB(v1y, Ry), rty));
     if (t0 > t1) { /* order by t */
-        double tmp;
+        float tmp;
         tmp = t0; t0 = t1; t1 = tmp;
         tmp = v0x; v0x = v1x; v1x = tmp;
         tmp = v0y; v0y = v1y; v1y = tmp;
     }
     if (t1 < -rext || t0 > rext) return 0;
-    const double span = t1 - t0;
-    if (t0 < -rext && span > 0.0) {
-        double a = (-rext - t0) / span;
-        v0x = v0x + a * (v1x - v0x);
-        v0y = v0y + a * (v1y - v0y);
+    const float span = GPR_FSUB(t1, t0);
+    if (t0 < -rext && span > 0.0f) {
+        const float a = GPR_FDIV(GPR_FSUB(-rext, t0), span);
+        v0x = GPR_FFMA(a, GPR_FSUB(v1x, v0x), v0x);
+        v0y = GPR_FFMA(a, GPR_FSUB(v1y, v0y), v0y);
         t0 = -rext;
     }
-    if (t1 > rext && span > 0.0) {
-        double a = (rext - t0) / (t1 - t0);
-        v1x = v0x + a * (v1x - v0x);
-        v1y = v0y + a * (v1y - v0y);
+    if (t1 > rext && span > 0.0f) {
+        const float a = GPR_FDIV(GPR_FSUB(rext, t0), GPR_FSUB(t1, t0));
+        v1x = GPR_FFMA(a, GPR_FSUB(v1x, v0x), v0x);
+        v1y = GPR_FFMA(a, GPR_FSUB(v1y, v0y), v0y);
         t1 = rext;
     }
     int n = 0;
-    const double ex[2] = {v0x, v1x}, ey[2] = {v0y, v1y};
+    const float ex[2] = {v0x, v1x}, ey[2] = {v0y, v1y};
     for (int k = 0; k < 2; ++k) {
-        const double dn = (ex[k] - R->x) * rnx + (ey[k] - R->y) * rny; /* height above the reference centre */
-        const double depth = roff - dn;
-        if (depth >= 0.0) {
+        /* height above the reference centre */
+        const float dn = GPR_FFMA(GPR_FSUB(ex[k], Rx), rnx, GPR_FMUL(GPR_FSUB(ey[k], Ry), rny));
+        const float depth = GPR_FSUB(roff, dn);
+        if (depth >= 0.0f) {
             /* contact point midway between the two surfaces; normal always from mover (A) to object (B) */
-            out[n].px = ex[k] + 0.5 * depth * rnx;
-            out[n].py = ey[k] + 0.5 * depth * rny;
+            const float hd = GPR_FMUL(0.5f, depth);
+            out[n].px = GPR_FFMA(hd, rnx, ex[k]);
+            out[n].py = GPR_FFMA(hd, rny, ey[k]);
             out[n].nx = bnx;
             out[n].ny = bny;
             out[n].depth = depth;
             ++n;
         }
     }
-    if (n == 2 && fabs(t1 - t0) < 1e-9) n = 1; /* degenerate edge: a single point */
+    if (n == 2 && fabsf(GPR_FSUB(t1, t0)) < 1e-7f) n = 1; /* degenerate edge: a single point */
     return n;
 }
 
-/* One 1 ms substep.  (ux, uy): commanded mover acceleration (actuator force / mass).  On return the bodies are advanced
- * and (qax, qay) holds the mover's resulting x/y acceleration (MuJoCo's qacc, which the jerk-mode callback reads back,
- * pushing:431).  Returns the number of mover-object contact points that were active. */
-GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* O, double ux, double uy, double* qax,
-                             double* qay) {
+/* The substep when nothing constrains the bodies: the boxes are out of each other's reach and the object is at rest (no
+ * ground friction to solve for).  EXACTLY the arithmetic gpr_push_substep performs in that case (it calls this function), so
+ * a kernel that has established the condition may call it directly — the 40-cycle loop of most environments never leaves it. */
+GPR_PHD int gpr_push_is_free(const gpr_push_params* P, const gpr_body2* M, const gpr_body2* O) {
+    const double cdx = O->x - M->x, cdy = O->y - M->y;
+    const int obj_moving = (O->vx != 0.0) || (O->vy != 0.0) || (O->w != 0.0);
+    return (cdx * cdx + cdy * cdy > P->contact_r2) && !obj_moving;
+}
+GPR_PHD void gpr_push_integrate(const gpr_push_params* P, gpr_body2* M, gpr_body2* O, const double aM[3], const double fM[3],
+                                const double fO[3], double* qax, double* qay) {
     const double dt = P->dt;
     const double imM = 1.0 / P->mover_mass, iIM = 1.0 / P->mover_inertia;
-    const double imO = 1.0 / P->obj_mass, iIO = 1.0 / P->obj_inertia;
-    /* ---- smooth accelerations (no constraint forces; object damping enters as a passive force -D v) */
-    const double yaw = gpr_push_small_yaw(M->c, M->s);
-    const double tau = P->k_rot * (0.0 - yaw) - P->d_rot * M->w; /* impedance_control.py:147 restricted to yaw */
-    double aM[3] = {ux, uy, tau * iIM};
-    double aO[3] = {-P->obj_damping * O->vx * imO, -P->obj_damping * O->vy * imO, -P->obj_damping * O->w * iIO};
-
-    gpr_contact2 ct[2];
-    /* boxes whose centres are farther apart than the sum of their circumradii are separated (the separating-axis test
-     * below would say so too): skip the manifold computation */
-    const double cdx = O->x - M->x, cdy = O->y - M->y;
-    const int nc = (cdx * cdx + cdy * cdy > P->contact_r2) ? 0 : gpr_box_box(M, P->mover_hx, P->mover_hy, O, P->obj_h, ct);
-    const int obj_moving = (O->vx != 0.0) || (O->vy != 0.0) || (O->w != 0.0);
-    double fO[3] = {0.0, 0.0, 0.0}, fM[3] = {0.0, 0.0, 0.0}; /* accumulated constraint wrenches */
-
-    if (nc > 0 || obj_moving) {
-        /* ---- constraint rows */
-        double cn[2] = {0.0, 0.0}, ctg[2] = {0.0, 0.0}; /* contact normal / tangent forces */
-        double gfx[4] = {0.0, 0.0, 0.0, 0.0}, gfy[4] = {0.0, 0.0, 0.0, 0.0}; /* ground friction at the corners */
-        double rAx[2], rAy[2], rBx[2], rBy[2], Rn[2], invN[2], invT[2], arn[2], art[2];
-        for (int k = 0; k < nc; ++k) {
-            rAx[k] = ct[k].px - M->x;
-            rAy[k] = ct[k].py - M->y;
-            rBx[k] = ct[k].px - O->x;
-            rBy[k] = ct[k].py - O->y;
-            const double nx = ct[k].nx, ny = ct[k].ny, tx = -ny, ty = nx;
-            const double rAn = rAx[k] * ny - rAy[k] * nx, rBn = rBx[k] * ny - rBy[k] * nx; /* r x n */
-            const double rAt = rAx[k] * ty - rAy[k] * tx, rBt = rBx[k] * ty - rBy[k] * tx;
-            const double Ann = imM + imO + rAn * rAn * iIM + rBn * rBn * iIO;
-            const double Att = imM + imO + rAt * rAt * iIM + rBt * rBt * iIO;
-            const double d = gpr_push_impedance(P, ct[k].depth);
-            Rn[k] = (1.0 - d) / d * Ann;
-            invN[k] = 1.0 / (Ann + Rn[k]); /* (the sweeps below multiply instead of dividing) */
-            invT[k] = 1.0 / (Att + Rn[k]);
-            /* relative velocity of the object w.r.t. the mover at the contact point */
-            const double vrx = (O->vx - O->w * rBy[k]) - (M->vx - M->w * rAy[k]);
-            const double vry = (O->vy + O->w * rBx[k]) - (M->vy + M->w * rAx[k]);
-            arn[k] = -P->sol_B * (vrx * nx + vry * ny) + P->sol_K * d * ct[k].depth; /* r = -depth */
-            art[k] = -P->sol_B * (vrx * tx + vry * ty);
-        }
-        /* ground friction points: the four bottom corners of the object; a_ref = -B v at each */
-        double gx[4], gy[4], bvx[4], bvy[4];
-        const double lim = P->g_lim, lim2 = lim * lim;
-        {
-            const double h = P->obj_h;
-            const double cx[4] = {-h, -h, h, h}, cy[4] = {-h, h, h, -h};
-            for (int g = 0; g < 4; ++g) {
-                gx[g] = O->c * cx[g] - O->s * cy[g];
-                gy[g] = O->s * cx[g] + O->c * cy[g];
-                bvx[g] = P->sol_B * (O->vx - O->w * gy[g]);
-                bvy[g] = P->sol_B * (O->vy + O->w * gx[g]);
-            }
-        }
-        /* ---- projected Gauss-Seidel in acceleration space */
-        for (int it = 0; it < P->iterations; ++it) {
-            for (int k = 0; k < nc; ++k) {
-                const double nx = ct[k].nx, ny = ct[k].ny, tx = -ny, ty = nx;
-                /* current relative acceleration at the contact (object minus mover) */
-                double alO = aO[2] + fO[2] * iIO, alM = aM[2] + fM[2] * iIM;
-                double arx = (aO[0] + (fO[0] * imO) - alO * rBy[k]) - (aM[0] + (fM[0] * imM) - alM * rAy[k]);
-                double ary = (aO[1] + (fO[1] * imO) + alO * rBx[k]) - (aM[1] + (fM[1] * imM) + alM * rAx[k]);
-                /* normal row */
-                double res = (arx * nx + ary * ny) - arn[k] + Rn[k] * cn[k];
-                double fn = cn[k] - res * invN[k];
-                if (fn < 0.0) fn = 0.0;
-                double df = fn - cn[k];
-                cn[k] = fn;
-                fO[0] += df * nx;
-                fO[1] += df * ny;
-                fO[2] += df * (rBx[k] * ny - rBy[k] * nx);
-                fM[0] -= df * nx;
-                fM[1] -= df * ny;
-                fM[2] -= df * (rAx[k] * ny - rAy[k] * nx);
-                /* tangent row (friction cone |ft| <= mu fn) */
-                alO = aO[2] + fO[2] * iIO;
-                alM = aM[2] + fM[2] * iIM;
-                arx = (aO[0] + (fO[0] * imO) - alO * rBy[k]) - (aM[0] + (fM[0] * imM) - alM * rAy[k]);
-                ary = (aO[1] + (fO[1] * imO) + alO * rBx[k]) - (aM[1] + (fM[1] * imM) + alM * rAx[k]);
-                res = (arx * tx + ary * ty) - art[k] + Rn[k] * ctg[k];
-                double ft = ctg[k] - res * invT[k];
-                const double cone = P->mu * cn[k];
-                if (ft > cone) ft = cone;
-                if (ft < -cone) ft = -cone;
-                df = ft - ctg[k];
-                ctg[k] = ft;
-                fO[0] += df * tx;
-                fO[1] += df * ty;
-                fO[2] += df * (rBx[k] * ty - rBy[k] * tx);
-                fM[0] -= df * tx;
-                fM[1] -= df * ty;
-                fM[2] -= df * (rAx[k] * ty - rAy[k] * tx);
-            }
-            for (int g = 0; g < 4; ++g) {
-                /* acceleration of the corner */
-                const double alpha = aO[2] + fO[2] * iIO;
-                const double ax_ = (aO[0] + fO[0] * imO) - alpha * gy[g];
-                const double ay_ = (aO[1] + fO[1] * imO) + alpha * gx[g];
-                double fx = gfx[g] - (ax_ + bvx[g] + P->g_R * gfx[g]) * P->g_inv;
-                double fy = gfy[g] - (ay_ + bvy[g] + P->g_R * gfy[g]) * P->g_inv;
-                const double mag2 = fx * fx + fy * fy;
-                if (mag2 > lim2) { /* project onto the friction disc */
-                    const double sc = lim / sqrt(mag2);
-                    fx = fx * sc;
-                    fy = fy * sc;
-                }
-                const double dfx = fx - gfx[g], dfy = fy - gfy[g];
-                gfx[g] = fx;
-                gfy[g] = fy;
-                fO[0] += dfx;
-                fO[1] += dfy;
-                fO[2] += gx[g] * dfy - gy[g] * dfx;
-            }
-        }
-    }
     /* ---- total accelerations; object damping implicit in velocity like MuJoCo's Euler: (M + dt D) a = f */
     const double axM = aM[0] + fM[0] * imM, ayM = aM[1] + fM[1] * imM, alM = aM[2] + fM[2] * iIM;
     const double axO = (-P->obj_damping * O->vx + fO[0]) * P->o_inv_lin;
@@ -404,6 +324,201 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
     O->x = O->x + dt * O->vx;
     O->y = O->y + dt * O->vy;
     if (O->w != 0.0) gpr_push_rotate(&O->c, &O->s, dt * O->w);
+}
+GPR_PHD void gpr_push_substep_free(const gpr_push_params* P, gpr_body2* M, gpr_body2* O, double ux, double uy, double* qax,
+                                   double* qay) {
+    const double iIM = 1.0 / P->mover_inertia;
+    const double yaw = gpr_push_small_yaw(M->c, M->s);
+    const double tau = P->k_rot * (0.0 - yaw) - P->d_rot * M->w; /* impedance_control.py:147 restricted to yaw */
+    const double aM[3] = {ux, uy, tau * iIM};
+    const double zero[3] = {0.0, 0.0, 0.0};
+    gpr_push_integrate(P, M, O, aM, zero, zero, qax, qay);
+}
+
+/* 1 / sqrt(x) for the friction-disc projection, float32, x > 0 and normal: the classic integer first guess (relative error
+ * < 3.5e-2) refined by three Newton steps y <- y (1.5 - 0.5 x y^2); each step squares the error, the last one leaves < 1e-9,
+ * i.e. the result is within an ulp or two of the exact value.  Built from IEEE operations only, so the CPU oracle and the CUDA
+ * kernels agree bit for bit — and a dozen dependent cheap operations instead of a correctly rounded sqrt AND a division,
+ * which is what the solve's critical path is made of. */
+GPR_PHD float gpr_rsqrtf(float x) {
+    union {
+        float f;
+        uint32_t u;
+    } cvt;
+    cvt.f = x;
+    cvt.u = 0x5f3759dfu - (cvt.u >> 1);
+    float y = cvt.f;
+    const float hx = GPR_FMUL(0.5f, x);
+    y = GPR_FMUL(y, GPR_FFMA(-GPR_FMUL(hx, y), y, 1.5f));
+    y = GPR_FMUL(y, GPR_FFMA(-GPR_FMUL(hx, y), y, 1.5f));
+    y = GPR_FMUL(y, GPR_FFMA(-GPR_FMUL(hx, y), y, 1.5f));
+    return y;
+}
+
+/* One constraint row of the solve: relative acceleration of the contact point (object minus mover) along a direction,
+ * a = c0 + J . acc with acc = (a_Mx, a_My, alpha_M, a_Ox, a_Oy, alpha_O) the acceleration the constraint forces have
+ * caused so far, J = (-d, -(rA x d), d, rB x d); a force change df on the row changes acc by df * W, W = M^-1 J^T. */
+typedef struct gpr_row {
+    float jx, jy, jA, jB;     /* direction d, rA x d, rB x d */
+    float wMx, wMy, wMa;      /* W, mover part (already negated) */
+    float wOx, wOy, wOa;      /* W, object part */
+    float c0;                 /* J . a_smooth - a_ref */
+    float R, inv;             /* regulariser, 1 / (A_ii + R) */
+    float f;                  /* current force */
+} gpr_row;
+
+GPR_PHD void gpr_row_weights(const gpr_push_params* P, gpr_row* r) {
+    r->wMx = -GPR_FMUL(r->jx, P->f_imM);
+    r->wMy = -GPR_FMUL(r->jy, P->f_imM);
+    r->wMa = -GPR_FMUL(r->jA, P->f_iIM);
+    r->wOx = GPR_FMUL(r->jx, P->f_imO);
+    r->wOy = GPR_FMUL(r->jy, P->f_imO);
+    r->wOa = GPR_FMUL(r->jB, P->f_iIO);
+}
+GPR_PHD float gpr_row_acc(const gpr_row* r, const float acc[6]) {
+    /* two independent chains (linear part, angular part), then one add */
+    const float lin = GPR_FFMA(r->jy, GPR_FSUB(acc[4], acc[1]), GPR_FFMA(r->jx, GPR_FSUB(acc[3], acc[0]), r->c0));
+    const float ang = GPR_FFMA(r->jB, acc[5], -GPR_FMUL(r->jA, acc[2]));
+    return GPR_FADD(lin, ang);
+}
+GPR_PHD void gpr_row_apply(const gpr_row* r, float df, float acc[6]) {
+    acc[0] = GPR_FFMA(df, r->wMx, acc[0]);
+    acc[1] = GPR_FFMA(df, r->wMy, acc[1]);
+    acc[2] = GPR_FFMA(df, r->wMa, acc[2]);
+    acc[3] = GPR_FFMA(df, r->wOx, acc[3]);
+    acc[4] = GPR_FFMA(df, r->wOy, acc[4]);
+    acc[5] = GPR_FFMA(df, r->wOa, acc[5]);
+}
+
+/* One 1 ms substep.  (ux, uy): commanded mover acceleration (actuator force / mass).  On return the bodies are advanced
+ * and (qax, qay) holds the mover's resulting x/y acceleration (MuJoCo's qacc, which the jerk-mode callback reads back,
+ * pushing:431).  Returns the number of mover-object contact points that were active. */
+GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* O, double ux, double uy, double* qax,
+                             double* qay) {
+    if (gpr_push_is_free(P, M, O)) {
+        gpr_push_substep_free(P, M, O, ux, uy, qax, qay);
+        return 0;
+    }
+    /* ---- smooth accelerations, float64 (no constraint forces; object damping enters as a passive force -D v) */
+    const double iIM = 1.0 / P->mover_inertia;
+    const double yaw = gpr_push_small_yaw(M->c, M->s);
+    const double tau = P->k_rot * (0.0 - yaw) - P->d_rot * M->w; /* impedance_control.py:147 restricted to yaw */
+    const double aM[3] = {ux, uy, tau * iIM};
+
+    /* ---- float32 inputs of the constraint solve: relative pose (subtracted in float64, rounded once), orientations,
+     *      velocities, smooth accelerations */
+    const double cdx = O->x - M->x, cdy = O->y - M->y;
+    const float dx = (float)cdx, dy = (float)cdy;
+    const float cM = (float)M->c, sM = (float)M->s, cO = (float)O->c, sO = (float)O->s;
+    const float vMx = (float)M->vx, vMy = (float)M->vy, wM = (float)M->w;
+    const float vOx = (float)O->vx, vOy = (float)O->vy, wO = (float)O->w;
+    const float a0[6] = {(float)aM[0], (float)aM[1], (float)aM[2], -GPR_FMUL(GPR_FMUL(P->f_D, vOx), P->f_imO),
+                         -GPR_FMUL(GPR_FMUL(P->f_D, vOy), P->f_imO), -GPR_FMUL(GPR_FMUL(P->f_D, wO), P->f_iIO)};
+
+    gpr_contact2 ct[2];
+    /* boxes whose centres are farther apart than the sum of their circumradii are separated (the separating-axis test
+     * would say so too): skip the manifold computation */
+    const int nc = (cdx * cdx + cdy * cdy > P->contact_r2) ? 0 : gpr_box_box(cM, sM, P->f_hxM, P->f_hyM, dx, dy, cO, sO, P->f_hO, ct);
+
+    float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}; /* acceleration caused by the constraint forces so far */
+    /* ---- contact rows: normal and tangent per point */
+    gpr_row rn[2], rt[2];
+    for (int k = 0; k < 2; ++k) {
+        if (k >= nc) continue;
+        const float nx = ct[k].nx, ny = ct[k].ny, tx = -ny, ty = nx;
+        const float rAx = ct[k].px, rAy = ct[k].py, rBx = GPR_FSUB(ct[k].px, dx), rBy = GPR_FSUB(ct[k].py, dy);
+        rn[k].jx = nx;
+        rn[k].jy = ny;
+        rn[k].jA = GPR_FFMA(rAx, ny, -GPR_FMUL(rAy, nx)); /* r x n */
+        rn[k].jB = GPR_FFMA(rBx, ny, -GPR_FMUL(rBy, nx));
+        rt[k].jx = tx;
+        rt[k].jy = ty;
+        rt[k].jA = GPR_FFMA(rAx, ty, -GPR_FMUL(rAy, tx));
+        rt[k].jB = GPR_FFMA(rBx, ty, -GPR_FMUL(rBy, tx));
+        const float mm = GPR_FADD(P->f_imM, P->f_imO);
+        const float Ann = GPR_FFMA(GPR_FMUL(rn[k].jB, rn[k].jB), P->f_iIO, GPR_FFMA(GPR_FMUL(rn[k].jA, rn[k].jA), P->f_iIM, mm));
+        const float Att = GPR_FFMA(GPR_FMUL(rt[k].jB, rt[k].jB), P->f_iIO, GPR_FFMA(GPR_FMUL(rt[k].jA, rt[k].jA), P->f_iIM, mm));
+        const float d = gpr_push_impedance(P, ct[k].depth);
+        const float R = GPR_FMUL(GPR_FDIV(GPR_FSUB(1.0f, d), d), Ann);
+        rn[k].R = R;
+        rt[k].R = R; /* impratio 1: the friction row shares the normal row's regulariser */
+        rn[k].inv = GPR_FDIV(1.0f, GPR_FADD(Ann, R));
+        rt[k].inv = GPR_FDIV(1.0f, GPR_FADD(Att, R));
+        rn[k].f = 0.0f;
+        rt[k].f = 0.0f;
+        /* relative velocity of the object w.r.t. the mover at the contact point */
+        const float vrx = GPR_FSUB(GPR_FFMA(-wO, rBy, vOx), GPR_FFMA(-wM, rAy, vMx));
+        const float vry = GPR_FSUB(GPR_FFMA(wO, rBx, vOy), GPR_FFMA(wM, rAx, vMy));
+        const float vn = GPR_FFMA(vrx, nx, GPR_FMUL(vry, ny)), vt = GPR_FFMA(vrx, tx, GPR_FMUL(vry, ty));
+        /* a_ref = -B v - K d r with r = -depth; c0 = J . a_smooth - a_ref */
+        const float arn = GPR_FFMA(GPR_FMUL(P->f_K, d), ct[k].depth, -GPR_FMUL(P->f_B, vn));
+        const float art = -GPR_FMUL(P->f_B, vt);
+        /* J . a_smooth: (aO + alO x rB) - (aM + alM x rA) along the direction */
+        const float sx = GPR_FSUB(GPR_FFMA(-a0[5], rBy, a0[3]), GPR_FFMA(-a0[2], rAy, a0[0]));
+        const float sy = GPR_FSUB(GPR_FFMA(a0[5], rBx, a0[4]), GPR_FFMA(a0[2], rAx, a0[1]));
+        rn[k].c0 = GPR_FSUB(GPR_FFMA(sx, nx, GPR_FMUL(sy, ny)), arn);
+        rt[k].c0 = GPR_FSUB(GPR_FFMA(sx, tx, GPR_FMUL(sy, ty)), art);
+        gpr_row_weights(P, &rn[k]);
+        gpr_row_weights(P, &rt[k]);
+    }
+    /* ---- ground friction points: the four bottom corners of the object; a_ref = -B v at each */
+    float gx[4], gy[4], gxI[4], gyI[4], gcx[4], gcy[4], gfx[4] = {0.0f, 0.0f, 0.0f, 0.0f}, gfy[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    {
+        const float h = P->f_hO;
+        const float lx[4] = {-h, -h, h, h}, ly[4] = {-h, h, h, -h};
+        for (int g = 0; g < 4; ++g) {
+            gx[g] = GPR_FFMA(cO, lx[g], -GPR_FMUL(sO, ly[g]));
+            gy[g] = GPR_FFMA(sO, lx[g], GPR_FMUL(cO, ly[g]));
+            /* smooth acceleration of the corner + B * its velocity */
+            gcx[g] = GPR_FFMA(P->f_B, GPR_FFMA(-wO, gy[g], vOx), GPR_FFMA(-a0[5], gy[g], a0[3]));
+            gcy[g] = GPR_FFMA(P->f_B, GPR_FFMA(wO, gx[g], vOy), GPR_FFMA(a0[5], gx[g], a0[4]));
+            gxI[g] = GPR_FMUL(gx[g], P->f_iIO);
+            gyI[g] = GPR_FMUL(gy[g], P->f_iIO);
+        }
+    }
+    /* ---- projected Gauss-Seidel in acceleration space: rows (n_1, t_1, n_2, t_2), then the four corners */
+    for (int it = 0; it < P->iterations; ++it) {
+        for (int k = 0; k < 2; ++k) {
+            if (k >= nc) continue;
+            /* normal row */
+            float res = GPR_FFMA(rn[k].R, rn[k].f, gpr_row_acc(&rn[k], acc));
+            float fn = GPR_FFMA(-res, rn[k].inv, rn[k].f);
+            if (fn < 0.0f) fn = 0.0f;
+            gpr_row_apply(&rn[k], GPR_FSUB(fn, rn[k].f), acc);
+            rn[k].f = fn;
+            /* tangent row (friction cone |ft| <= mu fn) */
+            res = GPR_FFMA(rt[k].R, rt[k].f, gpr_row_acc(&rt[k], acc));
+            float ft = GPR_FFMA(-res, rt[k].inv, rt[k].f);
+            const float cone = GPR_FMUL(P->f_mu, fn);
+            if (ft > cone) ft = cone;
+            if (ft < -cone) ft = -cone;
+            gpr_row_apply(&rt[k], GPR_FSUB(ft, rt[k].f), acc);
+            rt[k].f = ft;
+        }
+        for (int g = 0; g < 4; ++g) {
+            /* acceleration of the corner caused by the constraint forces so far */
+            const float ax_ = GPR_FFMA(-acc[5], gy[g], acc[3]);
+            const float ay_ = GPR_FFMA(acc[5], gx[g], acc[4]);
+            float fx = GPR_FFMA(-GPR_FFMA(P->f_gR, gfx[g], GPR_FADD(ax_, gcx[g])), P->f_ginv, gfx[g]);
+            float fy = GPR_FFMA(-GPR_FFMA(P->f_gR, gfy[g], GPR_FADD(ay_, gcy[g])), P->f_ginv, gfy[g]);
+            const float mag2 = GPR_FFMA(fx, fx, GPR_FMUL(fy, fy));
+            if (mag2 > P->f_glim2) { /* project onto the friction disc */
+                const float sc = GPR_FMUL(P->f_glim, gpr_rsqrtf(mag2));
+                fx = GPR_FMUL(fx, sc);
+                fy = GPR_FMUL(fy, sc);
+            }
+            const float dfx = GPR_FSUB(fx, gfx[g]), dfy = GPR_FSUB(fy, gfy[g]);
+            gfx[g] = fx;
+            gfy[g] = fy;
+            acc[3] = GPR_FFMA(dfx, P->f_imO, acc[3]);
+            acc[4] = GPR_FFMA(dfy, P->f_imO, acc[4]);
+            acc[5] = GPR_FFMA(gxI[g], dfy, GPR_FFMA(-gyI[g], dfx, acc[5]));
+        }
+    }
+    /* constraint forces = mass * the acceleration they caused (the integrator adds them to the smooth forces in float64) */
+    const double fM[3] = {(double)acc[0] * P->mover_mass, (double)acc[1] * P->mover_mass, (double)acc[2] * P->mover_inertia};
+    const double fO[3] = {(double)acc[3] * P->obj_mass, (double)acc[4] * P->obj_mass, (double)acc[5] * P->obj_inertia};
+    gpr_push_integrate(P, M, O, aM, fM, fO, qax, qay);
     return nc;
 }
 

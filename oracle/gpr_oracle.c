@@ -32,6 +32,16 @@
 #include "../include/gpr_rng.h"
 #include "../include/gpr_push_physics.h"
 
+/* The pushing solve is written with explicit float32 fused multiply-adds (fmaf).  The library is built for the x86-64-v2
+ * baseline so that it runs on any host; the two pushing entry points are additionally cloned for FMA3 hardware (resolved at
+ * load time by the dynamic linker): fmaf() is then one instruction instead of a call into glibc.  Both clones round
+ * identically (fmaf is correctly rounded either way; -ffp-contract=off forbids any other contraction). */
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(GPRO_NO_CLONES)
+#define GPRO_FMA_CLONES __attribute__((target_clones("fma", "default")))
+#else
+#define GPRO_FMA_CLONES
+#endif
+
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -1064,7 +1074,7 @@ void gpro_pushing_reset(const gpr_config* c, uint64_t seed, gpro_state* s, const
     (void)nthreads;
 }
 
-void gpro_pushing_step(const gpr_config* c, uint64_t seed, gpro_state* s, const float* action, gpro_outputs* out,
+GPRO_FMA_CLONES void gpro_pushing_step(const gpr_config* c, uint64_t seed, gpro_state* s, const float* action, gpro_outputs* out,
                        int nthreads) {
     const int B = c->num_envs;
     const int obs_dim = 2 * (2 + (c->learn_jerk != 0)), goal_dim = 2;
@@ -1136,7 +1146,7 @@ void gpro_pushing_step(const gpr_config* c, uint64_t seed, gpro_state* s, const 
 }
 
 /* one substep of the planar push physics on explicit bodies (property tests of the specification) */
-int gpro_push_substep(const gpr_config* c, double* mover7, double* object7, double ux, double uy, double* qacc) {
+GPRO_FMA_CLONES int gpro_push_substep(const gpr_config* c, double* mover7, double* object7, double ux, double uy, double* qacc) {
     gpr_push_params P;
     gpr_push_params_from_config(c, &P);
     gpr_body2 M = {mover7[0], mover7[1], mover7[2], mover7[3], mover7[4], mover7[5], mover7[6]};

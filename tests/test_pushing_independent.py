@@ -4,9 +4,12 @@
 show that the header implements the model it documents.  ``tests/push_model_numpy.py`` restates that model from MuJoCo's
 documentation in generalised coordinates with explicit Jacobians and shares no code with the header.  Stated tolerances:
 
-    * one substep from identical state, any contact configuration ........ relative 1e-9 on every state component
-      (measured: 1.2e-11 over 3000 random states; the only modelled difference is yaw = asin-series vs atan2)
-    * 600-substep push trajectory ......................................... absolute 1e-9 on poses and velocities
+    * one substep from identical state, any contact configuration: the same number of contact points, and the velocity
+      change of each body within float32-solver precision of the float64 model — median relative error < 1e-6, 99th
+      percentile < 1e-4, maximum < 5e-3 (measured over 3000 random states: 4e-8 / 3e-6 / 9e-4; with the float64 solve the
+      header used until round 2 the same comparison gave 1.2e-11, i.e. the two derivations are the same model; what remains
+      is the rounding of the float32 constraint solve)
+    * 600-substep push trajectory: poses within 1e-5 m / rad, velocities within 1e-4
     * solver truncation: 8 projected Gauss-Seidel sweeps (the shipped setting) against the converged solution (2000
       sweeps) of the same rows: median relative error of the object's velocity change 1e-5, 90th percentile < 2 %,
       maximum < 10 % (single substep, random penetrating states) — reported, and bounded here so a regression shows.
@@ -49,14 +52,20 @@ def test_single_substep_matches_the_independent_model(kw):
     P = pm.Params(iterations=int(cfg.contact_iterations), m_M=float(cfg.mover_mass), half_M=(cfg.mover_half[0], cfg.mover_half[1]))
     rng = np.random.default_rng(0)
     hist = [0, 0, 0]
+    rel = []
     for _ in range(600):
         M, O, u = _random_state(rng)
         a, b = _c_substep(cfg, M, O, u), pm.substep(P, M, O, u)
         assert a[3] == b[3]  # same number of contact points
         hist[a[3]] += 1
-        for x, y in zip(a[:3], b[:3]):
-            assert np.allclose(x, y, rtol=1e-9, atol=1e-12), (M, O, u)
+        for got, want, before in ((a[0], b[0], M), (a[1], b[1], O)):
+            dv_got, dv_want = (got - before)[4:7], (want - before)[4:7]
+            rel.append(np.abs(dv_got - dv_want).max() / (np.abs(dv_want).max() + 1e-9))
+            assert np.allclose(got[:4], want[:4], rtol=0, atol=1e-8)  # poses after one substep
+        assert np.allclose(a[2], b[2], rtol=1e-4, atol=1e-6)  # the mover's qacc
+    rel = np.array(rel)
     assert min(hist) > 60  # free, one-point and two-point manifolds all exercised
+    assert np.median(rel) < 1e-6 and np.percentile(rel, 99) < 1e-4 and rel.max() < 5e-3, (np.median(rel), np.percentile(rel, 99), rel.max())
 
 
 def test_push_trajectory_matches_the_independent_model():
@@ -70,10 +79,11 @@ def test_push_trajectory_matches_the_independent_model():
         u = np.array([4.0, 0.5]) if k < 300 else np.array([-4.0, 0.0])
         M, O, _, nc = pm.substep(P, M, O, u)
         M2, O2, _, nc2 = _c_substep(cfg, M2, O2, u)
-        assert nc == nc2
+        assert nc == nc2 or abs(k - 300) < 3
         touched += nc > 0
     assert touched > 50 and O[0] > 0.6  # the object really was pushed
-    assert np.abs(M - M2).max() < 1e-9 and np.abs(O - O2).max() < 1e-9
+    assert np.abs(M - M2)[:4].max() < 1e-5 and np.abs(O - O2)[:4].max() < 1e-5, (np.abs(M - M2), np.abs(O - O2))
+    assert np.abs(M - M2)[4:].max() < 1e-4 and np.abs(O - O2)[4:].max() < 1e-4
 
 
 def test_truncated_solver_is_close_to_the_converged_one():
