@@ -188,27 +188,47 @@ def time_oracle(wl, num_envs: int, steps: int, warmup: int, threads: int, seed: 
     return num_envs * steps / (time.perf_counter() - t0)
 
 
+def reference_numpy_share():
+    """The reference's UNMODIFIED NumPy share of one env-step, measured where its source is mounted
+    (the build container) by tools/reference_numpy_share.py and committed as profiles/reference_numpy_share.json: the
+    GPU box has no reference mount, so the bench line carries the committed measurement with its provenance."""
+    path = os.path.join(ROOT, 'profiles', 'reference_numpy_share.json')
+    if not os.path.exists(path):
+        return None
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def run_reference(args, wl):
     """Reference arm: the reference's CPU implementation of the path.  The real reference needs the MuJoCo wheel, which
-    cannot be installed offline, so this runs the oracle port with every host thread (kind 'port')."""
+    cannot be installed offline, so this runs the oracle port with every host thread (kind 'port') on the SAME config as
+    the B200 arm: the workload's full batch (65,536 envs for the headline), `--steps` steps of it."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
     threads = host_threads()
-    sample_envs = 4096  # bounded sample of the same workload: the per-env cost does not depend on the batch size
-    v = time_oracle(wl, sample_envs, args.steps, max(args.warmup, 1), threads)
-    cfg, d = make_cfg(wl, sample_envs)
+    B = args.num_envs or wl['num_envs']
+    v = time_oracle(wl, B, args.steps, max(args.warmup, 1), threads)
+    cfg, d = make_cfg(wl, B)
     line = {
         'impl': 'reference', 'metric': 'env-steps/s', 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': 1e3 * sample_envs / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * B / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': wl['desc'], 'env_id': wl['env_id'], 'num_cycles': int(cfg.num_cycles), 'std_noise': cfg.std_noise[0],
-                   'sample': f'{sample_envs} envs per step'},
+        'config': {'workload': wl['desc'], 'env_id': wl['env_id'], 'envs_per_gpu': B, 'num_cycles': int(cfg.num_cycles), 'std_noise': cfg.std_noise[0],
+                   'autoreset': 'same_step', 'sample': f'the full batch: {B} envs per step'},
         'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{sample_envs} envs x {args.steps} steps, OpenMP over envs; MuJoCo-backed reference not installable offline'},
+                         'sample': f'{B} envs x {args.steps} steps (the B200 arm\'s batch), OpenMP over envs; MuJoCo-backed reference not installable offline'},
         'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'reference_numpy_share': reference_numpy_share(),
     }
     print(json.dumps(line), flush=True)
+
+
+KERNEL_NAMES = {'planning': ('planning_step_kernel', 'autoreset', 'planning_autoreset_kernel'),
+                'pushing': ('pushing_step_kernel', 'contact', 'pushing_contact_kernel')}
 
 
 def run_b200(args, wl):
@@ -225,34 +245,41 @@ def run_b200(args, wl):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    B = args.num_envs or wl['num_envs']
     # one process per GPU: run on (and first-touch pinned memory from) the cores of the GPU's own NUMA node
     full_affinity = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
     numa_cpus = None if args.no_numa_bind else gpr.bind_to_gpu_numa(local)
-
-    def build(**over):
-        cls = gpr.BenchmarkPlanningVecEnv if wl['kind'] == 'planning' else gpr.BenchmarkPushingVecEnv
-        kw = dict(wl['kwargs'])
-        kw.update(over)
-        # weak scaling: B envs per GPU, global index base = rank * B (results independent of the split)
-        return cls(B, device=dev, env_index_base=rank * B, seed=args.seed, **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    peak, peak_src = measured_hbm_peak()
 
-    def timed(env, steps, warmup, per_kernel=False):
+    def build(w, B, **over):
+        cls = gpr.BenchmarkPlanningVecEnv if w['kind'] == 'planning' else gpr.BenchmarkPushingVecEnv
+        kw = dict(w['kwargs'])
+        kw.update(over)
+        # weak scaling: B envs per GPU, global index base = rank * B (results independent of the split)
+        return cls(B, device=dev, env_index_base=rank * B, seed=args.seed, **kw)
+
+    def timed(env, B, steps, warmup, per_kernel=False, reset=True):
         """Device time of `steps` steps: CUDA events around each gpr_step on the launching stream, L2 flushed in between.
         per_kernel: also record CUDA events around each kernel inside gpr_step (gpr_kernel_times).  An event between the
-        step kernel and the auto-reset kernel keeps the two from overlapping, so that pass is a separate one: it gives
-        the kernels' own launch durations (roofline), the plain pass gives the step time (value)."""
+        step kernel and the kernel that follows it keeps the two from overlapping, so that pass is a separate one: it
+        gives the kernels' own launch durations (roofline), the plain pass gives the step time (value)."""
         lim = env.j_max if env.learn_jerk else env.a_max
         acts = [(torch.rand((B, env.core.action_dim), device=dev, generator=gen) * 2 - 1) * lim for _ in range(8)]
-        env.reset(seed=args.seed)
+        if reset:
+            env.reset(seed=args.seed)
         for i in range(warmup):
             env.step(acts[i % 8])
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -271,16 +298,35 @@ def run_b200(args, wl):
         kt = env.core.kernel_times(False)
         return ms, env.core.launch_count - n0, wall, kt
 
-    env = build()
-    with ClockSampler(local) as clk:
-        ms, launches, wall, _ = timed(env, args.steps, args.warmup)
-        _, _, _, ktimes = timed(env, args.steps, 3, per_kernel=True)  # same steps again, each kernel timed alone
-    clocks = clk.summary()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * B * args.steps / (ms_max * 1e-3)
+    def measure(w, B, steps, warmup, repeats, clocks_into=None):
+        """The device-resident leg of one workload: best of `repeats` timed blocks of `steps` steps (every block: max over
+        ranks), then a per-kernel pass for the roofline of the dominant kernel."""
+        env = build(w, B)
+        blocks, launches, wall = [], 0, 0.0
+        ctx = ClockSampler(local)
+        with ctx:
+            for r in range(repeats):
+                ms, launches, wall, _ = timed(env, B, steps, warmup if r == 0 else 1, reset=(r == 0))
+                blocks.append(allmax(ms))
+            _, _, _, kt = timed(env, B, steps, 3, per_kernel=True, reset=False)  # same steps again, each kernel timed alone
+        best = min(blocks)
+        N, J = int(env.cfg.num_movers), int(env.cfg.learn_jerk)
+        abytes = algorithmic_bytes_per_env_step(w['kind'], N, J)
+        k_main, k_other_key, k_other = KERNEL_NAMES[w['kind']]
+        achieved = abytes * B / (kt['step_kernel_ms'] * 1e-3) / 1e9
+        res = {
+            'env': env, 'value': world * B * steps / (best * 1e-3), 'ms_per_step': best / steps, 'blocks_ms_per_step': [b / steps for b in blocks],
+            'launches': launches, 'wall': wall, 'clocks': ctx.summary(), 'abytes': abytes,
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_env_step': abytes, 'algorithmic_bytes_per_launch': abytes * B, 'kernel': k_main,
+                         'kernel_ms': kt['step_kernel_ms'], 'other_kernels_ms': {k_other_key: kt['autoreset_kernel_ms']},
+                         'whole_step_frac': abytes * B / (best / steps * 1e-3) / 1e9 / peak},
+        }
+        return res
+
+    B = args.num_envs or wl['num_envs']
+    m = measure(wl, B, args.steps, args.warmup, args.repeats)
+    env = m['env']
     stats = env.episode_stats(reset=True, all_reduce=world > 1)
     fails = env.core.reset_failures()
 
@@ -295,85 +341,108 @@ def run_b200(args, wl):
     for i in range(3):
         env.step_host(hacts[i % 4])
     e2e_steps = max(10, args.steps)  # (as many as the device-resident leg: a single host hiccup must not dominate)
-    barrier()
-    t0 = time.perf_counter()
-    acc = 0.0
+    e2e_blocks = []
+    d2h_written = 0
+    for r in range(args.repeats):
+        barrier()
+        t0 = time.perf_counter()
+        acc = 0.0
+        for i in range(e2e_steps):
+            out = env.step_host(hacts[i % 4])
+            acc += float(out[1][0])  # the host reads the step's result (reward of env 0) before issuing the next step
+        barrier()
+        e2e_blocks.append(allmax(time.perf_counter() - t0))
+    e2e_s = min(e2e_blocks)
+    env.core.kernel_times(True)  # device time of the same kernels when their I/O lives in pinned host memory (own pass)
+    done_rows = 0
     for i in range(e2e_steps):
         out = env.step_host(hacts[i % 4])
-        acc += float(out[1][0])  # the host reads the step's result (reward of env 0) before issuing the next step
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    env.core.kernel_times(True)  # device time of the same kernels when their I/O lives in pinned host memory (own pass)
-    for i in range(e2e_steps):
-        env.step_host(hacts[i % 4])
+        done_rows += int(np.count_nonzero(out[2] | out[3]))
     e2e_kt = env.core.kernel_times(False)
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(te.item())
+    e2e_value = world * B * e2e_steps / e2e_s
     h2d = B * env.core.action_dim * 4
-    d2h = int(sum(v.nbytes for v in env.core._host.values()))
+    d2h_buffers = int(sum(v.nbytes for v in env.core._host.values()))
+    # bytes a step actually moves device -> host: dense rows every step, final_* and desired_goal rows only for the
+    # environments that finished (GPR_OUT_GOAL_ON_CHANGE; final rows are written for finished envs only)
+    od, gd = env.core.obs_dim, env.core.goal_dim
+    dense = 4 * (od + gd) + 4 + sum(1 for k in env.core._host if env.core._host[k].dtype == np.uint8)
+    per_done = 4 * (od + gd + gd) + 4 * gd
+    d2h_written = int(B * dense + per_done * done_rows / e2e_steps)
     env.close()
 
     # context number: the same workload without sensor noise (the reference tests' parity setting).  EVERY rank runs it:
     # timed() holds barriers, so it must never sit inside rank-conditional code.
     extra = {}
     if not args.quick:
-        e0 = build(std_noise=0.0)
+        e0 = build(wl, B, std_noise=0.0)
         n0 = max(20, args.steps // 2)
-        ms0, _, _, _ = timed(e0, n0, 3)
-        t0 = torch.tensor([ms0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t0, op=dist.ReduceOp.MAX)
-        extra['value_no_noise'] = world * B * n0 / (float(t0.item()) * 1e-3)
+        ms0, _, _, _ = timed(e0, B, n0, 3)
+        extra['value_no_noise'] = world * B * n0 / (allmax(ms0) * 1e-3)
         e0.close()
 
+    # ---- the other BASELINE configs, measured by the same method outside the headline's timed region (one GPU only: the
+    #      scaling runs stay short).  Reported under `extra_workloads` so that every config is in the driver's record.
+    extra_workloads = {}
+    if world == 1 and not args.quick and not args.no_extra and args.workload == 'planning4':
+        for name, w, nb, st in (('pushing', WORKLOADS['pushing'], 65536, 20), ('planning8box', WORKLOADS['planning8box'], 262144, 10),
+                                ('planning4_1M', WORKLOADS['planning4'], 1048576, 10), ('pushing_1M', WORKLOADS['pushing'], 1048576, 10)):
+            try:
+                r = measure(w, nb, st, 3, 3)
+                r['env'].close()
+                extra_workloads[name] = {'workload': w['desc'].replace(f"{w['num_envs']:,} envs/GPU", f'{nb:,} envs/GPU'), 'envs_per_gpu': nb,
+                                         'value': r['value'], 'unit': 'env-steps/s', 'ms_per_step': r['ms_per_step'], 'steps': st, 'best_of': 3,
+                                         'roofline': r['roofline'], 'clocks': r['clocks']}
+            except Exception as exc:  # an extra leg must never take the headline line down with it
+                extra_workloads[name] = {'error': repr(exc)[:300]}
+
     if rank == 0:
-        N, J = int(env.cfg.num_movers), int(env.cfg.learn_jerk)
-        abytes = algorithmic_bytes_per_env_step(wl['kind'], N, J)
-        peak, peak_src = measured_hbm_peak()
-        kernel_ms = ms_max / args.steps  # whole step (all kernels of gpr_step), max over ranks
-        # roofline of the dominant kernel (the fused step kernel): its own average launch duration, CUDA events on the
-        # launching stream around that kernel alone (rank 0)
-        step_kernel_ms = ktimes['step_kernel_ms']
-        achieved = abytes * B / (step_kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_l2 = None, None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tp):
             try:
                 with open(tp) as f:
-                    traffic = json.load(f).get(args.workload)
+                    tj = json.load(f)
+                traffic = tj.get(args.workload)
+                traffic_l2 = tj.get(args.workload + '_lts_t_bytes')
             except Exception:
                 traffic = None
-        # CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
+        # CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample: the FULL batch, 10 steps)
         cpu = None
         if world == 1 and not args.no_cpu:
             if full_affinity is not None:
                 os.sched_setaffinity(0, full_affinity)  # the CPU baseline may use every host core again
             threads = host_threads()
-            cb, cs = 2048, 10
-            v1 = time_oracle(wl, cb, cs, 2, threads)
+            cs = 10
+            v1 = time_oracle(wl, B, cs, 2, threads)
             cpu = {'value': v1, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
-                   'sample': f'{cb} envs x {cs} steps of the same workload (float64 C oracle, OpenMP over envs); the MuJoCo-backed '
-                             f'reference is not installable offline'}
+                   'sample': f'{B} envs x {cs} steps of the same workload (the full batch; float64 C oracle, OpenMP over envs); the '
+                             f'MuJoCo-backed reference is not installable offline',
+                   'reference_numpy_share': reference_numpy_share()}
+        roof = dict(m['roofline'])
+        roof['traffic'] = traffic
+        roof['traffic_l2_lts_t_bytes'] = traffic_l2
+        roof['kernel_timing'] = 'CUDA events around this kernel alone, a second pass over the same steps (the timed pass overlaps the following kernel with its tail)'
+        roof['note'] = 'issue-bound kernel (40-cycle float64 loop per env): see profiles/ for issue-slot and stall breakdown'
         line = {
-            'metric': 'env-steps/s', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': kernel_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'metric': 'env-steps/s', 'value': m['value'], 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': m['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': wl['desc'], 'env_id': wl['env_id'], 'envs_per_gpu': B, 'num_cycles': int(env.cfg.num_cycles),
-                       'substeps_per_s': value * int(env.cfg.num_cycles), 'std_noise': env.cfg.std_noise[0], 'autoreset': 'same_step',
+                       'substeps_per_s': m['value'] * int(env.cfg.num_cycles), 'std_noise': env.cfg.std_noise[0], 'autoreset': 'same_step',
                        'actions': 'uniform(-max,max), 8 pre-generated device tensors cycled',
                        'l2': 'flushed between timed steps (256 MiB memset, outside the event pairs)', 'parallelism': f'env-shard x{world}',
+                       'timing': f'best of {args.repeats} blocks of {args.steps} steps, each block max over ranks',
                        'numa_bind': f'{len(numa_cpus)} cores local to the GPU' if numa_cpus else 'none'},
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                         'peak_source': peak_src, 'algorithmic_bytes_per_env_step': abytes, 'algorithmic_bytes_per_launch': abytes * B,
-                         'kernel_ms': step_kernel_ms, 'kernel_timing': 'CUDA events around this kernel alone, a second pass over the same steps (the timed pass overlaps the auto-reset kernel with its tail)', 'other_kernels_ms': {'autoreset': ktimes['autoreset_kernel_ms']}, 'kernel': 'planning_step_kernel' if wl['kind'] == 'planning' else 'pushing_step_kernel',
-                         'note': 'issue-bound kernel (40-cycle float64 loop per env): see profiles/ for issue-slot and stall breakdown'},
+            'timed_blocks_ms_per_step': m['blocks_ms_per_step'],
+            'roofline': roof,
             'cpu_baseline': cpu,
-            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-                    'ms_per_step': 1e3 * float(te.item()) / e2e_steps, 'kernel_ms_with_host_io': {'step': e2e_kt['step_kernel_ms'], 'autoreset': e2e_kt['autoreset_kernel_ms']},
+            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_written,
+                    'd2h_buffer_bytes': d2h_buffers, 'steps': e2e_steps, 'best_of': args.repeats, 'blocks_ms_per_step': [1e3 * b / e2e_steps for b in e2e_blocks],
+                    'ms_per_step': 1e3 * e2e_s / e2e_steps, 'kernel_ms_with_host_io': {'step': e2e_kt['step_kernel_ms'], KERNEL_NAMES[wl['kind']][1]: e2e_kt['autoreset_kernel_ms']},
+                    'd2h_note': 'd2h_bytes_per_step = bytes the kernels actually write per step (dense observation / achieved_goal / reward / flags rows + final_* and desired_goal rows of finished envs only); d2h_buffer_bytes = size of all result buffers',
                     'api': f'{type(env).__name__}.step_host -> gpr_step_host: NumPy views of page-locked host arrays in/out, read and written in place by the kernels over PCIe (zero-copy), stream sync before returning'},
-            'gpu_launches': int(launches), 'clocks': clocks,
-            'episode_stats': stats, 'reset_failures': fails, 'wall_s_timed_region': wall,
+            'gpu_launches': int(m['launches']), 'clocks': m['clocks'],
+            'episode_stats': stats, 'reset_failures': fails, 'wall_s_timed_region': m['wall'],
+            'extra_workloads': extra_workloads,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
@@ -390,7 +459,9 @@ def main():
     ap.add_argument('--workload', default='planning4', choices=sorted(WORKLOADS))
     ap.add_argument('--num-envs', type=int, default=0, help='envs per GPU (default: the workload\'s)')
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--repeats', type=int, default=5, help='timed blocks of --steps steps; the best block is reported (SURVEY §8d)')
     ap.add_argument('--quick', action='store_true', help='skip the extra context measurements')
+    ap.add_argument('--no-extra', action='store_true', help='skip the extra_workloads legs (pushing, planning8box, 1M-env points)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
     ap.add_argument('--no-numa-bind', action='store_true', help='do not pin the rank to the cores local to its GPU')
     args = ap.parse_args()

@@ -16,7 +16,7 @@ from typing import Any
 
 import numpy as np
 
-GPR_ABI_VERSION = 2
+GPR_ABI_VERSION = 3
 GPR_MAX_MOVERS = 32
 GPR_MAX_TILES_1D = 32
 GPR_MAX_OBSTACLES = 8
@@ -91,6 +91,7 @@ class GprConfig(ctypes.Structure):
         ('reserved0', ctypes.c_int32),
         ('obstacle_xy', (ctypes.c_double * 2) * GPR_MAX_OBSTACLES),
         ('obstacle_size', (ctypes.c_double * 2) * GPR_MAX_OBSTACLES),
+        ('obstacle_vel', (ctypes.c_double * 2) * GPR_MAX_OBSTACLES),
     ]
 
 
@@ -368,12 +369,19 @@ def planning_config(
     reference_quirks: bool = False,
     goal_output_on_change: bool = True,
     obstacles=None,
+    extra_bodies=None,
 ) -> tuple[GprConfig, dict[str, Any]]:
     """kwargs of ``BenchmarkPlanningEnv`` (planning:165-185) -> ``gpr_config``.
 
     ``obstacles``: static obstacles, the typed form of ``_check_for_other_collisions_callback`` (basic_envs.py:1976-1986):
     an array (K, 3) of ``[x, y, radius]`` rows for the circle collision shape or (K, 4) of ``[x, y, half_x, half_y]`` rows
-    (axis-aligned) for the box shape, K <= 8.  See ``gpr_config.num_obstacles`` in include/gpr.h for the rules."""
+    (axis-aligned) for the box shape, K <= 8; two more columns ``[..., vx, vy]`` give a body a prescribed constant
+    velocity.  See ``gpr_config.num_obstacles`` / ``obstacle_vel`` in include/gpr.h for the rules.
+
+    ``extra_bodies``: the same thing as a typed list — what a custom env of the reference would add to its MuJoCo model
+    through ``custom_model_xml_strings`` (basic_envs.py:134-155) and check in its collision callback, here without XML:
+    ``[{'shape': 'circle'|'box', 'pos': (x, y), 'size': r | (half_x, half_y), 'vel': (vx, vy)}, ...]`` (``vel`` optional:
+    static body; the shape must be the env's collision shape).  Appended to ``obstacles``."""
     del mover_colors_2D_plot, render_every_cycle, initial_mover_zpos  # visual only / z is not simulated (SURVEY §3.4)
     _reject_out_of_scope({} if mover_params is None else mover_params, render_mode, show_2D_plot, use_mj_passive_viewer)
     cfg = GprConfig()
@@ -410,21 +418,39 @@ def planning_config(
         min_goal_dist = 2 * np.linalg.norm(cs + d['c_size_offset'], ord=2)
     cfg.min_goal_dist = float(min_goal_dist)
     d['min_goal_dist'] = float(min_goal_dist)
-    obst = np.zeros((0, 4)) if obstacles is None else np.asarray(obstacles, dtype=np.float64)
+    want = 3 if d['c_shape'] == 'circle' else 4
+    obst = np.zeros((0, want + 2)) if obstacles is None else np.asarray(obstacles, dtype=np.float64)
     if obst.size:
-        want = 3 if d['c_shape'] == 'circle' else 4
-        if obst.ndim != 2 or obst.shape[1] != want:
-            raise ValueError(f"obstacles must have shape (K, {want}) for collision shape '{d['c_shape']}' "
-                             f"([x, y, radius] / [x, y, half_x, half_y]), got {obst.shape}")
+        if obst.ndim != 2 or obst.shape[1] not in (want, want + 2):
+            raise ValueError(f"obstacles must have shape (K, {want}) or (K, {want + 2}) for collision shape '{d['c_shape']}' "
+                             f"([x, y, radius] / [x, y, half_x, half_y], optionally followed by [vx, vy]), got {obst.shape}")
+        if obst.shape[1] == want:
+            obst = np.concatenate([obst, np.zeros((obst.shape[0], 2))], axis=1)
+    else:
+        obst = np.zeros((0, want + 2))
+    if extra_bodies:
+        rows = []
+        for body in extra_bodies:
+            if body.get('shape', d['c_shape']) != d['c_shape']:
+                raise NotImplementedError(f"an extra body must have the env's collision shape ('{d['c_shape']}'); mixed shapes have no "
+                                          'rule in the reference to restate')
+            size = np.atleast_1d(np.asarray(body['size'], dtype=np.float64))
+            if size.shape != (want - 2,):
+                raise ValueError(f"extra body size: expected {'a radius' if want == 3 else '(half_x, half_y)'}, got {body['size']!r}")
+            rows.append(np.concatenate([np.asarray(body['pos'], dtype=np.float64).reshape(2), size,
+                                        np.asarray(body.get('vel', (0.0, 0.0)), dtype=np.float64).reshape(2)]))
+        obst = np.concatenate([obst, np.stack(rows)], axis=0)
+    if obst.shape[0]:
         if obst.shape[0] > GPR_MAX_OBSTACLES:
-            raise ValueError(f'at most {GPR_MAX_OBSTACLES} obstacles')
-        if not (np.isfinite(obst).all() and (obst[:, 2:] > 0).all()):
+            raise ValueError(f'at most {GPR_MAX_OBSTACLES} obstacles / extra bodies')
+        if not (np.isfinite(obst).all() and (obst[:, 2:want] > 0).all()):
             raise ValueError('obstacle sizes must be finite and > 0')
         cfg.num_obstacles = int(obst.shape[0])
         for k in range(obst.shape[0]):
             cfg.obstacle_xy[k][0], cfg.obstacle_xy[k][1] = float(obst[k, 0]), float(obst[k, 1])
             cfg.obstacle_size[k][0] = float(obst[k, 2])
             cfg.obstacle_size[k][1] = float(obst[k, 3]) if want == 4 else float(obst[k, 2])
+            cfg.obstacle_vel[k][0], cfg.obstacle_vel[k][1] = float(obst[k, want]), float(obst[k, want + 1])
     d['obstacles'] = obst
     d['obs_dim'] = num_movers * (1 + int(bool(learn_jerk))) * 2
     d['goal_dim'] = num_movers * 2

@@ -170,9 +170,12 @@ static int validate(const gpr_config* c) {
     if (c->num_obstacles < 0 || c->num_obstacles > GPR_MAX_OBSTACLES) return fail(GPR_ERR_INVALID_ARG, "num_obstacles out of range");
     if (c->num_obstacles > 0 && c->env_kind != GPR_ENV_PLANNING)
         return fail(GPR_ERR_UNSUPPORTED, "static obstacles are a planning-env feature");
-    for (int k = 0; k < c->num_obstacles; ++k)
+    for (int k = 0; k < c->num_obstacles; ++k) {
         if (!(c->obstacle_size[k][0] > 0) || (c->c_shape == GPR_SHAPE_BOX && !(c->obstacle_size[k][1] > 0)))
             return fail(GPR_ERR_INVALID_ARG, "obstacle sizes must be > 0");
+        if (!std::isfinite(c->obstacle_vel[k][0]) || !std::isfinite(c->obstacle_vel[k][1]))
+            return fail(GPR_ERR_INVALID_ARG, "obstacle velocities must be finite");
+    }
     for (int m = 0; m < c->num_movers; ++m)
         for (int s = 0; s < 2; ++s) {
             if (!(c->c_wall[s][m][0] > 0) || !(c->c_mover[s][m][0] > 0))
@@ -390,12 +393,17 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     // static obstacles: float32 screen slack = position-noise bound + float rounding of coordinates up to the layout extent
     a.n_obst = c.num_obstacles;
     a.obst_delta = (float)((h->noise ? 6.0 * c.std_noise[0] * 1.01 : 0.0) + 4e-6 * std::max(1.0, extent) + 2e-6);
+    double vmax = 0.0;
     for (int k = 0; k < c.num_obstacles; ++k) {
         a.obst[k][0] = c.obstacle_xy[k][0];
         a.obst[k][1] = c.obstacle_xy[k][1];
         a.obst[k][2] = c.obstacle_size[k][0];
         a.obst[k][3] = c.obstacle_size[k][1];
+        a.obst_vel[k][0] = c.obstacle_vel[k][0];
+        a.obst_vel[k][1] = c.obstacle_vel[k][1];
+        vmax = std::max(vmax, std::hypot(c.obstacle_vel[k][0], c.obstacle_vel[k][1]));
     }
+    a.obst_vmaxf = vmax > 0.0 ? (float)(vmax * 1.000001) + 1e-12f : 0.f;  // (rounded up: a bound)
     a.inv_wxf = (float)(1.0 / (2.0 * c.tile_half[0]));
     a.inv_wyf = (float)(1.0 / (2.0 * c.tile_half[1]));
     a.sigma_p = c.std_noise[0];

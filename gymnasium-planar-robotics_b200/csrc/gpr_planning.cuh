@@ -64,7 +64,9 @@ struct PlanArgs {
     // static obstacles (gpr_config.num_obstacles): x, y, size0, size1 — circle radius / box half sizes
     int n_obst;
     float obst_delta;  // float32 screen slack: position-noise bound + float rounding
+    float obst_vmaxf;  // largest prescribed speed of an extra body (gpr_config.obstacle_vel), rounded up; 0 = all static
     double obst[GPR_MAX_OBSTACLES][4];
+    double obst_vel[GPR_MAX_OBSTACLES][2];
     const double* c_wall;   // [2][GPR_MAX_MOVERS][2] device
     const double* c_mover;  // [2][GPR_MAX_MOVERS][2] device
     // state (SoA, float64)
@@ -355,10 +357,11 @@ __device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part,
 // Exact test of ONE mover against every obstacle, on the position (x, y) the caller has made noisy or not; (s0, s1) are the
 // mover's collision sizes, rm its rectangle (box shape).  Mirrors gpro_check_obstacle_collision of the oracle.
 template <bool BOX>
-static __device__ __noinline__ bool obstacle_hit_exact(const PlanArgs& a, double x, double y, double s0, const Rect& rm) {
+// t: time the extra bodies have been moving (gpr_config.obstacle_vel); 0 at reset() and for start / goal sampling.
+static __device__ __noinline__ bool obstacle_hit_exact(const PlanArgs& a, double x, double y, double s0, const Rect& rm, double t = 0.0) {
 #pragma unroll 1
     for (int k = 0; k < a.n_obst; ++k) {
-        const double ox = a.obst[k][0], oy = a.obst[k][1];
+        const double ox = dadd(a.obst[k][0], dmul(a.obst_vel[k][0], t)), oy = dadd(a.obst[k][1], dmul(a.obst_vel[k][1], t));
         if (!BOX) {
             const double dx = dsub(x, ox), dy = dsub(y, oy);
             if (dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))) <= dadd(s0, a.obst[k][2])) return true;
@@ -375,12 +378,13 @@ static __device__ __noinline__ bool obstacle_hit_exact(const PlanArgs& a, double
 // float32 screen: 0 = certain miss (clear = distance the mover may still travel before that can change), 1 = certain hit
 // (circle only), 2 = too close to call.  (e0, e1): circle radius / bounding half extents of the (noise-rotated) box.
 template <bool BOX>
-__device__ __forceinline__ int obstacle_screen(const PlanArgs& a, double x, double y, float e0, float e1, float& clear) {
+__device__ __forceinline__ int obstacle_screen(const PlanArgs& a, double x, double y, float e0, float e1, float& clear, double t = 0.0) {
     clear = 3.0e38f;
     int verdict = 0;
 #pragma unroll 1
     for (int k = 0; k < a.n_obst; ++k) {
-        const float dx = fabsf((float)dsub(x, a.obst[k][0])), dy = fabsf((float)dsub(y, a.obst[k][1]));
+        const double ox = dadd(a.obst[k][0], dmul(a.obst_vel[k][0], t)), oy = dadd(a.obst[k][1], dmul(a.obst_vel[k][1], t));
+        const float dx = fabsf((float)dsub(x, ox)), dy = fabsf((float)dsub(y, oy));
         float gap;
         if (!BOX) {
             const float t = e0 + (float)a.obst[k][2];
@@ -1207,8 +1211,9 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
             p.y = dadd(p.y, dmul(a.dt, v.y));
             // |v| <= max + min/2 of the absolute components; 1e-4 covers the float roundings of the running sum
             const float avx = fabsf((float)v.x), avy = fabsf((float)v.y);
-            travel += (fmaxf(avx, avy) + 0.5f * fminf(avx, avy)) * 1.0001f;
-            if (LINF) travel_w += fmaxf(avx, avy) * 1.0001f;
+            // (obst_vmaxf: a moving extra body closes in on its own account; it uses up the shared wall / obstacle budget too)
+            travel += (fmaxf(avx, avy) + 0.5f * fminf(avx, avy) + a.obst_vmaxf) * 1.0001f;
+            if (LINF) travel_w += (fmaxf(avx, avy) + a.obst_vmaxf) * 1.0001f;
         }
         const bool due_w = part && !((LINF ? travel_w : travel) < lim_w);
         const bool due_p = G > 1 && part && !(travel < lim_p);
@@ -1247,7 +1252,9 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
             // ---- static obstacles (the hook of basic:1903), checked with the walls on the wall check's noisy qpos
             if (a.n_obst > 0) {
                 float clear_o;
-                const int f = obstacle_screen<BOX>(a, p.x, p.y, BOX ? pxf : (float)cm0, pyf, clear_o);
+                // (an extra body with a prescribed velocity has moved for as long as the movers have been integrated)
+                const double t_obst = dmul((double)(elapsed * a.num_cycles + cyc + 1), a.dt);
+                const int f = obstacle_screen<BOX>(a, p.x, p.y, BOX ? pxf : (float)cm0, pyf, clear_o, t_obst);
                 if (f == 2) {
                     double wx = p.x, wy = p.y;
                     Rect rm;
@@ -1265,7 +1272,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
                     } else if (BOX) {
                         rect_vertices_axis(wx, wy, cm0, cm1, rm);
                     }
-                    obad = obstacle_hit_exact<BOX>(a, wx, wy, cm0, rm);
+                    obad = obstacle_hit_exact<BOX>(a, wx, wy, cm0, rm, t_obst);
                 } else {
                     obad = f == 1;
                 }

@@ -104,7 +104,7 @@ def rasterize_scene(layout_tiles, tile_half, mover_pos, mover_half, c_shape, c_s
                 cv.rect(cx, cy, hx, hy, SILVER)
                 cv.rect(cx, cy, hx, hy, BACKGROUND, outline=True, width_px=1.0)  # tile joints
     if obstacles is not None:
-        for o in np.asarray(obstacles, dtype=np.float64).reshape(-1, 3 if c_shape == 'circle' else 4):
+        for o in np.asarray(obstacles, dtype=np.float64):  # rows [x, y, size..., (vx, vy)]: already at the time of the view
             if c_shape == 'circle':
                 cv.circle(o[0], o[1], o[2], OBSTACLE_COLOUR)
             else:
@@ -179,5 +179,11 @@ def view_of_env(env, env_index: int = 0, ppm: float = 400.0) -> np.ndarray:
         kw.update(object_pose=one['object_pos'], object_half=float(cfg.object_half_xy), object_goal=one['goal'].reshape(-1)[:2],
                   mover_yaw=np.array([np.arctan2(rot[1], rot[0])]))
     else:
-        kw.update(goals=one['goal'], obstacles=d.get('obstacles') if d.get('obstacles') is not None and len(d['obstacles']) else None)
+        ob = d.get('obstacles')
+        if ob is not None and len(ob):
+            # extra bodies with a prescribed velocity: where they are after the env-steps of the running episode
+            ob = np.array(ob, dtype=np.float64)
+            t = float(st['elapsed_steps'][env_index]) * int(cfg.num_cycles) * float(cfg.cycle_time)
+            ob[:, :2] += ob[:, -2:] * t
+        kw.update(goals=one['goal'], obstacles=ob if ob is not None and len(ob) else None)
     return rasterize_scene(**kw)

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GPR_ABI_VERSION 2
+#define GPR_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define GPR_API __attribute__((visibility("default")))
@@ -148,6 +148,14 @@ typedef struct gpr_config {
     int32_t reserved0;
     double obstacle_xy[GPR_MAX_OBSTACLES][2];
     double obstacle_size[GPR_MAX_OBSTACLES][2]; /* circle: radius in [0]; box: half sizes */
+    /* --- typed "extra bodies" (SURVEY.md §8f-3): what a custom env of the reference adds to the MuJoCo model through
+     * `custom_model_xml_strings` (basic_envs.py:134-155; docs/make_own_env.rst) and then checks in its
+     * `_check_for_other_collisions_callback` — here without XML, as kinematic planar bodies: each obstacle may carry a
+     * PRESCRIBED constant velocity.  Its centre at the check of control cycle c (0-based) of an episode's env-step s
+     * (0-based) is  obstacle_xy + obstacle_vel * ((s * num_cycles + c + 1) * cycle_time)  — product and sum each rounded
+     * once in float64 — i.e. the body has moved for as long as the movers have been integrated; at reset() (and for the
+     * start / goal sampling) it is at obstacle_xy.  All zeros = static obstacles = the behaviour of ABI version 2. */
+    double obstacle_vel[GPR_MAX_OBSTACLES][2];
 } gpr_config;
 
 /* output_flags bit: a step writes `desired_goal` rows only for environments whose goal changed in that call (they were

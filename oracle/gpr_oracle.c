@@ -346,9 +346,10 @@ int gpro_check_mover_collision(const gpr_config* c, int n, const double* qpos, c
  * mover-mover check (basic:390-424) between every mover and every obstacle: circle  ||p - o|| <= r_mover + r_obstacle
  * (inclusive like basic:409);  box  geom.check_rectangles_intersect (geom:107-138) or the mover's centre inside the
  * obstacle (the edge test alone does not see containment).  qpos: [n][7] (noisy) mover poses; csize: [n][2] sizes. */
-int gpro_check_obstacle_collision(const gpr_config* c, int n, const double* qpos, const double* csize) {
+int gpro_check_obstacle_collision_at(const gpr_config* c, int n, const double* qpos, const double* csize, double t) {
     for (int k = 0; k < c->num_obstacles; ++k) {
-        const double ox = c->obstacle_xy[k][0], oy = c->obstacle_xy[k][1];
+        /* typed extra bodies: prescribed constant velocity, position = p0 + v * t (gpr_config.obstacle_vel) */
+        const double ox = c->obstacle_xy[k][0] + c->obstacle_vel[k][0] * t, oy = c->obstacle_xy[k][1] + c->obstacle_vel[k][1] * t;
         for (int m = 0; m < n; ++m) {
             const double* q = qpos + 7 * m;
             if (c->c_shape == GPR_SHAPE_CIRCLE) {
@@ -363,6 +364,12 @@ int gpro_check_obstacle_collision(const gpr_config* c, int n, const double* qpos
         }
     }
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* the bodies at their initial positions (reset(), start / goal sampling) */
+int gpro_check_obstacle_collision(const gpr_config* c, int n, const double* qpos, const double* csize) {
+    return gpro_check_obstacle_collision_at(c, n, qpos, csize, 0.0);
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */
@@ -598,9 +605,9 @@ static int planning_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_g
 }
 
 /* basic:1835-1950 step for one planning env (state updated in place). */
-static void planning_step_one(const gpr_config* c, uint64_t seed, uint32_t env_global, uint32_t event, double* p,
-                              double* v, double* a, const float* action, int* mover_collision, int* wall_collision,
-                              int* other_collision) {
+static void planning_step_one(const gpr_config* c, uint64_t seed, uint32_t env_global, uint32_t event, int elapsed,
+                              double* p, double* v, double* a, const float* action, int* mover_collision,
+                              int* wall_collision, int* other_collision) {
     const int N = c->num_movers;
     const double dt = c->cycle_time;
     const double lim = c->learn_jerk ? c->j_max : c->a_max;
@@ -678,7 +685,10 @@ static void planning_step_one(const gpr_config* c, uint64_t seed, uint32_t env_g
         wc = 0;
         for (int m = 0; m < N; ++m) wc |= !valid[m];
         /* basic:1903 the hook: static obstacles, on the wall check's noisy qpos, no safety offset */
-        oc = c->num_obstacles > 0 ? gpro_check_obstacle_collision(c, N, qpos, cm) : 0;
+        /* (extra bodies with a prescribed velocity have moved for as long as the movers have been integrated) */
+        oc = c->num_obstacles > 0
+                 ? gpro_check_obstacle_collision_at(c, N, qpos, cm, (double)(elapsed * c->num_cycles + cyc + 1) * dt)
+                 : 0;
         /* basic:1895-1901 mover check on an independent noisy qpos */
         noisy_qpos(c, p, N, (noisy_p && N > 1) ? nxy_m : NULL, (noisy_p && box && N > 1) ? nq_m : NULL, qpos);
         mc = gpro_check_mover_collision(c, N, qpos, cm);
@@ -775,7 +785,7 @@ void gpro_planning_step(const gpr_config* c, uint64_t seed, gpro_state* s, const
             continue;
         }
         uint32_t event = s->rng_counter[e];
-        planning_step_one(c, seed, env_global, event, p, v, a, action + e * 2 * N, &mc, &wc, &oc);
+        planning_step_one(c, seed, env_global, event, s->elapsed_steps[e], p, v, a, action + e * 2 * N, &mc, &wc, &oc);
         planning_obs(c, p, v, a, g, seed, env_global, event, o, ag, dg);
         s->rng_counter[e] = event + 1u;
         double r;

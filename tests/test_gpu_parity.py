@@ -814,6 +814,37 @@ def test_obstacles_with_autoreset_sampling(shape, movers, mode):
     env.close()
 
 
+@pytest.mark.parametrize('shape,movers,mode', [('circle', 2, 'same_step'), ('circle', 4, 'next_step'), ('box', 3, 'same_step'), ('box', 8, 'off')])
+def test_extra_bodies_with_prescribed_velocity(shape, movers, mode):
+    """typed extra bodies — kinematic circles / boxes with a constant velocity (gpr_config.obstacle_vel).
+    CUDA == oracle bit for bit, including the travel-budget bookkeeping of the step kernel (a moving body uses up the
+    certified clearance on its own account)."""
+    rng = np.random.default_rng(500 + movers)
+    if shape == 'circle':
+        cp = {'shape': 'circle', 'size': 0.08}
+        bodies = [{'pos': (0.48, 0.48), 'size': 0.05}, {'pos': (0.1, 0.8), 'size': 0.04, 'vel': (0.4, -0.05)}, {'pos': (0.9, 0.2), 'size': 0.03, 'vel': (-0.5, 0.3)}]
+    else:
+        cp = {'shape': 'box', 'size': np.array([0.07, 0.05])}
+        bodies = [{'shape': 'box', 'pos': (0.5, 0.5), 'size': (0.06, 0.03)}, {'shape': 'box', 'pos': (0.1, 0.75), 'size': (0.03, 0.08), 'vel': (0.45, 0.0)},
+                  {'shape': 'box', 'pos': (0.95, 0.3), 'size': (0.05, 0.02), 'vel': (-0.3, 0.2)}]
+    layout = np.ones((5, 5)) if movers == 8 else np.ones((4, 4))
+    env, ora = make_pair(1500, layout_tiles=layout, num_movers=movers, std_noise=1e-5, collision_params=cp, extra_bodies=bodies,
+                         autoreset_mode=mode, max_episode_steps=12, seed=9)
+    run_lockstep(env, ora, 30, rng, 4.0, inject=(mode == 'off'), seed=9)
+    assert ora.other_collision.any() or mode != 'off'
+    env.close()
+
+
+def test_custom_env_without_xml_matches_the_oracle():
+    """The docs/make_own_env.rst-style custom env of tests/test_oracle_obstacles.py (robot base + conveyor pallets, no XML)."""
+    from test_oracle_obstacles import custom_conveyor_env_kwargs
+
+    env, ora = make_pair(4096, seed=3, **custom_conveyor_env_kwargs())
+    run_lockstep(env, ora, 40, np.random.default_rng(1), 6.0, inject=False, seed=3)
+    assert env.episode_stats()['episodes'] > 1000
+    env.close()
+
+
 def test_obstacles_through_the_host_path_and_her():
     """step_host delivers other_collision like the other flags; compute_reward treats it as a collision."""
     cp = {'shape': 'circle', 'size': 0.08}

@@ -123,3 +123,68 @@ def test_no_obstacles_is_the_reference_path():
         a.step(act)
         b.step(act)
         assert np.array_equal(a.pos, b.pos) and np.array_equal(a.reward, b.reward) and not b.other_collision.any()
+
+
+# ---- typed extra bodies with a prescribed velocity (gpr_config.obstacle_vel) --------------------------
+def test_extra_body_kwarg_is_the_obstacle_list_with_velocities():
+    cfg, d = gpr.planning_config(num_envs=1, layout_tiles=np.ones((4, 4)), num_movers=1, obstacles=[[0.5, 0.5, 0.05]],
+                                 extra_bodies=[{'shape': 'circle', 'pos': (0.2, 0.7), 'size': 0.03, 'vel': (0.25, -0.125)}, {'pos': (0.8, 0.8), 'size': 0.02}])
+    assert cfg.num_obstacles == 3 and d['obstacles'].shape == (3, 5)
+    assert [cfg.obstacle_vel[0][0], cfg.obstacle_vel[0][1]] == [0.0, 0.0] and [cfg.obstacle_vel[1][0], cfg.obstacle_vel[1][1]] == [0.25, -0.125]
+    assert cfg.obstacle_xy[2][0] == 0.8 and cfg.obstacle_size[2][0] == 0.02
+    with pytest.raises(NotImplementedError):
+        gpr.planning_config(num_envs=1, layout_tiles=np.ones((4, 4)), num_movers=1, extra_bodies=[{'shape': 'box', 'pos': (0.2, 0.7), 'size': (0.1, 0.1)}])
+    with pytest.raises(ValueError):
+        gpr.planning_config(num_envs=1, layout_tiles=np.ones((4, 4)), num_movers=1, obstacles=np.zeros((9, 3)) + 0.1)
+
+
+@pytest.mark.parametrize('shape', ['circle', 'box'])
+def test_moving_body_reaches_a_resting_mover_at_the_predicted_cycle(shape):
+    """A body moving at constant velocity towards a mover at rest: the env must flag `other_collision` in the control cycle
+    in which  p0 + v * ((s * num_cycles + c + 1) * dt)  first touches the mover's collision shape, and freeze there."""
+    if shape == 'circle':
+        cp, body, reach = {'shape': 'circle', 'size': 0.08}, {'pos': (0.2, 0.48), 'size': 0.04, 'vel': (0.5, 0.0)}, 0.08 + 0.04
+    else:
+        cp, reach = {'shape': 'box', 'size': np.array([0.07, 0.05])}, 0.07 + 0.03
+        body = {'shape': 'box', 'pos': (0.2, 0.48), 'size': (0.03, 0.2), 'vel': (0.5, 0.0)}
+    cfg, _ = gpr.planning_config(num_envs=1, layout_tiles=np.ones((4, 4)), num_movers=1, std_noise=0.0, collision_params=cp,
+                                 extra_bodies=[body], autoreset_mode='off', max_episode_steps=0)
+    env = oracle.OracleEnv(cfg)
+    env.reset(seed=0, inject_start=np.array([[[0.48, 0.48]]]), inject_goal=np.array([[[0.7, 0.7]]]))
+    assert not env.other_collision[0]
+    # gap at t = 0: 0.28 - reach; the body closes 0.5 mm per cycle.  The box test has the reference's 1e-7 edge tolerance.
+    gap = 0.48 - 0.2 - reach
+    hit_cycle = next(n for n in range(1, 4000) if 0.2 + 0.5 * (n * 0.001) + reach >= 0.48 - (1e-7 if shape == 'box' else 0.0))
+    assert abs(hit_cycle - gap / 0.0005) <= 1
+    steps = 0
+    while not env.other_collision[0]:
+        env.step(np.zeros((1, 2), np.float32))
+        steps += 1
+        assert steps <= 20
+    assert steps == (hit_cycle + 39) // 40  # the env-step that contains that cycle
+    assert env.terminated[0] and env.reward[0] == -50.0 and not env.mover_collision[0] and not env.wall_collision[0]
+    assert np.array_equal(env.pos[0, 0], [0.48, 0.48])  # the mover never moved
+
+
+def test_custom_env_without_xml_conveyor_example():
+    """docs/make_own_env.rst builds custom envs by adding bodies to the MuJoCo XML and checking them in
+    `_check_for_other_collisions_callback`.  The same env, typed: a fixed robot base and two pallets on a conveyor crossing the
+    tiles; movers must reach their goals without touching either.  (CUDA == oracle for this env: tests/test_gpu_parity.py)"""
+    kw = custom_conveyor_env_kwargs()
+    cfg, _ = gpr.planning_config(num_envs=64, seed=3, **kw)
+    env = oracle.OracleEnv(cfg)
+    env.reset(seed=3)
+    rng = np.random.default_rng(0)
+    hits = 0
+    for _ in range(40):
+        env.step(rng.uniform(-6, 6, (64, 4)).astype(np.float32))
+        hits += int(env.other_collision.sum())
+        assert ((env.reward == -50) == (env.other_collision | env.mover_collision | env.wall_collision).astype(bool)).all()
+    assert hits > 0
+
+
+def custom_conveyor_env_kwargs():
+    return dict(layout_tiles=np.ones((4, 4)), num_movers=2, collision_params={'shape': 'circle', 'size': 0.09, 'offset': 0.005},
+                extra_bodies=[{'shape': 'circle', 'pos': (0.48, 0.48), 'size': 0.07},                        # robot base, fixed
+                              {'shape': 'circle', 'pos': (0.10, 0.80), 'size': 0.04, 'vel': (0.30, 0.0)},    # pallets on a conveyor
+                              {'shape': 'circle', 'pos': (0.86, 0.16), 'size': 0.04, 'vel': (-0.30, 0.0)}])
