@@ -325,10 +325,15 @@ __device__ __forceinline__ bool pair_circle_fast(const PlanArgs& a, unsigned lan
 // than the position-noise bound + float slack `mg` cannot have intersecting edges (geom:107-138): a certain miss, and
 // `margin` is the largest of the two axis gaps — the L-infinity distance the pair may still close before that changes.
 // `near` marks lanes with a pair the screen cannot clear (the caller then runs the exact rectangle test for the warp).
+// `sure` (only with hx > 0: all boxes have ONE size (hx, hy), the true half sizes): the two boxes overlap along BOTH axes by
+// more than the noise bound + slack.  Two equal rectangles cannot contain one another, so their edges cross: a certain hit
+// (geom:107-138 reports it) — the exact 16-edge-pair test is only needed for pairs in the thin band around first touch.
 template <int G>
 __device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part, double x, double y, float exf, float eyf,
-                                                float mg, bool& near, float& margin, unsigned& kmask) {
+                                                float mg, bool& near, float& margin, unsigned& kmask, bool& sure, float hx = 0.f,
+                                                float hy = 0.f, float shrink = 0.f) {
     near = false;
+    sure = false;
     margin = 3.0e38f;
     kmask = 0u;  // bit k: the pair (m, m+k) could not be cleared
     if (G == 1) return;
@@ -341,10 +346,14 @@ __device__ __forceinline__ void pair_box_screen(unsigned lane, int m, bool part,
         const float tx = (exf + __shfl_sync(FULL, exf, src) + mg) * 1.000001f;
         const float ty = (eyf + __shfl_sync(FULL, eyf, src) + mg) * 1.000001f;
         const bool both = part && oxf < 1e29f;
-        const float mgn = fmaxf(fabsf(xf - oxf) * 0.999999f - tx, fabsf(yf - oyf) * 0.999999f - ty);
+        const float adx = fabsf(xf - oxf), ady = fabsf(yf - oyf);
+        const float mgn = fmaxf(adx * 0.999999f - tx, ady * 0.999999f - ty);
         if (both) {
-            near = near || !(mgn > 0.f);
-            kmask |= !(mgn > 0.f) ? (1u << k) : 0u;
+            // certain hit: overlap along both axes deeper than (noise bound + rotation of the noisy quaternion + slack)
+            const bool hitc = hx > 0.f && adx * 1.000001f < 2.f * hx - shrink && ady * 1.000001f < 2.f * hy - shrink;
+            sure = sure || hitc;
+            near = near || (!(mgn > 0.f) && !hitc);
+            kmask |= (!(mgn > 0.f) && !hitc) ? (1u << k) : 0u;
         }
         // (own pairs on both sides of the lane group, see pair_circle_fast)
         const float mk = both ? fmaxf(mgn, 0.f) : 3.0e38f;
@@ -455,11 +464,11 @@ __device__ __forceinline__ void store_obs(const PlanArgs& a, const Lane<G>& ln, 
 #endif
 #if GPR_SAMPLER_PHILOX_CALL
 static __device__ __noinline__ gpr_u32x4 sampler_block(uint64_t seed, uint32_t eg, uint32_t ev, uint32_t stream, uint32_t lane) {
-    return gpr_rng_block(seed, eg, ev, stream, lane);
+    return gpr_rng_block_sampling(seed, eg, ev, stream, lane);
 }
 #else
 __device__ __forceinline__ gpr_u32x4 sampler_block(uint64_t seed, uint32_t eg, uint32_t ev, uint32_t stream, uint32_t lane) {
-    return gpr_rng_block(seed, eg, ev, stream, lane);
+    return gpr_rng_block_sampling(seed, eg, ev, stream, lane);
 }
 #endif
 
@@ -928,13 +937,13 @@ __device__ __forceinline__ void reset_checks(const PlanArgs& a, const Tables& tb
             f = wall_fast(a, tb, p.x, p.y, (float)cw0 + ext_w, (float)cw1 + ext_w, gi, gj, clear);
         }
         const bool wneed = part && f != 1;  // (0 is not a verdict: the bounding rectangle is conservative)
-        bool near;
+        bool near, sure;
         float clear_p;
         unsigned kmask;
         pair_box_screen<G>(ln.lane, ln.m, part, p.x, p.y, (float)cm0 + ext_m, (float)cm1 + ext_m, a.pair_mgf[NOISE ? 1 : 0], near,
-                           clear_p, kmask);
+                           clear_p, kmask, sure, a.uniform_pairs ? (float)cm0 : 0.f, (float)cm1, 2.f * ext_m + a.pair_mgf[NOISE ? 1 : 0]);
         bad = false;
-        hit = false;
+        hit = sure;
         const bool wany = __any_sync(FULL, wneed), pany = G > 1 && __any_sync(FULL, near);
         if (wany || pany) {
             double wx = p.x, wy = p.y, mx = p.x, my = p.y;
@@ -962,7 +971,7 @@ __device__ __forceinline__ void reset_checks(const PlanArgs& a, const Tables& tb
                 rect_vertices_axis(mx, my, cm0, cm1, rm);
             }
             if (wneed) bad = !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
-            if (pany) hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0, kmask);
+            if (pany) hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0, kmask) || sure;
         }
     }
     // basic:1807 the hook: static obstacles on the wall check's noisy qpos, with the safety offset like that wall check
@@ -1025,6 +1034,60 @@ __device__ __forceinline__ void reset_group(const PlanArgs& a, const Tables& tb,
     reset_checks<G, BOX, NOISE>(a, tb, ln, need, event, p, mc, wc, oc);
 }
 
+// ---- box shape, step kernel: the exact fallbacks of the float32 screens as ONE out-of-line function each.  Inlined they put
+// ~4 Philox + Box-Muller expansions, two quat2mat rectangles, wall_valid<true> and the shuffles of pair_check into the
+// 40-cycle loop: the box step kernel was 167 KB of code with "no instruction" as a top stall reason (1.97 per issued
+// instruction, profiles/r2_full_planning8box.txt).  Measured on B200 (planning8box, 262,144 envs): out of line 1.96 ms per
+// step-kernel launch, inlined 1.91 ms — the calls cost more than the cache misses they save, so inlined stays the default
+// (GPR_BOX_OOL=1 builds the out-of-line form).
+#ifndef GPR_BOX_OOL
+#define GPR_BOX_OOL 0
+#endif
+#if GPR_BOX_OOL
+#define GPR_BOX_COLD static __device__ __noinline__
+#else
+#define GPR_BOX_COLD __device__ __forceinline__
+#endif
+// basic:1888-1894 for one box-shaped mover, exact: noisy position + noisy quaternion -> vertices -> wall_valid
+template <bool NOISE>
+GPR_BOX_COLD bool box_wall_exact(const PlanArgs& a, const Tables& tb, double px, double py, double cw0, double cw1,
+                                 uint32_t env_global, uint32_t event, uint32_t s0, uint32_t m) {
+    double wx = px, wy = py;
+    Rect rw;
+    if (NOISE) {
+        float n4[4], q[4];
+        normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, m, n4);
+        wx = noisy(px, n4[2], a.sigma_p);
+        wy = noisy(py, n4[3], a.sigma_p);
+        normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT, m, q);
+        rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                      dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
+    } else {
+        rect_vertices_axis(wx, wy, cw0, cw1, rw);
+    }
+    return !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
+}
+// basic:1895-1901 for the box shape, exact, warp-collective (EVERY lane of the warp calls it): noisy poses -> vertices ->
+// the rectangle test of the pairs in kmask
+template <int G, bool NOISE>
+GPR_BOX_COLD bool box_pair_exact(const PlanArgs& a, unsigned lane, int m, bool part, double px, double py, double cm0, double cm1,
+                                 uint32_t env_global, uint32_t event, uint32_t s0, unsigned kmask) {
+    double mx = px, my = py;
+    Rect rm;
+    if (NOISE) {
+        float k4[4], q[4];
+        normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_MOVER, (uint32_t)m, k4);
+        mx = noisy(px, k4[0], a.sigma_p);
+        my = noisy(py, k4[1], a.sigma_p);
+        normal4_cold(a.seed, env_global, event, s0 + GPR_RNG_BLOCK_MOVER_QUAT, (uint32_t)m, q);
+        rect_vertices(mx, my, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
+                      dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
+    } else {
+        rect_vertices_axis(mx, my, cm0, cm1, rm);
+    }
+    return pair_check<G, true>(lane, m, part, mx, my, cm0, cm1, rm, false, 0.0, kmask);
+}
+
 // reward / terminated / is_success for one env from the group reductions (plan:502-534, 459-479, 596-601)
 __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, bool wc, float& reward, bool& term,
                                                 bool& succ) {
@@ -1072,10 +1135,10 @@ __device__ __forceinline__ void planning_reward(int N, int reached, bool mc, boo
 #ifndef GPR_STEP_THREADS
 #define GPR_STEP_THREADS 128
 #endif
-// threads per CTA of planning_step_kernel: at least 8 envs per CTA (the CTA-gathered flag stores work in 8-byte units)
+// threads per CTA of planning_step_kernel
 template <int G>
 struct StepThreads {
-    static constexpr int value = GPR_STEP_THREADS >= 8 * G ? GPR_STEP_THREADS : 8 * G;
+    static constexpr int value = GPR_STEP_THREADS;
 };
 
 template <int G, bool BOX, bool NOISE, bool JERK>
@@ -1085,7 +1148,9 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
     // (programmatic dependent launch): its warps then fill the SM slots the last, partial wave of this grid leaves idle
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ Tables tb;
+    __shared__ unsigned s_signed_off;  // warps of this CTA that have dropped their per-env results into shared memory
     load_tables(tb, a.L);
+    if (threadIdx.x == 0) s_signed_off = 0u;
     __syncthreads();
     const Lane<G> ln = make_lane<G>(a);
     const int mm = ln.active ? ln.m : 0;
@@ -1231,21 +1296,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
                 // float32 screen with a bounding rectangle; the exact vertex / rectangle tests of basic:559-572, 657-783
                 // only where the screen cannot certify "valid" (0 is not a verdict: the rectangle is conservative)
                 if (wall_fast(a, tb, p.x, p.y, bxf, byf, gi, gj, clear_w) != 1) {
-                    double wx = p.x, wy = p.y;
-                    Rect rw;
-                    if (NOISE) {
-                        if (!have0) normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_VEL_WALL, (uint32_t)ln.m, n4);
-                        have0 = true;
-                        wx = noisy(p.x, n4[2], a.sigma_p);
-                        wy = noisy(p.y, n4[3], a.sigma_p);
-                        float q[4];
-                        normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_WALL_QUAT, (uint32_t)ln.m, q);
-                        rect_vertices(wx, wy, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
-                                      dmul((double)q[3], a.sigma_p), cw0, cw1, rw);
-                    } else {
-                        rect_vertices_axis(wx, wy, cw0, cw1, rw);
-                    }
-                    bad = !wall_valid<true>(tb, a.L, wx, wy, cw0, rw);
+                    bad = box_wall_exact<NOISE>(a, tb, p.x, p.y, cw0, cw1, ln.env_global, event, s0, (uint32_t)ln.m);
                     guess_cell(a, p.x, p.y, gi, gj);  // refresh the tracked cell
                 }
             }
@@ -1290,26 +1341,13 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
                                                  s0 + GPR_RNG_BLOCK_MOVER, clear_p);
             } else {
                 // axis-gap screen; the exact rectangle test of geom:107-138 only for a warp with an uncleared pair
-                bool near;
+                bool near, sure;
                 unsigned kmask;
-                pair_box_screen<G>(ln.lane, ln.m, part, p.x, p.y, pxf, pyf, a.pair_mgf[NOISE ? 1 : 0], near, clear_p, kmask);
-                if (__any_sync(FULL, near)) {
-                    double mx = p.x, my = p.y;
-                    Rect rm;
-                    if (NOISE) {
-                        float k4[4], q[4];
-                        normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER, (uint32_t)ln.m, k4);
-                        mx = noisy(p.x, k4[0], a.sigma_p);
-                        my = noisy(p.y, k4[1], a.sigma_p);
-                        normal4_cold(a.seed, ln.env_global, event, s0 + GPR_RNG_BLOCK_MOVER_QUAT, (uint32_t)ln.m, q);
-                        rect_vertices(mx, my, noisy(1.0, q[0], a.sigma_p), dmul((double)q[1], a.sigma_p), dmul((double)q[2], a.sigma_p),
-                                      dmul((double)q[3], a.sigma_p), cm0, cm1, rm);
-                    } else {
-                        rect_vertices_axis(mx, my, cm0, cm1, rm);
-                    }
-                    // exact test of the pairs the screen could not clear (the cleared ones are certain misses)
-                    hit = pair_check<G, true>(ln.lane, ln.m, part, mx, my, cm0, cm1, rm, false, 0.0, kmask);
-                }
+                pair_box_screen<G>(ln.lane, ln.m, part, p.x, p.y, pxf, pyf, a.pair_mgf[NOISE ? 1 : 0], near, clear_p, kmask, sure,
+                                   a.uniform_pairs ? (float)cm0 : 0.f, (float)cm1, 2.f * (pxf - (float)cm0) + a.pair_mgf[NOISE ? 1 : 0]);
+                hit = sure;
+                if (__any_sync(FULL, near))  // exact test of the pairs the screen could not decide (the others are certain)
+                    hit = box_pair_exact<G, NOISE>(a, ln.lane, ln.m, part, p.x, p.y, cm0, cm1, ln.env_global, event, s0, kmask) || sure;
             }
             // each mover may use up half of the smallest margin among its own pairs
 #if GPR_PAIR_ENV_MARGIN
@@ -1416,12 +1454,20 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         if (lead && stepped) a.ep_return[ln.env] = done ? 0.f : ret;
     }
 
-    // per-env scalars of the finished transition: gathered per CTA in shared memory and written as contiguous 8-byte
-    // units (one byte per env and flag would otherwise be a 1-byte store per env — harmless in HBM, but when the outputs
-    // live in pinned host memory every such fragment is its own PCIe write: measured 47 us per step for 0.3 MB).
-    // Envs that did not step (NEXT_STEP mode, pending reset) get zeros here and their real values from the auto-reset kernel.
+    // per-env scalars of the finished transition: gathered per CTA in shared memory and written as contiguous 8-byte units
+    // (one byte per env and flag would otherwise be a 1-byte store per env — harmless in HBM, but when the outputs live in
+    // pinned host memory every such fragment is its own PCIe write: measured 47 us per step for 0.3 MB).
+    // NO CTA BARRIER on the common path: every warp drops its slice into shared memory and signs off on a counter; the warp
+    // that signs off LAST writes the CTA's rows.  A warp whose environments have all collided therefore leaves the SM
+    // instead of waiting for the slowest warp of its CTA (the barrier was 1.4 / 2.8 stall cycles per issued instruction of
+    // the circle / box kernel, profiles/r1b_full_planning4.txt, r2_full_planning8box.txt).
+    // Envs that did not step (NEXT_STEP mode, pending reset) get zeros here and their real values from the auto-reset kernel
+    // — which may already be running: in that mode the rows are written behind a real barrier and published afterwards.
     {
-        constexpr int EPC = StepThreads<G>::value / G;  // envs per CTA (>= 8)
+        constexpr int EPC = StepThreads<G>::value / G;  // envs per CTA
+        constexpr int NW = StepThreads<G>::value / 32;  // warps per CTA
+        constexpr int U = EPC >= 8 ? 8 : EPC;           // bytes per flag store unit
+        constexpr int FU = EPC / U;                     // units per flag array
         __shared__ __align__(16) uint8_t s_flag[6][EPC];
         __shared__ __align__(16) float s_rew[EPC];
         const int le = (int)threadIdx.x / G;
@@ -1435,33 +1481,54 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
             s_flag[4][le] = stepped && wc;
             s_flag[5][le] = stepped && oc;
         }
-        __syncthreads();
-        uint8_t* const fo[6] = {a.out.terminated, a.out.truncated, a.out.is_success, a.out.mover_collision, a.out.wall_collision,
-                                a.out.other_collision};
-        const bool whole = env0 + EPC <= a.B;  // (the last CTA may be partial)
-        constexpr int FU = EPC / 8, RU = EPC / 2;  // 8-byte units per flag array / of the reward array
-        const int t = (int)threadIdx.x;
-        if (t < 6 * FU) {
-            const int f = t / FU, k = t % FU;
-            uint8_t* dst = fo[f];
-            if (dst) {
-                dst += env0;
-                if (whole && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0u) {
-                    reinterpret_cast<uint2*>(dst)[k] = reinterpret_cast<const uint2*>(s_flag[f])[k];
+        bool writer;
+        if (a.autoreset == GPR_AUTORESET_NEXT_STEP) {
+            __syncthreads();
+            writer = threadIdx.x < 32u;
+        } else {
+            __syncwarp();
+            unsigned prev = 0u;
+            if (ln.lane == 0) {
+                __threadfence_block();  // this warp's slice before its signature
+                prev = atomicAdd(&s_signed_off, 1u);
+            }
+            writer = __shfl_sync(FULL, prev, 0) == (unsigned)(NW - 1);
+            if (writer) __threadfence_block();  // ... and every other warp's slice before the reads below
+        }
+        if (writer) {
+            uint8_t* const fo[6] = {a.out.terminated, a.out.truncated, a.out.is_success, a.out.mover_collision, a.out.wall_collision,
+                                    a.out.other_collision};
+            const bool whole = env0 + EPC <= a.B;  // (the last CTA may be partial)
+            for (int t = (int)ln.lane; t < 6 * FU; t += 32) {
+                const int f = t / FU, k = t % FU;
+                uint8_t* dst = fo[f];
+                if (!dst) continue;
+                dst += env0 + U * k;
+                const volatile uint8_t* src = &s_flag[f][U * k];
+                if (whole && (reinterpret_cast<uintptr_t>(dst) & (uintptr_t)(U - 1)) == 0u) {
+                    if constexpr (U == 8) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(const_cast<const uint8_t*>(src));
+                    else if constexpr (U == 4) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(const_cast<const uint8_t*>(src));
+                    else if constexpr (U == 2) *reinterpret_cast<uint16_t*>(dst) = *reinterpret_cast<const uint16_t*>(const_cast<const uint8_t*>(src));
+                    else *dst = *src;
                 } else {
-                    for (int i = 8 * k; i < 8 * k + 8; ++i)
-                        if (env0 + i < a.B) dst[i] = s_flag[f][i];
+                    for (int i = 0; i < U; ++i)
+                        if (env0 + U * k + i < a.B) dst[i] = src[i];
                 }
             }
-        }
-        if (t < RU && a.out.reward) {
-            const int k = t;
-            float* dst = a.out.reward + env0;
-            if (whole && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0u) {
-                reinterpret_cast<float2*>(dst)[k] = reinterpret_cast<const float2*>(s_rew)[k];
-            } else {
-                for (int i = 2 * k; i < 2 * k + 2; ++i)
-                    if (env0 + i < a.B) dst[i] = s_rew[i];
+            if (a.out.reward) {
+                float* dst = a.out.reward + env0;
+                if constexpr (EPC >= 2) {
+                    for (int t = (int)ln.lane; t < EPC / 2; t += 32) {
+                        if (whole && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0u) {
+                            reinterpret_cast<float2*>(dst)[t] = reinterpret_cast<const float2*>(s_rew)[t];
+                        } else {
+                            for (int i = 2 * t; i < 2 * t + 2; ++i)
+                                if (env0 + i < a.B) dst[i] = s_rew[i];
+                        }
+                    }
+                } else {
+                    if (ln.lane == 0 && env0 < a.B) dst[0] = s_rew[0];
+                }
             }
         }
     }

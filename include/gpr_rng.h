@@ -7,7 +7,8 @@
  * construction; what is kept is the *distribution* (uniform over the same box, N(0, sigma^2)).
  *
  * This header is therefore a specification of its own, not a restatement of reference code:
- *   - generator: Philox4x32-10 (Salmon et al., SC'11), key = 64-bit seed, counter = (env, event, stream, lane);
+ *   - generator: Philox4x32 (Salmon et al., SC'11), key = 64-bit seed, counter = (env, event, stream, lane); 10 rounds for
+ *     the sensor-noise streams, 7 rounds for the rejection-sampling streams (see gpr_rng_block_sampling);
  *   - uniform coordinate: 32 random bits * 2^-32 in [0,1), `low + (high-low)*u` with separate multiply and add
  *     (numpy's `uniform` does the same with 53 bits; 32 bits resolve 1e-10 m and let one block feed two attempts);
  *   - normal float: Box-Muller whose log / sin / cos are fixed polynomials evaluated with IEEE float32 operations only
@@ -79,13 +80,15 @@ GPR_HD void gpr_mulhilo32(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
 #endif
 }
 
-/* Philox4x32-10. counter = (c0,c1,c2,c3), key = (k0,k1). */
-GPR_HD gpr_u32x4 gpr_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+/* Philox4x32-R. counter = (c0,c1,c2,c3), key = (k0,k1).  R = 10 is the generator's standard strength; R = 7 is the reduced
+ * variant Random123 ships and tests as well (it passes BigCrush; known-answer vectors for both in the test-suite). */
+#define GPR_PHILOX_ROUNDS_SAMPLING 7
+GPR_HD gpr_u32x4 gpr_philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, const int rounds) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         gpr_mulhilo32(M0, c0, &hi0, &lo0);
         gpr_mulhilo32(M1, c2, &hi1, &lo1);
@@ -106,9 +109,21 @@ GPR_HD gpr_u32x4 gpr_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32
     return out;
 }
 
-/* One random block for (env, event, stream, lane) under a 64-bit seed. */
+GPR_HD gpr_u32x4 gpr_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return gpr_philox4x32_r(c0, c1, c2, c3, k0, k1, 10);
+}
+
+/* One random block for (env, event, stream, lane) under a 64-bit seed: the sensor-noise streams. */
 GPR_HD gpr_u32x4 gpr_rng_block(uint64_t seed, uint32_t env_global, uint32_t event, uint32_t stream, uint32_t lane) {
     return gpr_philox4x32_10(env_global, event, stream, lane, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+/* The same for the REJECTION-SAMPLING streams (GPR_RNG_RESET_SAMPLE / GPR_RNG_RESET_OBJECT): Philox4x32-7.  Acceptance of
+ * the reference's all-movers-at-once sampling is ~1 % (planning:369-385), so a reset consumes hundreds of blocks and the
+ * generator is a third of the auto-reset kernel's instructions; the 7-round variant still passes BigCrush (Salmon et al.,
+ * SC'11, table 2) and saves 30 % of them.  (Different streams of one counter space never overlap: the stream id is a
+ * counter word.) */
+GPR_HD gpr_u32x4 gpr_rng_block_sampling(uint64_t seed, uint32_t env_global, uint32_t event, uint32_t stream, uint32_t lane) {
+    return gpr_philox4x32_r(env_global, event, stream, lane, (uint32_t)seed, (uint32_t)(seed >> 32), GPR_PHILOX_ROUNDS_SAMPLING);
 }
 
 /* 53-bit uniform in [0,1) from two words. */
@@ -124,7 +139,7 @@ GPR_HD double gpr_uniform32(uint32_t w) { return (double)w * (1.0 / 4294967296.0
    separately like numpy's Generator.uniform */
 GPR_HD void gpr_sample_xy(uint64_t seed, uint32_t env_global, uint32_t event, uint32_t base, uint32_t kind, uint32_t t,
                           uint32_t lane, double* ux, double* uy) {
-    gpr_u32x4 r = gpr_rng_block(seed, env_global, event, base + 2u * (t >> 1) + kind, lane);
+    gpr_u32x4 r = gpr_rng_block_sampling(seed, env_global, event, base + 2u * (t >> 1) + kind, lane);
     *ux = gpr_uniform32(r.v[2u * (t & 1u)]);
     *uy = gpr_uniform32(r.v[2u * (t & 1u) + 1u]);
 }

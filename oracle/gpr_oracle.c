@@ -1192,6 +1192,10 @@ void gpro_compute_reward(const gpr_config* c, int batch, const float* achieved, 
 }
 
 /* --- small helpers exported for the tests ---------------------------------------------------------------------------- */
+void gpro_philox_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, int rounds, uint32_t out[4]) {
+    gpr_u32x4 r = gpr_philox4x32_r(c0, c1, c2, c3, k0, k1, rounds);
+    memcpy(out, r.v, sizeof(r.v));
+}
 void gpro_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
     gpr_u32x4 r = gpr_philox4x32_10(c0, c1, c2, c3, k0, k1);
     memcpy(out, r.v, sizeof(r.v));

@@ -147,9 +147,9 @@ def compute_reward(cfg, achieved, desired, mover_collision=None, wall_collision=
     return r, t.astype(bool)
 
 
-def philox(c, k):
+def philox(c, k, rounds=10):
     out = np.zeros(4, dtype=np.uint32)
-    lib().gpro_philox(*[ctypes.c_uint32(int(x)) for x in c], *[ctypes.c_uint32(int(x)) for x in k], _p(out, ctypes.c_uint32))
+    lib().gpro_philox_r(*[ctypes.c_uint32(int(x)) for x in c], *[ctypes.c_uint32(int(x)) for x in k], ctypes.c_int(rounds), _p(out, ctypes.c_uint32))
     return out
 
 

@@ -176,7 +176,7 @@ def test_obstacle_rules_against_reference_vectors():
 
 
 def test_philox_known_answers():
-    """Random123 kat_vectors for philox4x32-10."""
+    """Random123 kat_vectors for philox4x32-10 and philox4x32-7."""
     assert oracle.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
     assert oracle.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2).tolist() == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
     assert oracle.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]).tolist() == [
@@ -185,6 +185,11 @@ def test_philox_known_answers():
         0x5001E420,
         0x24126EA1,
     ]
+    # philox4x32-7 (the rejection-sampling streams, gpr_rng_block_sampling): Random123's kat_vectors for 7 rounds
+    assert oracle.philox([0, 0, 0, 0], [0, 0], 7).tolist() == [0x5F6FB709, 0x0D893F64, 0x4F121F81, 0x4F730A48]
+    assert oracle.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, 7).tolist() == [0x5207DDC2, 0x45165E59, 0x4D8EE751, 0x8C52F662]
+    assert oracle.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0], 7).tolist() == [
+        0x4DFCCABA, 0x190A87F0, 0xC47362BA, 0xB6B5242A]
 
 
 def test_portable_normals_are_standard_normal():
