@@ -313,13 +313,19 @@ def run_b200(args, wl):
         N, J = int(env.cfg.num_movers), int(env.cfg.learn_jerk)
         abytes = algorithmic_bytes_per_env_step(w['kind'], N, J)
         k_main, k_other_key, k_other = KERNEL_NAMES[w['kind']]
-        achieved = abytes * B / (kt['step_kernel_ms'] * 1e-3) / 1e9
+        # the dominant kernel: planning -> the fused step kernel; pushing -> the step is split by population into the free
+        # kernel and the contact kernel (each env runs its 40 cycles in one or both), so both launches count
+        dom_ms = kt['step_kernel_ms'] + (kt['autoreset_kernel_ms'] if w['kind'] == 'pushing' else 0.0)
+        if w['kind'] == 'pushing':
+            k_main = 'pushing_step_kernel + pushing_contact_kernel'
+        achieved = abytes * B / (dom_ms * 1e-3) / 1e9
         res = {
             'env': env, 'value': world * B * steps / (best * 1e-3), 'ms_per_step': best / steps, 'blocks_ms_per_step': [b / steps for b in blocks],
             'launches': launches, 'wall': wall, 'clocks': ctx.summary(), 'abytes': abytes,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
                          'algorithmic_bytes_per_env_step': abytes, 'algorithmic_bytes_per_launch': abytes * B, 'kernel': k_main,
-                         'kernel_ms': kt['step_kernel_ms'], 'other_kernels_ms': {k_other_key: kt['autoreset_kernel_ms']},
+                         'kernel_ms': dom_ms, 'kernels_ms': {'step': kt['step_kernel_ms'], k_other_key: kt['autoreset_kernel_ms']},
+                         'other_kernels_ms': {} if w['kind'] == 'pushing' else {k_other_key: kt['autoreset_kernel_ms']},
                          'whole_step_frac': abytes * B / (best / steps * 1e-3) / 1e9 / peak},
         }
         return res

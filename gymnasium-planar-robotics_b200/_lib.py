@@ -38,6 +38,9 @@ EXPORTED_SYMBOLS = (
     'gpr_reset_failures',
     'gpr_kernel_times',
     'gpr_launch_count',
+    'gpr_invalidate_outputs',
+    'gpr_debug_build',
+    'gpr_debug_errors',
 )
 
 _lib = None
@@ -81,6 +84,8 @@ def load():
     lib.gpr_kernel_times.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
     lib.gpr_launch_count.argtypes = [vp]
     lib.gpr_launch_count.restype = u64
+    lib.gpr_invalidate_outputs.argtypes = [vp]
+    lib.gpr_debug_errors.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     if lib.gpr_abi_version() != GPR_ABI_VERSION or lib.gpr_config_bytes() != ctypes.sizeof(GprConfig):
         raise GprError(
             f'ABI mismatch: library ABI {lib.gpr_abi_version()} / gpr_config {lib.gpr_config_bytes()} bytes, '

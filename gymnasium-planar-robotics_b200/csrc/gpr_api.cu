@@ -57,6 +57,7 @@ struct gpr_handle {
     float* ep_return = nullptr;
     double* stats = nullptr;
     uint32_t* fail_count = nullptr;
+    uint32_t* debug_errors = nullptr;  // [DBG_NUM_SLOTS], counted by GPR_DEBUG_BOUNDS builds
     unsigned long long* reset_list = nullptr;  // auto-reset work list (see planning_autoreset_kernel)
     unsigned long long* reset_count = nullptr;  // [2] control words (reported warps, reserved slots), then [2] uint32 cursors
     int parity = 0;
@@ -193,7 +194,7 @@ extern "C" void gpr_destroy(gpr_handle* h) {
     cudaGetDevice(&prev);
     cudaSetDevice(h->device);
     void* ptrs[] = {h->pos, h->vel, h->acc, h->goal, h->elapsed, h->rng, h->needs_reset, h->ep_return, h->stats,
-                    h->fail_count, h->reset_list, h->reset_count, h->act, h->mover_rot, h->obj_pos, h->obj_vel, h->cx, h->cy, h->c_wall, h->c_mover,
+                    h->fail_count, h->debug_errors, h->reset_list, h->reset_count, h->act, h->mover_rot, h->obj_pos, h->obj_vel, h->cx, h->cy, h->c_wall, h->c_mover,
                     h->cell, h->d_stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -251,6 +252,7 @@ extern "C" int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_ha
     TRY(dalloc(&h->ep_return, B));
     TRY(dalloc(&h->stats, 6));
     TRY(dalloc(&h->fail_count, 1));
+    TRY(dalloc(&h->debug_errors, DBG_NUM_SLOTS));
     TRY(dalloc(&h->reset_list, B));
     CU(cudaMemset(h->reset_list, 0xFF, std::max<size_t>(B, 1) * sizeof(unsigned long long)));  // all ones: slot not published
     TRY(dalloc(&h->reset_count, 4));
@@ -421,6 +423,7 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     a.ep_return = h->ep_return;
     a.stats = h->stats;
     a.fail_count = h->fail_count;
+    a.debug_errors = h->debug_errors;
     a.reset_list = h->reset_list;
     a.reset_ctl = h->reset_count;
     a.reset_cursor = reinterpret_cast<uint32_t*>(h->reset_count + 2);
@@ -498,6 +501,7 @@ static PushArgs push_args(const gpr_handle* h, const gpr_outputs* out) {
     a.ep_return = h->ep_return;
     a.stats = h->stats;
     a.fail_count = h->fail_count;
+    a.debug_errors = h->debug_errors;
     a.queue = h->reset_list;  // (the planning env's auto-reset work list: same size, unused by the pushing env)
     a.queue_ctl = h->reset_count;
     a.queue_cursor = reinterpret_cast<uint32_t*>(h->reset_count + 2);
@@ -589,7 +593,16 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
         CU(launch_plan(h, PLAN_STEP, a, s));
         if (te) CU(cudaEventRecord(te[1], s));
         if (h->cfg.autoreset_mode != GPR_AUTORESET_OFF) {
-            CU(launch_plan(h, PLAN_AUTORESET, a, s));
+            const cudaError_t ae = launch_plan(h, PLAN_AUTORESET, a, s);
+            if (ae != cudaSuccess) {
+                // the step kernel has published finished envs that nobody will consume: put the work list of this parity back
+                // into its empty state (after the step kernel, in stream order) so the next step starts from a clean list;
+                // the finished envs keep their terminal state and must be reset by the caller
+                cudaMemsetAsync(h->reset_list, 0xFF, sizeof(unsigned long long) * (size_t)h->cfg.num_envs, s);
+                cudaMemsetAsync(h->reset_count, 0, 4 * sizeof(unsigned long long), s);
+                h->goal_dirty = true;
+                return fail(GPR_ERR_CUDA, "auto-reset kernel launch: %s", cudaGetErrorString(ae));
+            }
             h->parity ^= 1;
             h->launches += 1;
         }
@@ -701,12 +714,21 @@ struct HostRoute {
     void* pinned[kOutSlots];  // staged field whose destination is page-locked: the copy engine writes it directly
 };
 
-// GPR_HOST_IO=dma: results of *_host calls always go through device staging and the copy engine (into the caller's buffer
-// when it is page-locked), never through zero-copy stores.  For hosts where SM-issued PCIe writes scale badly.
+// How the results of *_host calls reach page-locked caller buffers:
+//   zero-copy  the kernels store straight into the buffers over PCIe (fastest on an otherwise idle host: B200, 65,536 envs,
+//              192M vs 119M env-steps/s)
+//   dma        device staging, then the copy engine writes the caller's buffers (faster when several GPUs write into one
+//              host at once — 8 ranks: 497M vs 436M env-steps/s in total: SM-issued PCIe writes of 8 GPUs contend in the host)
+// GPR_HOST_IO=zerocopy | dma forces one; the default `auto` takes dma when this process is one of several ranks on the host
+// (LOCAL_WORLD_SIZE / WORLD_SIZE > 1, as torchrun exports them) and zero-copy otherwise.  Read once per process.
 static bool host_io_dma() {
     static const bool v = [] {
         const char* e = getenv("GPR_HOST_IO");
-        return e && strcmp(e, "dma") == 0;
+        if (e && strcmp(e, "dma") == 0) return true;
+        if (e && (strcmp(e, "zerocopy") == 0 || strcmp(e, "zc") == 0)) return false;
+        const char* lw = getenv("LOCAL_WORLD_SIZE");
+        const char* w = lw ? lw : getenv("WORLD_SIZE");
+        return w && atoi(w) > 1;
     }();
     return v;
 }
@@ -869,6 +891,46 @@ extern "C" int gpr_episode_stats(gpr_handle* h, double* dst, int reset_after, vo
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaMemcpyAsync(dst, h->stats, 6 * sizeof(double), cudaMemcpyDeviceToDevice, s));
     if (reset_after) CU(cudaMemsetAsync(h->stats, 0, 6 * sizeof(double), s));
+    return GPR_OK;
+}
+
+extern "C" int gpr_invalidate_outputs(gpr_handle* h) {
+    if (!h) return fail(GPR_ERR_INVALID_ARG, "handle is NULL");
+    h->goal_dirty = true;
+    h->goal_ptr = nullptr;
+    return GPR_OK;
+}
+
+extern "C" int gpr_debug_build(void) {
+#ifdef GPR_DEBUG_BOUNDS
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+extern "C" int gpr_debug_errors(gpr_handle* h, uint32_t* host_counts) {
+    if (!h || !host_counts) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(h->device);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_counts, h->debug_errors, DBG_NUM_SLOTS * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    // host-side invariants of the work list after a completed step: every slot handed back ("empty" pattern, planning) and
+    // the consumers' cursor at or beyond the published count of the step that just ran (slot 6 / 7)
+    host_counts[6] = host_counts[7] = 0;
+    const size_t B = (size_t)h->cfg.num_envs;
+    unsigned long long ctl[4];
+    CU(cudaMemcpy(ctl, h->reset_count, sizeof(ctl), cudaMemcpyDeviceToHost));
+    const int last = h->parity ^ 1;  // the buffer the last step used
+    const uint32_t* cur = reinterpret_cast<const uint32_t*>(ctl + 2);
+    const unsigned long long published = h->cfg.env_kind == GPR_ENV_PLANNING ? (ctl[last] & 0xffffffffull) : ctl[last];
+    if (published > B) host_counts[7] += 1;
+    if (h->cfg.autoreset_mode != GPR_AUTORESET_OFF || h->cfg.env_kind == GPR_ENV_PUSHING)
+        if ((unsigned long long)cur[last] < published) host_counts[7] += 1;
+    if (h->cfg.env_kind == GPR_ENV_PLANNING) {
+        std::vector<unsigned long long> list(B);
+        CU(cudaMemcpy(list.data(), h->reset_list, B * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < B; ++i) host_counts[6] += list[i] != ~0ull;
+    }
     return GPR_OK;
 }
 

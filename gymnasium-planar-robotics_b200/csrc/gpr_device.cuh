@@ -39,6 +39,30 @@
 #define GPR_COLD_CAT(x) GPR_COLD_##x
 #define GPR_COLD(flag) GPR_COLD_CAT(flag)
 
+// GPR_DEBUG_BOUNDS (csrc/Makefile target `debug` -> libgpr_b200_dbg.so): compute-sanitizer is closed on this GPU pool, so a
+// debug build range-checks every index the kernels derive for global memory — env / mover indices under ragged batch
+// sizes, work-list slots and entries of the streamed auto-reset and of the pushing contact queue, output rows — into a
+// device error counter that gpr_debug_errors() reads (tests/test_gpu_debug_bounds.py).  A violating access is SKIPPED in
+// the debug build where that is cheap, and always counted.  The release build compiles the checks away.
+#ifdef GPR_DEBUG_BOUNDS
+#define GPR_CHECK(args, cond, slot)                                   \
+    do {                                                              \
+        if (!(cond)) atomicAdd((args).debug_errors + (slot), 1u);     \
+    } while (0)
+#else
+#define GPR_CHECK(args, cond, slot) ((void)0)
+#endif
+// error slots
+enum : int {
+    DBG_LANE_INDEX = 0,    // a lane's (env, mover) index out of [0, B*N)
+    DBG_LIST_SLOT = 1,     // work-list / queue slot out of [0, B)
+    DBG_LIST_ENTRY = 2,    // work-list / queue entry names an env out of [0, B) (or a cycle out of range)
+    DBG_LIST_CLAIM = 3,    // consumer claimed past the published count
+    DBG_OUTPUT_ROW = 4,    // output row out of [0, B)
+    DBG_SHARED_INDEX = 5,  // shared-memory staging index out of range
+    DBG_NUM_SLOTS = 8
+};
+
 namespace gpr {
 
 constexpr unsigned FULL = 0xffffffffu;

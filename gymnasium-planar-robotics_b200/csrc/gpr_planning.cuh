@@ -80,6 +80,7 @@ struct PlanArgs {
     float* ep_return;
     double* stats;         // 6 accumulators, see gpr_episode_stats
     uint32_t* fail_count;  // number of resets whose rejection loop hit max_reset_attempts
+    uint32_t* debug_errors;  // [DBG_NUM_SLOTS] GPR_DEBUG_BOUNDS builds only (see gpr_device.cuh)
     // auto-reset work list: the step kernel appends finished envs, the auto-reset kernel consumes them — WHILE the step
     // kernel is still running when the two are launched as a programmatic dependent pair (see planning_autoreset_kernel).
     unsigned long long* reset_list;  // [B]  (RNG event << 32 | env); all ones = slot not published (consumers restore it)
@@ -123,6 +124,7 @@ __device__ __forceinline__ Lane<G> make_lane(const PlanArgs& a) {
     ln.active = ln.env_ok && ln.m < a.N;
     ln.idx = (size_t)ln.env * (size_t)a.N + (size_t)ln.m;
     ln.env_global = a.env_base + (uint32_t)ln.env;
+    GPR_CHECK(a, !ln.active || (ln.env >= 0 && ln.idx < (size_t)a.B * (size_t)a.N), DBG_LANE_INDEX);
     return ln;
 }
 
@@ -1421,6 +1423,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         unsigned long long t = 0ull;
         if (ln.lane == 0) t = atomicAdd(a.reset_ctl + a.parity, (1ull << 32) | (unsigned long long)__popc(leaders));
         const unsigned slot0 = (unsigned)__shfl_sync(FULL, t, 0);
+        GPR_CHECK(a, !(need && ln.m == 0) || slot0 + __popc(leaders & ((1u << ln.lane) - 1u)) < (unsigned)a.B, DBG_LIST_SLOT);
         if (need && ln.m == 0)
             *reinterpret_cast<volatile unsigned long long*>(a.reset_list + slot0 + __popc(leaders & ((1u << ln.lane) - 1u))) =
                 ((unsigned long long)event << 32) | (unsigned long long)(uint32_t)ln.env;
@@ -1472,6 +1475,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         __shared__ __align__(16) float s_rew[EPC];
         const int le = (int)threadIdx.x / G;
         const int env0 = (int)blockIdx.x * EPC;
+        GPR_CHECK(a, le >= 0 && le < EPC, DBG_SHARED_INDEX);
         if (ln.m == 0) {
             s_rew[le] = stepped ? reward : 0.f;
             s_flag[0][le] = stepped && term;
@@ -1503,6 +1507,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
                 const int f = t / FU, k = t % FU;
                 uint8_t* dst = fo[f];
                 if (!dst) continue;
+                GPR_CHECK(a, !whole || env0 + U * k + U <= a.B, DBG_OUTPUT_ROW);
                 dst += env0 + U * k;
                 const volatile uint8_t* src = &s_flag[f][U * k];
                 if (whole && (reinterpret_cast<uintptr_t>(dst) & (uintptr_t)(U - 1)) == 0u) {
@@ -1634,6 +1639,7 @@ __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) plan
         i0 = __shfl_sync(FULL, i0, 0);
         nb = __shfl_sync(FULL, nb, 0);
         if (nb == 0) break;
+        GPR_CHECK(a, lane != 0 || ((unsigned long long)i0 + nb <= (unsigned long long)(uint32_t)ld_acquire_u64(a.reset_ctl + a.parity) && i0 + nb <= (uint32_t)a.B), DBG_LIST_CLAIM);
         Lane<G> ln;
         ln.lane = lane;
         ln.gmask = group_mask<G>(lane);
@@ -1650,6 +1656,10 @@ __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) plan
         if (ln.env_ok && ln.m == 0) a.reset_list[i0 + grp] = ~0ull;  // leave the list empty for the next step
         __threadfence();  // (the producer's early desired_goal store is ordered before the row written below)
         ln.env = (int)(uint32_t)entry;
+        GPR_CHECK(a, !ln.env_ok || (uint32_t)entry < (uint32_t)a.B, DBG_LIST_ENTRY);
+#ifdef GPR_DEBUG_BOUNDS
+        if (ln.env_ok && (uint32_t)entry >= (uint32_t)a.B) ln.env_ok = false;  // (counted above; do not touch memory with it)
+#endif
         ln.active = ln.env_ok && ln.m < a.N;
         ln.idx = (size_t)ln.env * (size_t)a.N + (size_t)ln.m;
         ln.env_global = a.env_base + (uint32_t)ln.env;

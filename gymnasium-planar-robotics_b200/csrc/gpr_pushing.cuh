@@ -49,6 +49,7 @@ struct PushArgs {
     float* ep_return;
     double* stats;
     uint32_t* fail_count;
+    uint32_t* debug_errors;  // [DBG_NUM_SLOTS] GPR_DEBUG_BOUNDS builds only (see gpr_device.cuh)
     int write_goal;  // see PlanArgs
     // work queue of the envs that entered the contact regime (see pushing_step_kernel), double-buffered by step parity
     unsigned long long* queue;      // [B] (cycle << 32 | env)
@@ -512,6 +513,7 @@ __global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(c
         unsigned long long t = 0ull;
         if (lane == 0) t = atomicAdd(a.queue_ctl + a.parity, (unsigned long long)__popc(pm));
         const unsigned slot0 = (unsigned)__shfl_sync(FULL, t, 0);
+        GPR_CHECK(a, !parked || (slot0 + __popc(pm & ((1u << lane) - 1u)) < (unsigned)a.B && e < a.B), DBG_LIST_SLOT);
         if (parked) {
             push_store(a, e, s);
             a.queue[slot0 + __popc(pm & ((1u << lane) - 1u))] = ((unsigned long long)(unsigned)parked_at << 32) | (unsigned long long)(uint32_t)e;
@@ -550,6 +552,8 @@ __global__ void __launch_bounds__(kPushContactCta, GPR_PUSH_CONTACT_MINB) pushin
             const unsigned long long entry = a.queue[base + lane];
             e = (int)(uint32_t)entry;
             cyc0 = (int)(entry >> 32);
+            GPR_CHECK(a, (uint32_t)entry < (uint32_t)a.B && cyc0 >= 0 && cyc0 < a.num_cycles, DBG_LIST_ENTRY);
+            GPR_CHECK(a, base + lane < (uint32_t)a.B, DBG_LIST_SLOT);
             push_load(a, e, s);
             event = a.rng[e];
             elapsed = a.elapsed[e];

@@ -281,6 +281,16 @@ class BatchedCore:
         n = max(out[2], 1.0)
         return {'steps': out[2], 'step_kernel_ms': out[0] / n, 'autoreset_kernel_ms': out[1] / n}
 
+    def debug_errors(self) -> list[int]:
+        """``gpr_debug_errors``: the 8 counters of the bounds-checking build (all 0 in a release build except the two
+        host-side work-list invariants [6], [7])."""
+        c = (ctypes.c_uint32 * 8)()
+        _lib.check(self.lib.gpr_debug_errors(self.handle, c))
+        return [int(x) for x in c]
+
+    def invalidate_outputs(self) -> None:
+        _lib.check(self.lib.gpr_invalidate_outputs(self.handle))
+
     def reset_failures(self) -> int:
         c = ctypes.c_uint32()
         _lib.check(self.lib.gpr_reset_failures(self.handle, ctypes.byref(c)))

@@ -162,7 +162,10 @@ typedef struct gpr_config {
  * reset); the other rows keep what an earlier call wrote.  For callers that pass the SAME desired_goal buffer to every
  * call (the Python env classes do): it takes a quarter off the result traffic, which is what bounds *_host calls.
  * gpr_reset always writes the rows of the environments it resets; after gpr_set_state with a goal, the next step writes
- * every row once. */
+ * every row once.
+ * The library recognises "the same buffer" by its ADDRESS: a caller that frees and re-allocates its desired_goal buffer (a
+ * caching allocator may well hand back the same address) must call gpr_invalidate_outputs() before the next step, which
+ * then writes every row once.  Callers that cannot guarantee a persistent buffer should leave this flag clear. */
 #define GPR_OUT_GOAL_ON_CHANGE 1
 
 /* Per-step results. Device pointers (host pointers for *_host calls), caller-owned, row-major; NULL = do not write.
@@ -247,9 +250,10 @@ GPR_API int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* out,
  * buffers are valid.  `host_out` holds host pointers.  Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch
  * pinned tensors) are read and written by the kernels IN PLACE through their device alias (zero-copy: result stores cross
  * PCIe while the rest of the grid still computes); pageable buffers are staged through the handle's pinned mirror.
- * Environment variable GPR_HOST_IO=dma (read once per process) routes the results of page-locked buffers through device
- * staging and the copy engine instead — slower on an otherwise idle host (B200: 192M -> 119M env-steps/s at 65,536
- * envs), faster when many GPUs write into one host at once (8 ranks: 436M -> 497M). */
+ * Environment variable GPR_HOST_IO (read once per process): `zerocopy` as above; `dma` routes the results of page-locked
+ * buffers through device staging and the copy engine instead — slower on an otherwise idle host (B200: 192M -> 119M
+ * env-steps/s at 65,536 envs), faster when many GPUs write into one host at once (8 ranks: 436M -> 497M); unset = `auto`:
+ * dma when the process is one of several ranks on the host (LOCAL_WORLD_SIZE / WORLD_SIZE > 1), zero-copy otherwise. */
 GPR_API int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out);
 GPR_API int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_outputs* host_out);
 
@@ -282,6 +286,18 @@ GPR_API int gpr_reset_failures(gpr_handle* h, uint32_t* host_count);
  * [0] total ms of the step kernel, [1] total ms of the auto-reset kernel, [2] number of gpr_step calls covered, and the
  * accumulation restarts.  enable == 0 stops recording. */
 GPR_API int gpr_kernel_times(gpr_handle* h, int enable, double* host_ms);
+
+/* GPR_OUT_GOAL_ON_CHANGE: forget which desired_goal buffer has been written — the next gpr_step writes every row. */
+GPR_API int gpr_invalidate_outputs(gpr_handle* h);
+
+/* Memory-safety aid (compute-sanitizer is not available on every pool): a library built with -DGPR_DEBUG_BOUNDS
+ * (csrc/Makefile target `debug` -> libgpr_b200_dbg.so; gpr_debug_build() returns 1) range-checks every index its kernels
+ * derive for global memory and counts violations.  gpr_debug_errors synchronises the device and fills host_counts[8]:
+ * [0] lane (env, mover) index, [1] work-list slot, [2] work-list entry, [3] consumer claim beyond the published count,
+ * [4] output row, [5] shared-memory staging index (all always 0 in a release build), [6] work-list slots not handed back
+ * after the last step, [7] work-list counters inconsistent (checked on the host in every build). */
+GPR_API int gpr_debug_build(void);
+GPR_API int gpr_debug_errors(gpr_handle* h, uint32_t* host_counts);
 
 /* Number of kernels this library has launched on behalf of the handle (bench "gpu_launches" evidence). */
 GPR_API uint64_t gpr_launch_count(const gpr_handle* h);

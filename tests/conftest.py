@@ -12,6 +12,7 @@ for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
     config.addinivalue_line('markers', 'reference: needs the read-only reference mount (/root/reference); skipped elsewhere')
+    config.addinivalue_line('markers', 'slow: long soak run (minutes of GPU time); deselect with -m "gpu and not slow"')
 
 
 def pytest_collection_modifyitems(config, items):
