@@ -368,6 +368,7 @@ def planning_config(
     seed: int = 0,
     reference_quirks: bool = False,
     goal_output_on_change: bool = True,
+    float64_outputs: bool = False,
     obstacles=None,
     extra_bodies=None,
 ) -> tuple[GprConfig, dict[str, Any]]:
@@ -456,7 +457,8 @@ def planning_config(
     d['goal_dim'] = num_movers * 2
     d['action_dim'] = num_movers * 2
     # the env classes hand the same output buffers to every call: desired_goal rows are rewritten only when they change
-    cfg.output_flags = 1 if goal_output_on_change else 0  # GPR_OUT_GOAL_ON_CHANGE
+    # float64_outputs (GPR_OUT_FLOAT64): observation / goal arrays in the reference's dtype (the single-env classes set it)
+    cfg.output_flags = (1 if goal_output_on_change else 0) | (2 if float64_outputs else 0)
     return cfg, d
 
 
@@ -485,6 +487,7 @@ def pushing_config(
     seed: int = 0,
     contact_iterations: int = 8,
     goal_output_on_change: bool = True,
+    float64_outputs: bool = False,
 ) -> tuple[GprConfig, dict[str, Any]]:
     """kwargs of ``BenchmarkPushingEnv`` (pushing:154-169) -> ``gpr_config``.
 
@@ -557,5 +560,6 @@ def pushing_config(
     d['goal_dim'] = 2
     d['action_dim'] = 2
     # the env classes hand the same output buffers to every call: desired_goal rows are rewritten only when they change
-    cfg.output_flags = 1 if goal_output_on_change else 0  # GPR_OUT_GOAL_ON_CHANGE
+    # float64_outputs (GPR_OUT_FLOAT64): observation / goal arrays in the reference's dtype (the single-env classes set it)
+    cfg.output_flags = (1 if goal_output_on_change else 0) | (2 if float64_outputs else 0)
     return cfg, d

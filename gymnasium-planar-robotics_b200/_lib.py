@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     'gpr_get_seed',
     'gpr_set_seed',
     'gpr_compute_reward',
+    'gpr_compute_reward_f64',
     'gpr_episode_stats',
     'gpr_reset_failures',
     'gpr_kernel_times',
@@ -79,6 +80,7 @@ def load():
     lib.gpr_get_seed.argtypes = [vp, ctypes.POINTER(u64)]
     lib.gpr_set_seed.argtypes = [vp, u64]
     lib.gpr_compute_reward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.gpr_compute_reward_f64.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.gpr_episode_stats.argtypes = [vp, vp, i32, vp]
     lib.gpr_reset_failures.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     lib.gpr_kernel_times.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]

@@ -429,6 +429,7 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     a.reset_cursor = reinterpret_cast<uint32_t*>(h->reset_count + 2);
     a.overlap = (h->timing || no_overlap()) ? 0 : 1;  // (an event between the two launches would break the pairing)
     a.parity = h->parity;
+    a.out_f64 = (c.output_flags & GPR_OUT_FLOAT64) != 0;
     if (out) a.out = *out;
     return a;
 }
@@ -506,6 +507,7 @@ static PushArgs push_args(const gpr_handle* h, const gpr_outputs* out) {
     a.queue_ctl = h->reset_count;
     a.queue_cursor = reinterpret_cast<uint32_t*>(h->reset_count + 2);
     a.parity = h->parity;
+    a.out_f64 = (c.output_flags & GPR_OUT_FLOAT64) != 0;
     if (out) a.out = *out;
     return a;
 }
@@ -661,9 +663,10 @@ static StageLayout stage_layout(const gpr_handle* h) {
         return o;
     };
     L.off_action = take(B * h->action_dim * sizeof(float));
-    const size_t sz[kOutSlots] = {B * h->obs_dim * sizeof(float), B * h->goal_dim * sizeof(float), B * h->goal_dim * sizeof(float),
+    const size_t el = (h->cfg.output_flags & GPR_OUT_FLOAT64) ? sizeof(double) : sizeof(float);  // observation / goal arrays
+    const size_t sz[kOutSlots] = {B * h->obs_dim * el, B * h->goal_dim * el, B * h->goal_dim * el,
                                   B * sizeof(float), B, B, B, B, B,
-                                  B * h->obs_dim * sizeof(float), B * h->goal_dim * sizeof(float), B * h->goal_dim * sizeof(float), B};
+                                  B * h->obs_dim * el, B * h->goal_dim * el, B * h->goal_dim * el, B};
     for (int k = 0; k < kOutSlots; ++k) {
         L.bytes[k] = sz[k];
         L.off[k] = take(sz[k]);
@@ -879,7 +882,20 @@ extern "C" int gpr_compute_reward(gpr_handle* h, int batch, const float* achieve
     if (batch < 0) return fail(GPR_ERR_INVALID_ARG, "batch < 0");
     if (batch == 0) return GPR_OK;
     DeviceGuard g(h->device);
-    CU(launch_compute_reward(h->cfg.env_kind, h->cfg.num_movers, batch, h->cfg.threshold_pos, achieved, desired, mover_collision,
+    CU(launch_compute_reward(h->cfg.env_kind, h->cfg.num_movers, batch, h->cfg.threshold_pos, achieved, desired, false, mover_collision,
+                             wall_collision, reward, terminated, (cudaStream_t)stream));
+    h->launches += 1;
+    return GPR_OK;
+}
+
+extern "C" int gpr_compute_reward_f64(gpr_handle* h, int batch, const double* achieved, const double* desired,
+                                      const uint8_t* mover_collision, const uint8_t* wall_collision, float* reward,
+                                      uint8_t* terminated, void* stream) {
+    if (!h || !achieved || !desired) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
+    if (batch < 0) return fail(GPR_ERR_INVALID_ARG, "batch < 0");
+    if (batch == 0) return GPR_OK;
+    DeviceGuard g(h->device);
+    CU(launch_compute_reward(h->cfg.env_kind, h->cfg.num_movers, batch, h->cfg.threshold_pos, achieved, desired, true, mover_collision,
                              wall_collision, reward, terminated, (cudaStream_t)stream));
     h->launches += 1;
     return GPR_OK;

@@ -20,7 +20,7 @@ enum PushKernel { PUSH_STEP = 0, PUSH_RESET = 1, PUSH_CONTACT = 2 };
 cudaError_t launch_push(PushKernel which, bool box, bool noise, const PushArgs& a, int num_sms, cudaStream_t s);
 
 // gpr_misc_kernels.cu
-cudaError_t launch_compute_reward(int kind, int N, int batch, double threshold, const float* achieved, const float* desired,
+cudaError_t launch_compute_reward(int kind, int N, int batch, double threshold, const void* achieved, const void* desired, bool f64,
                                   const uint8_t* mcol, const uint8_t* wcol, float* reward, uint8_t* terminated, cudaStream_t s);
 
 }  // namespace gpr

@@ -91,6 +91,7 @@ struct PlanArgs {
     int overlap;             // host side: launch the auto-reset kernel as the step kernel's programmatic dependent
     int parity;
     int write_goal;  // 0: the step kernel leaves desired_goal rows of envs that were not reset alone (GPR_OUT_GOAL_ON_CHANGE)
+    int out_f64;     // GPR_OUT_FLOAT64: observation / goal outputs are double arrays
     // per-call I/O
     const float2* action;
     gpr_outputs out;
@@ -434,11 +435,28 @@ __device__ __forceinline__ void observe(const PlanArgs& a, const Lane<G>& ln, ui
     reached_cnt = __popc(__ballot_sync(FULL, reached) & ln.gmask);
 }
 
+// one (x, y) pair of an output row: element index `pair` of a float2 (or, with GPR_OUT_FLOAT64, double2) array
+template <class Args>
+__device__ __forceinline__ void store_pair(const Args& a, float* base, size_t pair, double x, double y) {
+    if (a.out_f64) reinterpret_cast<double2*>(base)[pair] = make_double2(x, y);
+    else reinterpret_cast<float2*>(base)[pair] = make_float2((float)x, (float)y);
+}
+
 template <int G>
 __device__ __forceinline__ void store_obs(const PlanArgs& a, const Lane<G>& ln, float* O, float* AG, float* DG, double2 ov,
                                           double2 acc, double2 ag, double2 goal) {
     if (!ln.active) return;
     const int N = a.N;
+    if (a.out_f64) {  // (cold: the vector envs use float32 outputs)
+        if (O) {
+            const size_t rowp = (size_t)ln.env * (size_t)(N * (1 + a.learn_jerk));
+            store_pair(a, O, rowp + ln.m, ov.x, ov.y);
+            if (a.learn_jerk) store_pair(a, O, rowp + N + ln.m, acc.x, acc.y);
+        }
+        if (AG) store_pair(a, AG, ln.idx, ag.x, ag.y);
+        if (DG) store_pair(a, DG, ln.idx, goal.x, goal.y);
+        return;
+    }
     if (O) {
         const size_t row = (size_t)ln.env * (size_t)(2 * N * (1 + a.learn_jerk));
         reinterpret_cast<float2*>(O + row)[ln.m] = make_float2((float)ov.x, (float)ov.y);
@@ -1181,8 +1199,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         u.y = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
         // desired_goal does not change during a step: store it now, so that (when the output lives in pinned host memory)
         // this part of the result traffic crosses PCIe under the 40-cycle loop instead of in the burst at the end
-        if (!pending_reset && a.write_goal && a.out.desired_goal)
-            reinterpret_cast<float2*>(a.out.desired_goal)[ln.idx] = make_float2((float)goal.x, (float)goal.y);
+        if (!pending_reset && a.write_goal && a.out.desired_goal) store_pair(a, a.out.desired_goal, ln.idx, goal.x, goal.y);
     }
 
     // ------------------------------------------------------------------ the 40-cycle loop (basic:1879-1905)

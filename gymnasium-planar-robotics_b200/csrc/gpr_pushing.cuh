@@ -51,6 +51,7 @@ struct PushArgs {
     uint32_t* fail_count;
     uint32_t* debug_errors;  // [DBG_NUM_SLOTS] GPR_DEBUG_BOUNDS builds only (see gpr_device.cuh)
     int write_goal;  // see PlanArgs
+    int out_f64;     // GPR_OUT_FLOAT64
     // work queue of the envs that entered the contact regime (see pushing_step_kernel), double-buffered by step parity
     unsigned long long* queue;      // [B] (cycle << 32 | env)
     unsigned long long* queue_ctl;  // [2] entries appended
@@ -171,14 +172,13 @@ __device__ __forceinline__ void push_observe(const PushArgs& a, const PushState&
 __device__ __forceinline__ void push_store_obs(const PushArgs& a, int e, float* O, float* AG, float* DG, const double (&obs)[6],
                                                double2 ag, double2 goal) {
     if (O) {
-        const int od = 2 * (2 + a.learn_jerk);
-        float* row = O + (size_t)e * od;
-        reinterpret_cast<float2*>(row)[0] = make_float2((float)obs[0], (float)obs[1]);
-        reinterpret_cast<float2*>(row)[1] = make_float2((float)obs[2], (float)obs[3]);
-        if (a.learn_jerk) reinterpret_cast<float2*>(row)[2] = make_float2((float)obs[4], (float)obs[5]);
+        const size_t rowp = (size_t)e * (size_t)(2 + a.learn_jerk);  // in (x, y) pairs
+        store_pair(a, O, rowp + 0, obs[0], obs[1]);
+        store_pair(a, O, rowp + 1, obs[2], obs[3]);
+        if (a.learn_jerk) store_pair(a, O, rowp + 2, obs[4], obs[5]);
     }
-    if (AG) reinterpret_cast<float2*>(AG)[e] = make_float2((float)ag.x, (float)ag.y);
-    if (DG) reinterpret_cast<float2*>(DG)[e] = make_float2((float)goal.x, (float)goal.y);
+    if (AG) store_pair(a, AG, (size_t)e, ag.x, ag.y);
+    if (DG) store_pair(a, DG, (size_t)e, goal.x, goal.y);
 }
 
 // push:373-417 + basic:1797-1805, split in three stages so that the object-placement loop (push:392-407) can be shared by

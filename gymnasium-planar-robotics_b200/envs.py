@@ -100,14 +100,16 @@ class BatchedCore:
         self.action_dim = lib.gpr_action_dim(handle)
         B = self.num_envs
         f32, u8 = torch.float32, torch.uint8
+        self.f64_outputs = bool(int(cfg.output_flags) & 2)  # GPR_OUT_FLOAT64
+        fo = torch.float64 if self.f64_outputs else torch.float32
 
         def z(shape, dtype):
             return torch.zeros(shape, dtype=dtype, device=device)
 
         self.buf = {
-            'observation': z((B, self.obs_dim), f32),
-            'achieved_goal': z((B, self.goal_dim), f32),
-            'desired_goal': z((B, self.goal_dim), f32),
+            'observation': z((B, self.obs_dim), fo),
+            'achieved_goal': z((B, self.goal_dim), fo),
+            'desired_goal': z((B, self.goal_dim), fo),
             'reward': z((B,), f32),
             'terminated': z((B,), u8),
             'truncated': z((B,), u8),
@@ -118,9 +120,9 @@ class BatchedCore:
         if int(getattr(cfg, 'num_obstacles', 0)) > 0:  # (the reference's info has no such key: only present with obstacles)
             self.buf['other_collision'] = z((B,), u8)
         if int(cfg.autoreset_mode) == AUTORESET_SAME_STEP:
-            self.buf['final_observation'] = z((B, self.obs_dim), f32)
-            self.buf['final_achieved_goal'] = z((B, self.goal_dim), f32)
-            self.buf['final_desired_goal'] = z((B, self.goal_dim), f32)
+            self.buf['final_observation'] = z((B, self.obs_dim), fo)
+            self.buf['final_achieved_goal'] = z((B, self.goal_dim), fo)
+            self.buf['final_desired_goal'] = z((B, self.goal_dim), fo)
         self._out = GprOutputs()
         for name in _OUT_FIELDS:
             setattr(self._out, name, _ptr(self.buf.get(name)))
@@ -255,14 +257,19 @@ class BatchedCore:
     # ---------------------------------------------------------------------------------------------------------- extras
     def compute_reward(self, achieved_goal, desired_goal, mover_collision=None, wall_collision=None):
         """Batched compute_reward + compute_terminated on device (HER relabelling, planning:459-534 / pushing:457-527)."""
-        ag = torch.as_tensor(achieved_goal, device=self.device).to(torch.float32).reshape(-1, self.goal_dim).contiguous()
-        dg = torch.as_tensor(desired_goal, device=self.device).to(torch.float32).reshape(-1, self.goal_dim).contiguous()
+        # float64 goals (the single-env classes; GPR_OUT_FLOAT64) are compared in float64: the step's own decision
+        ag = torch.as_tensor(achieved_goal, device=self.device)
+        f64 = ag.dtype == torch.float64
+        gt = torch.float64 if f64 else torch.float32
+        ag = ag.to(gt).reshape(-1, self.goal_dim).contiguous()
+        dg = torch.as_tensor(desired_goal, device=self.device).to(gt).reshape(-1, self.goal_dim).contiguous()
         b = ag.shape[0]
         mc = None if mover_collision is None else torch.as_tensor(mover_collision, device=self.device).to(torch.uint8).contiguous()
         wc = None if wall_collision is None else torch.as_tensor(wall_collision, device=self.device).to(torch.uint8).contiguous()
         r = torch.empty(b, dtype=torch.float32, device=self.device)
         t = torch.empty(b, dtype=torch.uint8, device=self.device)
-        _lib.check(self.lib.gpr_compute_reward(self.handle, b, ag.data_ptr(), dg.data_ptr(), _ptr(mc), _ptr(wc), r.data_ptr(), t.data_ptr(), self._stream()))
+        fn = self.lib.gpr_compute_reward_f64 if f64 else self.lib.gpr_compute_reward
+        _lib.check(fn(self.handle, b, ag.data_ptr(), dg.data_ptr(), _ptr(mc), _ptr(wc), r.data_ptr(), t.data_ptr(), self._stream()))
         return r, t.bool()
 
     def episode_stats(self, reset: bool = True, all_reduce: bool = False) -> dict[str, float]:
@@ -526,6 +533,7 @@ class _SingleEnvBase:
     def __init__(self, **kwargs):
         kwargs.setdefault('autoreset_mode', 'off')  # like the reference: the caller (or gymnasium's wrappers) resets
         kwargs.setdefault('max_episode_steps', 0)   # TimeLimit(50) is added by gymnasium at registration (__init__.py:28)
+        kwargs.setdefault('float64_outputs', True)  # the reference's spaces are float64: observations / goals unrounded
         self._vec = type(self)._vec_cls(num_envs=1, **kwargs)
         v = self._vec
         self.observation_space, self.action_space = v.single_observation_space, v.single_action_space

@@ -167,6 +167,15 @@ typedef struct gpr_config {
  * caching allocator may well hand back the same address) must call gpr_invalidate_outputs() before the next step, which
  * then writes every row once.  Callers that cannot guarantee a persistent buffer should leave this flag clear. */
 #define GPR_OUT_GOAL_ON_CHANGE 1
+/* output_flags bit: observation, achieved_goal, desired_goal and the final_* arrays are float64 (`double*` behind the
+ * `float*` fields of gpr_outputs): the reference's dtype.  The kernels compute in float64 and decide goal-reached / reward /
+ * terminated on the float64 values; float32 outputs are those values rounded once, so a caller that RE-derives the reward
+ * from float32 goals (HER: compute_reward(achieved_goal, desired_goal, info)) can disagree with the step's own reward when
+ * a distance lies within float32 rounding (~3e-8 m) of threshold_pos — about once per 1e6 mover-steps.  With this flag the
+ * outputs are the very values the step decided on and gpr_compute_reward_f64 reproduces its reward and termination
+ * exactly, as the reference guarantees (its spaces are float64).  The single-env classes of the Python binding set it;
+ * the vector classes default to float32 (half the result traffic).  reward stays float32 (-50, +50, -k: exact). */
+#define GPR_OUT_FLOAT64 2
 
 /* Per-step results. Device pointers (host pointers for *_host calls), caller-owned, row-major; NULL = do not write.
  * planning: obs_dim = 2*N*(1+learn_jerk) (planning:242-254), goal_dim = 2*N
@@ -272,6 +281,11 @@ GPR_API int gpr_set_seed(gpr_handle* h, uint64_t seed);
 GPR_API int gpr_compute_reward(gpr_handle* h, int batch, const float* achieved, const float* desired,
                        const uint8_t* mover_collision, const uint8_t* wall_collision, float* reward, uint8_t* terminated,
                        void* stream);
+
+/* The same for float64 goals (GPR_OUT_FLOAT64 outputs): achieved, desired are double [batch, goal_dim]. */
+GPR_API int gpr_compute_reward_f64(gpr_handle* h, int batch, const double* achieved, const double* desired,
+                           const uint8_t* mover_collision, const uint8_t* wall_collision, float* reward, uint8_t* terminated,
+                           void* stream);
 
 /* Episode statistics accumulated on device since the last call with reset_after != 0 (6 float64 values):
  * [episodes finished, sum of returns, sum of lengths, successes, mover collisions, wall collisions].

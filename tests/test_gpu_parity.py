@@ -381,6 +381,53 @@ def test_compute_reward_kernel_matches_oracle():
     env.close()
 
 
+def test_float64_outputs_make_compute_reward_consistent_with_the_step():
+    """the step decides goal-reached / reward / terminated on float64 values; float32 outputs are those values
+    rounded once, so re-deriving the reward from float32 goals can disagree within ~3e-8 m of threshold_pos.  With
+    GPR_OUT_FLOAT64 (what the single-env drop-in classes use) the outputs are the reference's dtype, equal the oracle's
+    float64 values exactly, and compute_reward(achieved_goal, desired_goal, info) == the step's reward for EVERY env —
+    here 200,000 movers parked within +-2e-7 m of the threshold."""
+    B = 100000
+    kw = dict(layout_tiles=np.ones((4, 4)), num_movers=2, std_noise=0.0, autoreset_mode='off', max_episode_steps=0, seed=2)
+    env = gpr.BenchmarkPlanningVecEnv(B, device=DEV, float64_outputs=True, **kw)
+    e32 = gpr.BenchmarkPlanningVecEnv(B, device=DEV, **kw)
+    cfg, _ = gpr.planning_config(num_envs=B, **kw)
+    ora = oracle.OracleEnv(cfg, nthreads=oracle.max_threads())
+    rng = np.random.default_rng(4)
+    goal = np.tile(np.array([[0.25, 0.25], [0.7, 0.7]]), (B, 1, 1))
+    ang = rng.uniform(0, 2 * np.pi, (B, 2))
+    dist = 0.1 + rng.uniform(-2e-7, 2e-7, (B, 2))
+    start = goal + dist[..., None] * np.stack([np.cos(ang), np.sin(ang)], axis=-1)
+    opts = {'mover_start_xy_pos': start, 'mover_goal_xy_pos': goal}
+    obs, info = env.reset(seed=2, options=opts)
+    e32.reset(seed=2, options=opts)
+    ora.reset(seed=2, inject_start=start, inject_goal=goal)
+    assert obs['achieved_goal'].dtype == torch.float64
+    a = torch.zeros((B, 4), device=DEV)
+    obs, r, term, trunc, info = env.step(a)
+    o32, r32, *_, i32 = e32.step(a)
+    ora.step(np.zeros((B, 4), np.float32))
+    torch.cuda.synchronize()
+    for k in ('observation', 'achieved_goal', 'desired_goal'):
+        assert np.array_equal(obs[k].cpu().numpy(), getattr(ora, k)), k  # float64, unrounded
+    assert torch.equal(r, r32) and np.array_equal(r.cpu().numpy(), ora.reward.astype(np.float32))
+    assert 0.2 < float((r == 50).float().mean()) < 0.3 and not bool((r == -50).any())  # both movers inside in about a quarter of the envs
+    rr = env.compute_reward(obs['achieved_goal'], obs['desired_goal'], info)
+    tt = env.compute_terminated(obs['achieved_goal'], obs['desired_goal'], info)
+    assert torch.equal(rr, r) and torch.equal(tt, term)  # exact for every env
+    rr32 = e32.compute_reward(o32['achieved_goal'], o32['desired_goal'], i32)
+    assert int((rr32 != r32).sum()) > 0  # the float32 outputs cannot guarantee it this close to the threshold
+    env.close()
+    e32.close()
+    # the single-env drop-in (NumPy float64 API) uses the float64 outputs
+    one = gpr.BenchmarkPlanningEnv(layout_tiles=np.ones((4, 4)), num_movers=2, std_noise=0.0)
+    o, i = one.reset(seed=1, options={'mover_start_xy_pos': start[0], 'mover_goal_xy_pos': goal[0]})
+    o, r1, t1, _, i = one.step(np.zeros(4))
+    assert o['achieved_goal'].dtype == np.float64 and np.array_equal(o['achieved_goal'], ora.achieved_goal[0])
+    assert one.compute_reward(o['achieved_goal'], o['desired_goal'], i) == r1 == ora.reward[0]
+    one.close()
+
+
 def test_step_host_matches_device_step():
     """gpr_step_host (NumPy in / NumPy out) is the same computation as gpr_step on device tensors."""
     rng = np.random.default_rng(17)
