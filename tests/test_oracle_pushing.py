@@ -84,7 +84,7 @@ def test_reset_sampling_follows_the_reference_ranges():
     # then inside min_mo_dist; the reference would loop forever): only such envs may report a failed reset
     corners = np.array([[0.22, 0.22], [0.22, 0.44], [0.44, 0.22], [0.44, 0.44]])
     far = np.linalg.norm(mp[:, None, :] - corners[None], axis=2).max(axis=1)
-    assert (far[~ok] < d['min_mo_dist'] + 2e-3).all() and (~ok).sum() <= 8
+    assert (far[~ok] < d['min_mo_dist'] + 4e-3).all() and (~ok).sum() <= 8  # (a sliver of < 4 mm: < 1e-4 per attempt)
     assert mp.std(axis=0).min() > 0.1 and op.std(axis=0).min() > 0.05  # actually spread over the boxes
     assert not env.wall_collision.any()
     # achieved goal = object position (+ N(0,1e-5), push:565), desired = goal
