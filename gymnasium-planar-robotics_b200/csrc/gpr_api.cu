@@ -67,6 +67,7 @@ struct gpr_handle {
     double* mover_rot = nullptr;   // [B,3] cos yaw, sin yaw, yaw rate
     double* obj_pos = nullptr;     // [B,4] x, y, cos yaw, sin yaw
     double* obj_vel = nullptr;     // [B,3]
+    float* push_warm = nullptr;    // [B,GPR_PUSH_WARM] warm-start state of the contact solve
     // tables
     double *cx = nullptr, *cy = nullptr, *c_wall = nullptr, *c_mover = nullptr;
     uint16_t* cell = nullptr;
@@ -194,7 +195,7 @@ extern "C" void gpr_destroy(gpr_handle* h) {
     cudaGetDevice(&prev);
     cudaSetDevice(h->device);
     void* ptrs[] = {h->pos, h->vel, h->acc, h->goal, h->elapsed, h->rng, h->needs_reset, h->ep_return, h->stats,
-                    h->fail_count, h->debug_errors, h->reset_list, h->reset_count, h->act, h->mover_rot, h->obj_pos, h->obj_vel, h->cx, h->cy, h->c_wall, h->c_mover,
+                    h->fail_count, h->debug_errors, h->reset_list, h->reset_count, h->act, h->mover_rot, h->obj_pos, h->obj_vel, h->push_warm, h->cx, h->cy, h->c_wall, h->c_mover,
                     h->cell, h->d_stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -262,6 +263,7 @@ extern "C" int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_ha
         TRY(dalloc(&h->mover_rot, 3 * B));
         TRY(dalloc(&h->obj_pos, 4 * B));
         TRY(dalloc(&h->obj_vel, 3 * B));
+        TRY(dalloc(&h->push_warm, GPR_PUSH_WARM * B));
     }
     TRY(dalloc(&h->cx, GPR_MAX_TILES_1D));
     TRY(dalloc(&h->cy, GPR_MAX_TILES_1D));
@@ -495,6 +497,7 @@ static PushArgs push_args(const gpr_handle* h, const gpr_outputs* out) {
     a.mover_rot = h->mover_rot;
     a.obj_pos = h->obj_pos;
     a.obj_vel = h->obj_vel;
+    a.warm = h->push_warm;
     a.goal = h->goal;
     a.elapsed = h->elapsed;
     a.rng = h->rng;
@@ -840,6 +843,7 @@ static int copy_state(gpr_handle* h, const gpr_state* st, bool to_handle, cudaSt
         {h->obj_vel, st->object_vel, 3 * B * sizeof(double)},
         {h->needs_reset, st->needs_reset, B * sizeof(uint8_t)},
         {h->ep_return, st->episode_return, B * sizeof(float)},
+        {h->push_warm, st->contact_warm, GPR_PUSH_WARM * B * sizeof(float)},
     };
     for (const Item& it : items) {
         if (!it.theirs) continue;

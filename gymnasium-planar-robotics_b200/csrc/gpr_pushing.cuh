@@ -42,6 +42,7 @@ struct PushArgs {
     double* mover_rot;  // [B,3] cos yaw, sin yaw, yaw rate
     double* obj_pos;    // [B,4] x, y, cos yaw, sin yaw
     double* obj_vel;    // [B,3] vx, vy, yaw rate
+    float* warm;        // [B,GPR_PUSH_WARM] warm-start state of the contact solve (zero for every env in the free regime)
     double2* goal;     // object goal
     int32_t* elapsed;
     uint32_t* rng;
@@ -280,6 +281,7 @@ __device__ __forceinline__ void push_reset_c(const PushArgs& a, const Tables& tb
     s.O.s = 0.0;
     s.acc = make_double2(0.0, 0.0);
     s.act = make_double2(0.0, 0.0);
+    for (int i = 0; i < GPR_PUSH_WARM; ++i) a.warm[(size_t)e * GPR_PUSH_WARM + i] = 0.f;  // fresh MjData: no warm-start forces
     // basic:1799-1801 wall check with the safety offset on noisy qpos
     float n4[4] = {0.f, 0.f, 0.f, 0.f};
     if (NOISE) gpr_normal4(a.seed, env_global, event, GPR_RNG_RESET_CHECK, 0u, n4);
@@ -548,6 +550,9 @@ __global__ void __launch_bounds__(kPushContactCta, GPR_PUSH_CONTACT_MINB) pushin
         uint32_t event = 0;
         int elapsed = 0;
         double ux = 0.0, uy = 0.0;
+        float warm[GPR_PUSH_WARM];
+#pragma unroll
+        for (int i = 0; i < GPR_PUSH_WARM; ++i) warm[i] = 0.f;
         if (live) {
             const unsigned long long entry = a.queue[base + lane];
             e = (int)(uint32_t)entry;
@@ -555,6 +560,8 @@ __global__ void __launch_bounds__(kPushContactCta, GPR_PUSH_CONTACT_MINB) pushin
             GPR_CHECK(a, (uint32_t)entry < (uint32_t)a.B && cyc0 >= 0 && cyc0 < a.num_cycles, DBG_LIST_ENTRY);
             GPR_CHECK(a, base + lane < (uint32_t)a.B, DBG_LIST_SLOT);
             push_load(a, e, s);
+#pragma unroll
+            for (int i = 0; i < GPR_PUSH_WARM; ++i) warm[i] = a.warm[(size_t)e * GPR_PUSH_WARM + i];
             event = a.rng[e];
             elapsed = a.elapsed[e];
             const float2 af = a.action[e];
@@ -572,13 +579,20 @@ __global__ void __launch_bounds__(kPushContactCta, GPR_PUSH_CONTACT_MINB) pushin
             bool have0 = false;
             double cx, cy, qax, qay;
             push_control<BOX, NOISE>(a, s, ux, uy, env_global, event, s0, n4, have0, cx, cy);
-            gpr_push_substep(&a.P, &s.M, &s.O, cx, cy, &qax, &qay);  // mj_step (basic:1882), general
+            gpr_push_substep(&a.P, &s.M, &s.O, cx, cy, &qax, &qay, warm);  // mj_step (basic:1882), general
             s.acc = make_double2(qax, qay);
             wc = push_wall_cycle<BOX, NOISE>(a, tb, s, env_global, event, s0, n4, have0, cwf, gi, gj, travel, lim_w);
             if (wc) break;  // basic:1904
         }
         __syncwarp();
-        push_finish<BOX, NOISE>(a, tb, e, live, false, s, env_global, event, elapsed, wc);
+        if (live) {
+            // An env that is FREE again (object at exact rest, out of reach) will run its next cycles in
+            // pushing_step_kernel, which never touches this state: leave it as the free substep would — all zero.
+            const bool free_now = gpr_push_is_free(&a.P, &s.M, &s.O);
+#pragma unroll
+            for (int i = 0; i < GPR_PUSH_WARM; ++i) a.warm[(size_t)e * GPR_PUSH_WARM + i] = free_now ? 0.f : warm[i];
+        }
+        push_finish<BOX, NOISE>(a, tb, e, live, false, s, env_global, event, elapsed, wc);  // (a reset zeroes it again)
     }
 }
 

@@ -227,7 +227,8 @@ class BatchedCore:
             'episode_return': z((B,), torch.float32),
         }
         if self.kind != ENV_PLANNING:
-            st.update(act=z((B, 2)), mover_rot=z((B, 3)), object_pos=z((B, 4)), object_vel=z((B, 3)))
+            st.update(act=z((B, 2)), mover_rot=z((B, 3)), object_pos=z((B, 4)), object_vel=z((B, 3)),
+                      contact_warm=z((B, 13), torch.float32))
         return st
 
     def get_state(self) -> dict[str, torch.Tensor]:

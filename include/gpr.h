@@ -145,7 +145,7 @@ typedef struct gpr_config {
      * other two (basic_envs.py:1904) and counts as a collision in reward / termination; starts and goals are re-sampled
      * until they clear every obstacle by the safety offset.  num_obstacles = 0 reproduces the reference exactly. */
     int32_t num_obstacles;
-    int32_t reserved0;
+    int32_t contact_warm_start; /* pushing: start the contact solve from the previous substep's forces (include/gpr_push_physics.h) */
     double obstacle_xy[GPR_MAX_OBSTACLES][2];
     double obstacle_size[GPR_MAX_OBSTACLES][2]; /* circle: radius in [0]; box: half sizes */
     /* --- typed "extra bodies" (SURVEY.md §8f-3): what a custom env of the reference adds to the MuJoCo model through
@@ -216,6 +216,7 @@ typedef struct gpr_state {
     /* bookkeeping needed to resume an interrupted run exactly (checkpoint / restore) */
     uint8_t* needs_reset;   /* [num_envs] NEXT_STEP auto-reset: the env finished in the previous step */
     float* episode_return;  /* [num_envs] return accumulated so far in the running episode (episode statistics) */
+    float* contact_warm;    /* pushing only: [num_envs, 13] warm-start state of the contact solve (GPR_PUSH_WARM) */
 } gpr_state;
 
 typedef struct gpr_handle gpr_handle;

@@ -23,6 +23,12 @@
  *            (6e-8) is far below that, and the dependent float32 chain is what bounds the kernel's latency.  Every float32
  *            operation is an explicitly rounded IEEE operation (GPR_FMUL / GPR_FFMA / GPR_FDIV / GPR_FSQRT of gpr_rng.h),
  *            so the CPU oracle and the CUDA kernels still produce bit-identical trajectories.
+ *   warm start  like MuJoCo (its default), the solver starts from the constraint forces of the previous substep: the four
+ *            ground-friction forces always, the contact forces when the number of contact points is unchanged.  Measured
+ *            on 400-substep pushes against the converged solution (tests/test_pushing_independent.py): 3 warm-started
+ *            sweeps track it as closely as 8 cold ones (final object position within 2.4e-5 m vs 2.2e-5 m mean), so the
+ *            default is contact_iterations = 3 — and the sweeps are the dependent chain that bounds the kernel's latency.
+ *            The forces are 13 floats of per-environment state (gpr_state.contact_warm), zero at reset.
  *   contacts MuJoCo-style soft constraints solved by projected Gauss-Seidel in acceleration space:
  *            a_ref = -B v - K d(r) r,  B = 2/(dmax tc),  K = 1/(dmax^2 tc^2 dr^2),  R = (1 - d)/d * A_ii,
  *            solref = (tc, dr) = (0.02, 1), solimp = (0.9, 0.95, 0.001, 0.5, 2) (MuJoCo defaults), friction cone
@@ -60,6 +66,7 @@ typedef struct gpr_push_params {
     double g_lim;      /* friction limit per corner: mu * m g / 4 */
     double o_inv_lin, o_inv_rot; /* 1 / (m + dt D), 1 / (I + dt D): implicit joint damping of the object */
     int iterations;
+    int warm_start; /* start the sweeps from the previous substep's forces (gpr_config.contact_warm_start) */
     /* float32 copies for the constraint solve (each the float64 value rounded once) */
     float f_hxM, f_hyM, f_hO, f_imM, f_iIM, f_imO, f_iIO, f_mu, f_B, f_K;
     float f_d0, f_dw, f_width, f_mid, f_power, f_gR, f_ginv, f_glim, f_glim2, f_D;
@@ -90,6 +97,7 @@ static inline void gpr_push_params_from_config(const gpr_config* c, gpr_push_par
     P->imp_mid = c->solimp[3];
     P->imp_power = c->solimp[4];
     P->iterations = c->contact_iterations;
+    P->warm_start = c->contact_warm_start != 0;
     {
         const double rm = sqrt(c->mover_half[0] * c->mover_half[0] + c->mover_half[1] * c->mover_half[1]);
         const double ro = sqrt(2.0 * c->object_half_xy * c->object_half_xy);
@@ -126,6 +134,10 @@ static inline void gpr_push_params_from_config(const gpr_config* c, gpr_push_par
     P->f_D = (float)P->obj_damping;
 }
 
+/* per-environment solver state carried from substep to substep (warm start): contact forces (fn, ft) of up to two points,
+ * ground-friction forces (fx, fy) of the four corners, and the number of contact points they belong to */
+#define GPR_PUSH_WARM 13
+
 typedef struct gpr_body2 {
     double x, y, c, s;  /* position, (cos yaw, sin yaw) */
     double vx, vy, w;   /* linear velocity, yaw rate */
@@ -150,13 +162,16 @@ GPR_PHD float gpr_push_impedance(const gpr_push_params* P, float r) {
     return GPR_FFMA(y, GPR_FSUB(P->f_dw, P->f_d0), P->f_d0);
 }
 
-/* advance (c, s) by angle a = dt * w: second-order rotation + renormalisation (no sin/cos call) */
+/* advance (c, s) by angle a = dt * w: second-order rotation, then ONE Newton step of 1/sqrt towards the unit circle
+ * (n2 = c^2 + s^2 deviates from 1 by ~a^4/4 <= 1e-12 per substep; inv = 1.5 - 0.5 n2 leaves a deviation of the order of its
+ * square, i.e. the iteration holds |(c, s)| = 1 to rounding — without the float64 sqrt and division a literal
+ * renormalisation costs on the solve's critical path).  No transcendental function is called. */
 GPR_PHD void gpr_push_rotate(double* c, double* s, double a) {
     double ca = 1.0 - 0.5 * (a * a);
     double sa = a - (a * a) * a * (1.0 / 6.0);
     double nc = (*c) * ca - (*s) * sa;
     double ns = (*s) * ca + (*c) * sa;
-    double inv = 1.0 / sqrt(nc * nc + ns * ns);
+    double inv = 1.5 - 0.5 * (nc * nc + ns * ns);
     *c = nc * inv;
     *s = ns * inv;
 }
@@ -325,6 +340,8 @@ GPR_PHD void gpr_push_integrate(const gpr_push_params* P, gpr_body2* M, gpr_body
     O->y = O->y + dt * O->vy;
     if (O->w != 0.0) gpr_push_rotate(&O->c, &O->s, dt * O->w);
 }
+/* (a free substep has no constraint forces: it also leaves the warm-start state all zero — callers that skip the general
+ * function for free environments rely on that state being zero already, see pushing_contact_kernel) */
 GPR_PHD void gpr_push_substep_free(const gpr_push_params* P, gpr_body2* M, gpr_body2* O, double ux, double uy, double* qax,
                                    double* qay) {
     const double iIM = 1.0 / P->mover_inertia;
@@ -394,11 +411,14 @@ GPR_PHD void gpr_row_apply(const gpr_row* r, float df, float acc[6]) {
  * and (qax, qay) holds the mover's resulting x/y acceleration (MuJoCo's qacc, which the jerk-mode callback reads back,
  * pushing:431).  Returns the number of mover-object contact points that were active. */
 GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* O, double ux, double uy, double* qax,
-                             double* qay) {
+                             double* qay, float* warm /* [GPR_PUSH_WARM] in/out, or NULL: cold start, nothing kept */) {
     if (gpr_push_is_free(P, M, O)) {
         gpr_push_substep_free(P, M, O, ux, uy, qax, qay);
+        if (warm)
+            for (int i = 0; i < GPR_PUSH_WARM; ++i) warm[i] = 0.0f;
         return 0;
     }
+    const int use_warm = warm != 0 && P->warm_start;
     /* ---- smooth accelerations, float64 (no constraint forces; object damping enters as a passive force -D v) */
     const double iIM = 1.0 / P->mover_inertia;
     const double yaw = gpr_push_small_yaw(M->c, M->s);
@@ -444,8 +464,10 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
         rt[k].R = R; /* impratio 1: the friction row shares the normal row's regulariser */
         rn[k].inv = GPR_FDIV(1.0f, GPR_FADD(Ann, R));
         rt[k].inv = GPR_FDIV(1.0f, GPR_FADD(Att, R));
-        rn[k].f = 0.0f;
-        rt[k].f = 0.0f;
+        /* warm start: the previous substep's forces when it had the same number of contact points */
+        const int keep = use_warm && (int)warm[12] == nc;
+        rn[k].f = keep ? warm[2 * k] : 0.0f;
+        rt[k].f = keep ? warm[2 * k + 1] : 0.0f;
         /* relative velocity of the object w.r.t. the mover at the contact point */
         const float vrx = GPR_FSUB(GPR_FFMA(-wO, rBy, vOx), GPR_FFMA(-wM, rAy, vMx));
         const float vry = GPR_FSUB(GPR_FFMA(wO, rBx, vOy), GPR_FFMA(wM, rAx, vMy));
@@ -474,6 +496,22 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
             gcy[g] = GPR_FFMA(P->f_B, GPR_FFMA(wO, gx[g], vOy), GPR_FFMA(a0[5], gx[g], a0[4]));
             gxI[g] = GPR_FMUL(gx[g], P->f_iIO);
             gyI[g] = GPR_FMUL(gy[g], P->f_iIO);
+            if (use_warm) {
+                gfx[g] = warm[4 + 2 * g];
+                gfy[g] = warm[5 + 2 * g];
+            }
+        }
+    }
+    if (use_warm) { /* the acceleration the warm forces cause: rows in solve order, then the corners */
+        for (int k = 0; k < 2; ++k) {
+            if (k >= nc) continue;
+            gpr_row_apply(&rn[k], rn[k].f, acc);
+            gpr_row_apply(&rt[k], rt[k].f, acc);
+        }
+        for (int g = 0; g < 4; ++g) {
+            acc[3] = GPR_FFMA(gfx[g], P->f_imO, acc[3]);
+            acc[4] = GPR_FFMA(gfy[g], P->f_imO, acc[4]);
+            acc[5] = GPR_FFMA(gxI[g], gfy[g], GPR_FFMA(-gyI[g], gfx[g], acc[5]));
         }
     }
     /* ---- projected Gauss-Seidel in acceleration space: rows (n_1, t_1, n_2, t_2), then the four corners */
@@ -514,6 +552,17 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
             acc[4] = GPR_FFMA(dfy, P->f_imO, acc[4]);
             acc[5] = GPR_FFMA(gxI[g], dfy, GPR_FFMA(-gyI[g], dfx, acc[5]));
         }
+    }
+    if (warm) {
+        for (int k = 0; k < 2; ++k) {
+            warm[2 * k] = k < nc ? rn[k].f : 0.0f;
+            warm[2 * k + 1] = k < nc ? rt[k].f : 0.0f;
+        }
+        for (int g = 0; g < 4; ++g) {
+            warm[4 + 2 * g] = gfx[g];
+            warm[5 + 2 * g] = gfy[g];
+        }
+        warm[12] = (float)nc;
     }
     /* constraint forces = mass * the acceleration they caused (the integrator adds them to the smooth forces in float64) */
     const double fM[3] = {(double)acc[0] * P->mover_mass, (double)acc[1] * P->mover_mass, (double)acc[2] * P->mover_inertia};

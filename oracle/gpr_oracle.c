@@ -421,6 +421,7 @@ typedef struct gpro_state {
     double* mover_rot;  /* [B, 3] cos yaw, sin yaw, yaw rate */
     double* object_pos; /* [B, 4] x, y, cos yaw, sin yaw */
     double* object_vel; /* [B, 3] vx, vy, yaw rate */
+    float* contact_warm; /* [B, GPR_PUSH_WARM] warm-start state of the contact solve */
 } gpro_state;
 
 typedef struct gpro_outputs {
@@ -831,6 +832,7 @@ void gpro_planning_step(const gpr_config* c, uint64_t seed, gpro_state* s, const
 typedef struct push_env {
     gpr_body2 M, O;
     double acc[2], act[2], goal[2];
+    float warm[GPR_PUSH_WARM];
 } push_env;
 
 static void push_env_load(const gpro_state* s, int64_t e, push_env* x) {
@@ -853,6 +855,7 @@ static void push_env_load(const gpro_state* s, int64_t e, push_env* x) {
         x->act[k] = s->act[2 * e + k];
         x->goal[k] = s->goal[2 * e + k];
     }
+    for (int i = 0; i < GPR_PUSH_WARM; ++i) x->warm[i] = s->contact_warm ? s->contact_warm[GPR_PUSH_WARM * e + i] : 0.0f;
 }
 
 static void push_env_store(gpro_state* s, int64_t e, const push_env* x) {
@@ -875,6 +878,8 @@ static void push_env_store(gpro_state* s, int64_t e, const push_env* x) {
         s->act[2 * e + k] = x->act[k];
         s->goal[2 * e + k] = x->goal[k];
     }
+    if (s->contact_warm)
+        for (int i = 0; i < GPR_PUSH_WARM; ++i) s->contact_warm[GPR_PUSH_WARM * e + i] = x->warm[i];
 }
 
 /* basic:1888-1894 / 1799-1801: check_wall_collision on the noisy qpos of the single mover.
@@ -986,6 +991,7 @@ static int pushing_reset_one(const gpr_config* c, uint64_t seed, uint32_t env_gl
     x->O.c = 1.0;
     x->O.s = 0.0;
     x->acc[0] = x->acc[1] = x->act[0] = x->act[1] = 0.0;
+    for (int i = 0; i < GPR_PUSH_WARM; ++i) x->warm[i] = 0.0f; /* fresh MjData: no warm-start forces */
     /* basic:1799-1801: wall check WITH the safety offset on noisy qpos */
     float n4[4] = {0.f, 0.f, 0.f, 0.f};
     const int noisy = c->std_noise[0] != 0.0 || c->std_noise[1] != 0.0;
@@ -1035,7 +1041,7 @@ static void pushing_step_one(const gpr_config* c, const gpr_push_params* P, uint
         }
         /* mj_step (basic:1882): planar substitute, see include/gpr_push_physics.h */
         double qax, qay;
-        gpr_push_substep(P, &x->M, &x->O, ctrl[0], ctrl[1], &qax, &qay);
+        gpr_push_substep(P, &x->M, &x->O, ctrl[0], ctrl[1], &qax, &qay, x->warm);
         x->acc[0] = qax;
         x->acc[1] = qay;
         /* basic:1888-1894 wall check; a single mover has no mover-mover check (push:592 asserts no mover collision) */
@@ -1043,6 +1049,10 @@ static void pushing_step_one(const gpr_config* c, const gpr_push_params* P, uint
                                  (uint32_t)cyc * 4u + GPR_RNG_BLOCK_WALL_QUAT);
         if (wc) break; /* basic:1904 */
     }
+    /* an env that ends its step in the free regime holds no warm-start forces (the next free substep would clear them
+     * anyway; normalising here keeps the stored state independent of which kernel runs the next cycles) */
+    if (gpr_push_is_free(P, &x->M, &x->O))
+        for (int i = 0; i < GPR_PUSH_WARM; ++i) x->warm[i] = 0.0f;
     *wall_collision = wc;
 }
 
@@ -1156,12 +1166,13 @@ GPRO_FMA_CLONES void gpro_pushing_step(const gpr_config* c, uint64_t seed, gpro_
 }
 
 /* one substep of the planar push physics on explicit bodies (property tests of the specification) */
-GPRO_FMA_CLONES int gpro_push_substep(const gpr_config* c, double* mover7, double* object7, double ux, double uy, double* qacc) {
+GPRO_FMA_CLONES int gpro_push_substep(const gpr_config* c, double* mover7, double* object7, double ux, double uy, double* qacc,
+                                      float* warm /* [GPR_PUSH_WARM] in/out or NULL */) {
     gpr_push_params P;
     gpr_push_params_from_config(c, &P);
     gpr_body2 M = {mover7[0], mover7[1], mover7[2], mover7[3], mover7[4], mover7[5], mover7[6]};
     gpr_body2 O = {object7[0], object7[1], object7[2], object7[3], object7[4], object7[5], object7[6]};
-    int nc = gpr_push_substep(&P, &M, &O, ux, uy, &qacc[0], &qacc[1]);
+    int nc = gpr_push_substep(&P, &M, &O, ux, uy, &qacc[0], &qacc[1], warm);
     double m[7] = {M.x, M.y, M.c, M.s, M.vx, M.vy, M.w}, o[7] = {O.x, O.y, O.c, O.s, O.vx, O.vy, O.w};
     memcpy(mover7, m, sizeof(m));
     memcpy(object7, o, sizeof(o));

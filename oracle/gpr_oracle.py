@@ -60,6 +60,7 @@ class OState(ctypes.Structure):
         ('mover_rot', ctypes.c_void_p),
         ('object_pos', ctypes.c_void_p),
         ('object_vel', ctypes.c_void_p),
+        ('contact_warm', ctypes.c_void_p),
     ]
 
 
@@ -192,6 +193,7 @@ class OracleEnv:
         self.mover_rot = np.zeros((B, 3))
         self.object_pos = np.zeros((B, 4))
         self.object_vel = np.zeros((B, 3))
+        self.contact_warm = np.zeros((B, 13), dtype=np.float32)
         self._alloc_out()
 
     def _alloc_out(self):

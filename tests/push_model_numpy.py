@@ -15,7 +15,9 @@ The model (a specification of this project — MuJoCo itself is n
     constraints   : <= 2 mover-object contact points (normal n from mover to object, tangent t = (-n_y, n_x)) with a
                     friction interval |f_t| <= mu f_n; four ground-friction points at the object's bottom corners, each a
                     2-D force limited to the disc mu m_O g / 4, a_ref = -b v (no position term), R from d0
-    solver        : projected Gauss-Seidel, `iterations` sweeps, rows in the order (n_1, t_1, n_2, t_2, corners 1..4)
+    solver        : projected Gauss-Seidel, `iterations` sweeps, rows in the order (n_1, t_1, n_2, t_2, corners 1..4), optionally
+                    WARM-STARTED from the previous substep's forces (the corner forces always, the contact forces when the
+                    number of contact points is unchanged) — MuJoCo's default
     integrator    : qacc = qacc_smooth + M^-1 J^T f; the object's joint damping implicit: (M + dt D) a = f_total (MuJoCo's
                     Euler integrator); v += dt a; x += dt v; orientation kept as (cos, sin), advanced by the second-order
                     rotation (1 - a^2/2, a - a^3/6) and renormalised.
@@ -41,7 +43,7 @@ class Params:
     k_rot: float = 0.1
     solref: tuple = (0.02, 1.0)
     solimp: tuple = (0.9, 0.95, 0.001, 0.5, 2.0)
-    iterations: int = 8
+    iterations: int = 3
 
     @property
     def I_M(self):
@@ -135,8 +137,9 @@ def _row(pM, pO, pt, d):
     return np.array([-d[0], -d[1], -_cross(rA, d), d[0], d[1], _cross(rB, d)])
 
 
-def substep(P: Params, M: np.ndarray, O: np.ndarray, u: np.ndarray, iterations: int | None = None):
-    """One substep.  M, O: [x, y, cos, sin, vx, vy, w].  Returns (M', O', mover qacc_xy, number of contact points)."""
+def substep(P: Params, M: np.ndarray, O: np.ndarray, u: np.ndarray, iterations: int | None = None, warm: dict | None = None):
+    """One substep.  M, O: [x, y, cos, sin, vx, vy, w].  Returns (M', O', mover qacc_xy, number of contact points).
+    warm: None = cold start; a dict = warm start, read (keys 'n', 'f', 'g'; empty = no forces yet) and updated in place."""
     it = P.iterations if iterations is None else iterations
     dt = P.dt
     Minv = np.array([1 / P.m_M, 1 / P.m_M, 1 / P.I_M, 1 / P.m_O, 1 / P.m_O, 1 / P.I_O])
@@ -181,6 +184,14 @@ def substep(P: Params, M: np.ndarray, O: np.ndarray, u: np.ndarray, iterations: 
         lim = P.mu * P.m_O * P.g / 4.0
         f = np.zeros(len(rows))
         fg = np.zeros((4, 2))
+        if warm:  # previous substep's forces and the generalised force they amount to
+            if pts and warm['n'] == len(pts):
+                f = warm['f'].copy()
+            fg = warm['g'].copy()
+            for i, J in enumerate(rows):
+                f_gen = f_gen + J * f[i]
+            for g_, (Jx, Jy, _, _) in enumerate(corner_rows):
+                f_gen = f_gen + Jx * fg[g_, 0] + Jy * fg[g_, 1]
         for _ in range(it):
             for i, J in enumerate(rows):
                 acc = J @ (a_smooth + Minv * f_gen)
@@ -201,6 +212,10 @@ def substep(P: Params, M: np.ndarray, O: np.ndarray, u: np.ndarray, iterations: 
                     nx, ny = nx * lim / mag, ny * lim / mag
                 f_gen = f_gen + Jx * (nx - fg[g_, 0]) + Jy * (ny - fg[g_, 1])
                 fg[g_] = (nx, ny)
+        if warm is not None:
+            warm.update(n=len(pts), f=f.copy(), g=fg.copy())
+    elif warm is not None:
+        warm.clear()  # a free substep has no constraint forces
     qacc = a_smooth + Minv * f_gen
     # the object's joint damping is implicit in MuJoCo's Euler integrator: (M + dt D) a = -D v + J^T f
     qacc[3] = (-P.D * O[4] + f_gen[3]) / (P.m_O + dt * P.D)

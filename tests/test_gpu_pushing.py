@@ -16,7 +16,7 @@ import gymnasium_planar_robotics_b200 as gpr
 pytestmark = pytest.mark.gpu
 
 DEV = 'cuda:0'
-STATE_KEYS = ('pos', 'vel', 'acc', 'goal', 'act', 'mover_rot', 'object_pos', 'object_vel')
+STATE_KEYS = ('pos', 'vel', 'acc', 'goal', 'act', 'mover_rot', 'object_pos', 'object_vel', 'contact_warm')
 
 
 def make_pair(num_envs, **kw):

@@ -22,12 +22,17 @@ def _env(num_envs=1, **kw):
     return oracle.OracleEnv(cfg), cfg, d
 
 
+_WARM = {}
+
+
 def _substep(cfg, mover, obj, ux, uy):
-    """one 1 ms substep on explicit bodies [x, y, cos, sin, vx, vy, w]; returns (contacts, mover qacc)"""
+    """one 1 ms substep on explicit bodies [x, y, cos, sin, vx, vy, w]; returns (contacts, mover qacc).  The warm-start state
+    of the contact solve is carried from call to call per `obj` array, as the env carries it from substep to substep."""
     qacc = np.zeros(2)
     lib = oracle.lib()
+    warm = _WARM.setdefault(id(obj), (obj, np.zeros(13, dtype=np.float32)))[1]
     nc = lib.gpro_push_substep(ctypes.byref(cfg), mover.ctypes.data_as(ctypes.POINTER(_D)), obj.ctypes.data_as(ctypes.POINTER(_D)),
-                               _D(ux), _D(uy), qacc.ctypes.data_as(ctypes.POINTER(_D)))
+                               _D(ux), _D(uy), qacc.ctypes.data_as(ctypes.POINTER(_D)), warm.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
     return nc, qacc
 
 
