@@ -110,6 +110,8 @@ class GprOutputs(ctypes.Structure):
         ('final_achieved_goal', ctypes.c_void_p),
         ('final_desired_goal', ctypes.c_void_p),
         ('other_collision', ctypes.c_void_p),
+        ('final_index', ctypes.c_void_p),
+        ('final_count', ctypes.c_void_p),
     ]
 
 

@@ -86,6 +86,11 @@ struct gpr_handle {
     // synchronise host_stream before they return.
     cudaEvent_t order_ev = nullptr;
     bool order_pending = false;
+    // compact transport of the sparse results of gpr_step_host (copy-engine route, see step_host_compact)
+    bool compact_now = false;              // plan_args: hand the compact buffers to the kernels, do not write desired_goal rows
+    const void* host_goal_synced = nullptr;  // the caller's HOST desired_goal buffer that holds every env's current goal
+    bool in_host_call = false;             // gpr_step / gpr_reset were entered from a *_host call
+    cudaEvent_t count_ev = nullptr;
     void* d_stage = nullptr;  // device: action + all outputs
     void* h_stage = nullptr;  // pinned mirror
     size_t stage_bytes = 0;
@@ -202,6 +207,7 @@ extern "C" void gpr_destroy(gpr_handle* h) {
     for (cudaEvent_t ev : h->tev) cudaEventDestroy(ev);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->order_ev) cudaEventDestroy(h->order_ev);
+    if (h->count_ev) cudaEventDestroy(h->count_ev);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     cudaSetDevice(prev);
     delete h;
@@ -294,6 +300,43 @@ extern "C" int gpr_create(const gpr_config* cfg, int device, gpr_handle** out_ha
     *out_handle = h;
     g_err[0] = 0;
     return GPR_OK;
+}
+
+// staging layout of the *_host entry points (device buffer and its pinned host mirror share it)
+constexpr int kOutSlots = 13;  // pointers in gpr_outputs
+constexpr int kCompact = 6;    // compact transport: final obs / ag / dg rows, new goal rows, env index, entry count
+enum { C_FOBS = 0, C_FAG = 1, C_FDG = 2, C_GOAL = 3, C_INDEX = 4, C_COUNT = 5 };
+struct StageLayout {
+    size_t off_action, off[kOutSlots], bytes[kOutSlots], total;
+    size_t coff[kCompact], crow[kCompact];  // offsets and bytes per row of the compact areas (B rows each; the count: one row)
+};
+
+static StageLayout stage_layout(const gpr_handle* h) {
+    const size_t B = (size_t)h->cfg.num_envs;
+    StageLayout L;
+    size_t cur = 0;
+    auto take = [&](size_t n) {
+        size_t o = cur;
+        cur += (n + 255) & ~(size_t)255;
+        return o;
+    };
+    L.off_action = take(B * h->action_dim * sizeof(float));
+    const size_t el = (h->cfg.output_flags & GPR_OUT_FLOAT64) ? sizeof(double) : sizeof(float);  // observation / goal arrays
+    const size_t sz[kOutSlots] = {B * h->obs_dim * el, B * h->goal_dim * el, B * h->goal_dim * el,
+                                  B * sizeof(float), B, B, B, B, B,
+                                  B * h->obs_dim * el, B * h->goal_dim * el, B * h->goal_dim * el, B};
+    for (int k = 0; k < kOutSlots; ++k) {
+        L.bytes[k] = sz[k];
+        L.off[k] = take(sz[k]);
+    }
+    const size_t crow[kCompact] = {h->obs_dim * el, h->goal_dim * el, h->goal_dim * el, h->goal_dim * el, sizeof(int32_t),
+                                   sizeof(unsigned long long)};
+    for (int k = 0; k < kCompact; ++k) {
+        L.crow[k] = crow[k];
+        L.coff[k] = take(k == C_COUNT ? crow[k] : B * crow[k]);
+    }
+    L.total = cur;
+    return L;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -433,6 +476,15 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     a.parity = h->parity;
     a.out_f64 = (c.output_flags & GPR_OUT_FLOAT64) != 0;
     if (out) a.out = *out;
+    if (h->compact_now && h->d_stage) {
+        const StageLayout L = stage_layout(h);
+        char* ds = (char*)h->d_stage;
+        a.compact_final_obs = (float*)(ds + L.coff[C_FOBS]);
+        a.compact_final_ag = (float*)(ds + L.coff[C_FAG]);
+        a.compact_final_dg = (float*)(ds + L.coff[C_FDG]);
+        a.compact_goal = (float*)(ds + L.coff[C_GOAL]);
+        a.compact_index = (int32_t*)(ds + L.coff[C_INDEX]);
+    }
     return a;
 }
 
@@ -551,6 +603,7 @@ extern "C" int gpr_reset(gpr_handle* h, const uint8_t* reset_mask, int reseed, u
         CU(cudaMemsetAsync(h->rng, 0, sizeof(uint32_t) * (size_t)h->cfg.num_envs, s));
     }
     if (!out || out->desired_goal != h->goal_ptr) h->goal_dirty = true;  // new goals the steps' buffer does not see
+    if (!h->in_host_call) h->host_goal_synced = nullptr;
     if (h->cfg.env_kind == GPR_ENV_PLANNING) {
         if (inject_object) return fail(GPR_ERR_INVALID_ARG, "inject_object is for the pushing env");
         PlanArgs a = plan_args(h, out);
@@ -588,9 +641,15 @@ extern "C" int gpr_step(gpr_handle* h, const float* action, const gpr_outputs* o
         CU(cudaEventRecord(te[0], s));
     }
     // GPR_OUT_GOAL_ON_CHANGE: rows of envs that are not reset are skipped — unless this buffer has not seen all of them yet
-    const int write_goal = !(h->cfg.output_flags & GPR_OUT_GOAL_ON_CHANGE) || h->goal_dirty || out->desired_goal != h->goal_ptr;
-    h->goal_dirty = false;
-    h->goal_ptr = out->desired_goal;
+    int write_goal = !(h->cfg.output_flags & GPR_OUT_GOAL_ON_CHANGE) || h->goal_dirty || out->desired_goal != h->goal_ptr;
+    if (h->compact_now) {
+        write_goal = 0;  // (goal rows travel on the compact list; the caller's host buffer is known to be current)
+        h->goal_dirty = true;  // ... but no device-side desired_goal buffer sees this step's new goals
+    } else {
+        h->goal_dirty = false;
+        h->goal_ptr = out->desired_goal;
+    }
+    if (!h->in_host_call) h->host_goal_synced = nullptr;  // goals may change on the device without reaching a host buffer
     if (h->cfg.env_kind == GPR_ENV_PLANNING) {
         PlanArgs a = plan_args(h, out);
         a.action = reinterpret_cast<const float2*>(action);
@@ -651,33 +710,6 @@ extern "C" int gpr_kernel_times(gpr_handle* h, int enable, double* host_ms) {
 // ---------------------------------------------------------------------------------------------------------------------
 // host-buffer entry points (what a user of the reference calls: NumPy in, NumPy out)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kOutSlots = 13;  // pointers in gpr_outputs
-struct StageLayout {
-    size_t off_action, off[kOutSlots], bytes[kOutSlots], total;
-};
-
-static StageLayout stage_layout(const gpr_handle* h) {
-    const size_t B = (size_t)h->cfg.num_envs;
-    StageLayout L;
-    size_t cur = 0;
-    auto take = [&](size_t n) {
-        size_t o = cur;
-        cur += (n + 255) & ~(size_t)255;
-        return o;
-    };
-    L.off_action = take(B * h->action_dim * sizeof(float));
-    const size_t el = (h->cfg.output_flags & GPR_OUT_FLOAT64) ? sizeof(double) : sizeof(float);  // observation / goal arrays
-    const size_t sz[kOutSlots] = {B * h->obs_dim * el, B * h->goal_dim * el, B * h->goal_dim * el,
-                                  B * sizeof(float), B, B, B, B, B,
-                                  B * h->obs_dim * el, B * h->goal_dim * el, B * h->goal_dim * el, B};
-    for (int k = 0; k < kOutSlots; ++k) {
-        L.bytes[k] = sz[k];
-        L.off[k] = take(sz[k]);
-    }
-    L.total = cur;
-    return L;
-}
-
 static int ensure_stage(gpr_handle* h) {
     if (h->d_stage) return GPR_OK;
     const StageLayout L = stage_layout(h);
@@ -739,6 +771,15 @@ static bool host_io_dma() {
     return v;
 }
 
+// GPR_HOST_COMPACT=0: the copy-engine route moves the dense final_* / desired_goal arrays instead of compact lists (A/B)
+static bool host_io_no_compact() {
+    static const bool v = [] {
+        const char* e = getenv("GPR_HOST_COMPACT");
+        return e && e[0] == '0';
+    }();
+    return v;
+}
+
 static HostRoute route_outputs(gpr_handle* h, const StageLayout& L, const gpr_outputs* host_out) {
     HostRoute r;
     gpr_outputs ho = *host_out;
@@ -778,6 +819,94 @@ static int order_host_stream(gpr_handle* h) {
     return GPR_OK;
 }
 
+// COMPACT TRANSPORT (copy-engine route, planning env, SAME_STEP auto-reset).  Of the 201 bytes per env of result buffers only
+// the dense rows (observation, achieved_goal, reward, flags: 74 B with 4 movers) change for every env; final_* and the new
+// desired_goal concern the envs that finished — a third of them with random actions.  The kernels write those rows to
+// row `slot` of compact device buffers (slot = the env's position on the auto-reset work list), the copy engine moves the
+// dense arrays plus the first `count` rows of the compact ones, and this function scatters them into the caller's arrays:
+// the caller sees exactly what the other routes deliver.  With 8 ranks on one host the copy engines together sustain
+// 175-193 GB/s into host memory (tools/pcie_bw.py under torchrun) while SM-issued zero-copy stores of 8 GPUs get ~58 GB/s
+// (profiles/r2_bench_8gpu.txt): this route moves ~104 B/env at the former rate.
+static int step_host_compact(gpr_handle* h, const StageLayout& L, const float* dev_action, const gpr_outputs* host_out) {
+    gpr_outputs ho = *host_out;
+    char* hs = (char*)h->h_stage;
+    char* ds = (char*)h->d_stage;
+    if (!h->count_ev) CU(cudaEventCreateWithFlags(&h->count_ev, cudaEventDisableTiming));
+    // dense slots through device staging; the sparse ones (final_*, desired_goal) are not written in place at all
+    HostRoute r;
+    memset(&r, 0, sizeof(r));
+    const int sparse[4] = {2, 9, 10, 11};  // desired_goal, final_observation, final_achieved_goal, final_desired_goal
+    for (int k = 0; k < kOutSlots; ++k) {
+        void* dst = *out_slot(&ho, k);
+        if (!dst || k == sparse[0] || k == sparse[1] || k == sparse[2] || k == sparse[3]) continue;
+        r.pinned[k] = device_alias(dst) ? dst : nullptr;
+        r.staged[k] = true;
+        *out_slot(&r.dev, k) = (void*)(ds + L.off[k]);
+    }
+    const int par = h->parity;  // the work-list buffer this step uses (gpr_step flips it)
+    h->compact_now = true;
+    h->in_host_call = true;
+    int rc = gpr_step(h, dev_action, &r.dev, h->host_stream);
+    h->compact_now = false;
+    h->in_host_call = false;
+    if (rc != GPR_OK) return rc;
+    // the entry count first (the list copies are sized by it), then the dense arrays behind it in the same stream
+    unsigned long long* hcount = (unsigned long long*)(hs + L.coff[C_COUNT]);
+    CU(cudaMemcpyAsync(hcount, h->reset_count + par, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->host_stream));
+    CU(cudaEventRecord(h->count_ev, h->host_stream));
+    for (int k = 0; k < kOutSlots; ++k)
+        if (r.staged[k])
+            CU(cudaMemcpyAsync(r.pinned[k] ? r.pinned[k] : (void*)(hs + L.off[k]), ds + L.off[k], L.bytes[k], cudaMemcpyDeviceToHost,
+                               h->host_stream));
+    CU(cudaEventSynchronize(h->count_ev));
+    const size_t count = (size_t)(*hcount & 0xffffffffull);
+    if (count > (size_t)h->cfg.num_envs) return fail(GPR_ERR_CUDA, "work-list count %zu exceeds num_envs", count);
+    void* const sdst[4] = {ho.final_observation, ho.final_achieved_goal, ho.final_desired_goal, ho.desired_goal};
+    // the caller takes the terminal observations as a list (gpr_outputs.final_index): the copy engine writes the compact rows
+    // straight into its arrays (page-locked) and nothing but the new goals is scattered on the host
+    const bool list_out = ho.final_index != nullptr && ho.final_count != nullptr;
+    bool direct[4] = {false, false, false, false};
+    if (count) {
+        CU(cudaMemcpyAsync(hs + L.coff[C_INDEX], ds + L.coff[C_INDEX], count * L.crow[C_INDEX], cudaMemcpyDeviceToHost, h->host_stream));
+        for (int c = 0; c < 4; ++c) {
+            if (!sdst[c]) continue;
+            direct[c] = list_out && c < 3 && device_alias(sdst[c]) != nullptr;
+            CU(cudaMemcpyAsync(direct[c] ? sdst[c] : (void*)(hs + L.coff[c]), ds + L.coff[c], count * L.crow[c], cudaMemcpyDeviceToHost,
+                               h->host_stream));
+        }
+    }
+    CU(cudaStreamSynchronize(h->host_stream));
+    for (int k = 0; k < kOutSlots; ++k)
+        if (r.staged[k] && !r.pinned[k]) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
+    const int32_t* idx = (const int32_t*)(hs + L.coff[C_INDEX]);
+    if (list_out) {
+        memcpy(ho.final_index, idx, count * sizeof(int32_t));
+        *ho.final_count = (uint32_t)count;
+    }
+    // scatter: row s of the compact arrays belongs to env index[s]
+    for (int c = 0; c < 4; ++c) {
+        if (!sdst[c]) continue;
+        if (list_out && c < 3) {  // list form: rows stay compact
+            if (!direct[c]) memcpy(sdst[c], hs + L.coff[c], count * L.crow[c]);
+            continue;
+        }
+        const size_t rb = L.crow[c];
+        const char* src = hs + L.coff[c];
+        char* dst = (char*)sdst[c];
+        if (rb % 8 == 0) {  // rows are whole (x, y) pairs: fixed-size word moves instead of a memcpy call per row
+            const size_t w = rb / 8;
+            const uint64_t* s8 = (const uint64_t*)src;
+            for (size_t s_ = 0; s_ < count; ++s_) {
+                uint64_t* d8 = (uint64_t*)(dst + (size_t)idx[s_] * rb);
+                for (size_t q = 0; q < w; ++q) d8[q] = s8[s_ * w + q];
+            }
+        } else {
+            for (size_t s_ = 0; s_ < count; ++s_) memcpy(dst + (size_t)idx[s_] * rb, src + s_ * rb, rb);
+        }
+    }
+    return GPR_OK;
+}
+
 extern "C" int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_outputs* host_out) {
     if (!h || !host_action || !host_out) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
     DeviceGuard g(h->device);
@@ -798,12 +927,23 @@ extern "C" int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_
     // env chunks on separate streams (with or without per-chunk copy-engine transfers) changes nothing (+-3%).  What the
     // host-I/O step pays for is the result traffic: SM stores to pinned memory sustain ~25 GB/s (the copy engine: 55),
     // and sub-sector stores are charged like full ones — hence the CTA-coalesced flag / reward stores of the step kernel.
-    const HostRoute r = route_outputs(h, L, host_out);
     rc = order_host_stream(h);
     if (rc != GPR_OK) return rc;
+    // compact transport: the copy-engine route of a planning env with SAME_STEP auto-reset whose caller keeps handing in the
+    // desired_goal buffer that already holds every env's current goal (the previous host call made it so)
+    if (host_io_dma() && !host_io_no_compact() && h->cfg.env_kind == GPR_ENV_PLANNING && h->cfg.autoreset_mode == GPR_AUTORESET_SAME_STEP &&
+        (h->cfg.output_flags & GPR_OUT_GOAL_ON_CHANGE) && host_out->desired_goal && h->host_goal_synced == host_out->desired_goal)
+        return step_host_compact(h, L, dev_action, host_out);
+    const HostRoute r = route_outputs(h, L, host_out);
+    h->in_host_call = true;
     rc = gpr_step(h, dev_action, &r.dev, h->host_stream);
+    h->in_host_call = false;
     if (rc != GPR_OK) return rc;
-    return finish_host_call(h, L, r, host_out);
+    rc = finish_host_call(h, L, r, host_out);
+    // every env's goal is in the caller's buffer now if this call wrote all rows or the buffer was current already
+    if (rc == GPR_OK && host_out->desired_goal) h->host_goal_synced = host_out->desired_goal;
+    if (host_out->final_count) *host_out->final_count = 0xffffffffu;  // final_* rows were written densely (row = env)
+    return rc;
 }
 
 extern "C" int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gpr_outputs* host_out) {
@@ -815,9 +955,13 @@ extern "C" int gpr_reset_host(gpr_handle* h, int reseed, uint64_t seed, const gp
     const HostRoute r = route_outputs(h, L, host_out);
     rc = order_host_stream(h);
     if (rc != GPR_OK) return rc;
+    h->in_host_call = true;
     rc = gpr_reset(h, nullptr, reseed, seed, nullptr, nullptr, nullptr, &r.dev, h->host_stream);
+    h->in_host_call = false;
     if (rc != GPR_OK) return rc;
-    return finish_host_call(h, L, r, host_out);
+    rc = finish_host_call(h, L, r, host_out);
+    if (rc == GPR_OK) h->host_goal_synced = host_out->desired_goal;  // a full reset wrote every env's goal
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -863,6 +1007,7 @@ extern "C" int gpr_set_state(gpr_handle* h, const gpr_state* src, void* stream) 
     if (!h || !src) return fail(GPR_ERR_INVALID_ARG, "NULL argument");
     DeviceGuard g(h->device);
     if (src->goal) h->goal_dirty = true;
+    if (src->goal) h->host_goal_synced = nullptr;
     int rc = copy_state(h, src, true, (cudaStream_t)stream);
     return rc != GPR_OK ? rc : note_caller_work(h, (cudaStream_t)stream);
 }
@@ -918,6 +1063,7 @@ extern "C" int gpr_invalidate_outputs(gpr_handle* h) {
     if (!h) return fail(GPR_ERR_INVALID_ARG, "handle is NULL");
     h->goal_dirty = true;
     h->goal_ptr = nullptr;
+    h->host_goal_synced = nullptr;
     return GPR_OK;
 }
 

@@ -92,6 +92,16 @@ struct PlanArgs {
     int parity;
     int write_goal;  // 0: the step kernel leaves desired_goal rows of envs that were not reset alone (GPR_OUT_GOAL_ON_CHANGE)
     int out_f64;     // GPR_OUT_FLOAT64: observation / goal outputs are double arrays
+    // COMPACT TRANSPORT of the sparse results (gpr_step_host, copy-engine route; SAME_STEP auto-reset): the terminal
+    // observation of a finished env and the goal of its new episode go to row `slot` of these arrays — slot = the env's
+    // position on the auto-reset work list — instead of row `env` of final_* / desired_goal, with compact_index[slot] = env;
+    // the host copies the first `count` rows (count = entries published) and scatters them into the caller's arrays.
+    // All NULL = off (the kernels then write final_* / desired_goal rows in place).
+    float* compact_final_obs;
+    float* compact_final_ag;
+    float* compact_final_dg;
+    float* compact_goal;
+    int32_t* compact_index;
     // per-call I/O
     const float2* action;
     gpr_outputs out;
@@ -442,19 +452,28 @@ __device__ __forceinline__ void store_pair(const Args& a, float* base, size_t pa
     else reinterpret_cast<float2*>(base)[pair] = make_float2((float)x, (float)y);
 }
 
+// Rows of an arbitrary row index (compact transport: row = work-list slot): the general, colder form of store_obs.
+template <int G>
+__device__ __forceinline__ void store_obs_row(const PlanArgs& a, const Lane<G>& ln, size_t row, float* O, float* AG, float* DG,
+                                              double2 ov, double2 acc, double2 ag, double2 goal) {
+    if (!ln.active) return;
+    const int N = a.N;
+    if (O) {
+        const size_t rowp = row * (size_t)(N * (1 + a.learn_jerk));
+        store_pair(a, O, rowp + ln.m, ov.x, ov.y);
+        if (a.learn_jerk) store_pair(a, O, rowp + N + ln.m, acc.x, acc.y);
+    }
+    if (AG) store_pair(a, AG, row * (size_t)N + ln.m, ag.x, ag.y);
+    if (DG) store_pair(a, DG, row * (size_t)N + ln.m, goal.x, goal.y);
+}
+
 template <int G>
 __device__ __forceinline__ void store_obs(const PlanArgs& a, const Lane<G>& ln, float* O, float* AG, float* DG, double2 ov,
                                           double2 acc, double2 ag, double2 goal) {
     if (!ln.active) return;
     const int N = a.N;
     if (a.out_f64) {  // (cold: the vector envs use float32 outputs)
-        if (O) {
-            const size_t rowp = (size_t)ln.env * (size_t)(N * (1 + a.learn_jerk));
-            store_pair(a, O, rowp + ln.m, ov.x, ov.y);
-            if (a.learn_jerk) store_pair(a, O, rowp + N + ln.m, acc.x, acc.y);
-        }
-        if (AG) store_pair(a, AG, ln.idx, ag.x, ag.y);
-        if (DG) store_pair(a, DG, ln.idx, goal.x, goal.y);
+        store_obs_row<G>(a, ln, (size_t)ln.env, O, AG, DG, ov, acc, ag, goal);
         return;
     }
     if (O) {
@@ -1434,16 +1453,21 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
     if (a.autoreset == GPR_AUTORESET_SAME_STEP) need = done;
     if (a.autoreset == GPR_AUTORESET_NEXT_STEP) need = ln.env_ok && pending_reset;
     const bool handed = need && a.autoreset == GPR_AUTORESET_SAME_STEP;  // nothing of this env's state is stored below
+    unsigned my_slot = 0u;  // this env's position on the work list (every lane of a handed-over env's group)
     auto publish = [&]() {
         const unsigned leaders = __ballot_sync(FULL, need && ln.m == 0);
         if (need && a.write_goal) __threadfence();  // (the early desired_goal store, if there was one)
         unsigned long long t = 0ull;
         if (ln.lane == 0) t = atomicAdd(a.reset_ctl + a.parity, (1ull << 32) | (unsigned long long)__popc(leaders));
         const unsigned slot0 = (unsigned)__shfl_sync(FULL, t, 0);
-        GPR_CHECK(a, !(need && ln.m == 0) || slot0 + __popc(leaders & ((1u << ln.lane) - 1u)) < (unsigned)a.B, DBG_LIST_SLOT);
-        if (need && ln.m == 0)
-            *reinterpret_cast<volatile unsigned long long*>(a.reset_list + slot0 + __popc(leaders & ((1u << ln.lane) - 1u))) =
+        const unsigned slot = slot0 + __popc(leaders & ((1u << ln.lane) - 1u));
+        GPR_CHECK(a, !(need && ln.m == 0) || slot < (unsigned)a.B, DBG_LIST_SLOT);
+        if (need && ln.m == 0) {
+            if (a.compact_index) a.compact_index[slot] = ln.env;
+            *reinterpret_cast<volatile unsigned long long*>(a.reset_list + slot) =
                 ((unsigned long long)event << 32) | (unsigned long long)(uint32_t)ln.env;
+        }
+        my_slot = __shfl_sync(FULL, slot, (int)(ln.lane & ~(unsigned)(G - 1)));  // from the group's lane m == 0
     };
     if (a.autoreset == GPR_AUTORESET_SAME_STEP) publish();
 
@@ -1562,8 +1586,12 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
     }
 
     // ------------------------------------------------------------------ final observation / observation rows
-    if (handed)
-        store_obs<G>(a, ln, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, ov, acc, ag, goal);
+    if (handed) {
+        if (a.compact_index)
+            store_obs_row<G>(a, ln, (size_t)my_slot, a.compact_final_obs, a.compact_final_ag, a.compact_final_dg, ov, acc, ag, goal);
+        else
+            store_obs<G>(a, ln, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, ov, acc, ag, goal);
+    }
     // (the rows of envs handed to planning_autoreset_kernel are written there: first observation of the new episode)
     if (stepped && !handed) store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, nullptr, ov, acc, ag, goal);
 
@@ -1719,7 +1747,13 @@ __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) plan
         double2 ag, ov;
         int reached;
         observe<G, NOISE>(a, ln, event, p, v, goal, ag, ov, reached);
-        store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, a.out.desired_goal, ov, acc, ag, goal);
+        if (a.compact_index && a.autoreset == GPR_AUTORESET_SAME_STEP) {
+            // compact transport: the new episode's goal goes to this entry's row of the list, not to row `env`
+            store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, nullptr, ov, acc, ag, goal);
+            if (ln.active) store_pair(a, a.compact_goal, (size_t)(i0 + grp) * (size_t)a.N + ln.m, goal.x, goal.y);
+        } else {
+            store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, a.out.desired_goal, ov, acc, ag, goal);
+        }
         if (ln.active) {
             a.pos[ln.idx] = p;
             a.vel[ln.idx] = v;

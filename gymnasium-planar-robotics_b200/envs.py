@@ -202,11 +202,25 @@ class BatchedCore:
             # page-locked result arrays (torch owns the memory, NumPy views it)
             self._host_pin = {k: torch.zeros(tuple(v.shape), dtype=v.dtype, pin_memory=True) for k, v in self.buf.items()}
             self._host = {k: t.numpy() for k, t in self._host_pin.items()}
+            # terminal observations may come back as a LIST (gpr_outputs.final_index; compact transport with several ranks
+            # on one host): room for the index and the count
+            self._final_index = np.zeros(self.num_envs, dtype=np.int32)
+            self._final_count = np.zeros(1, dtype=np.uint32)
             self._host_out = GprOutputs()
             for name in _OUT_FIELDS:
                 setattr(self._host_out, name, self._host[name].ctypes.data if name in self._host else None)
+            if 'final_observation' in self._host:
+                self._host_out.final_index = self._final_index.ctypes.data
+                self._host_out.final_count = self._final_count.ctypes.data
         _lib.check(self.lib.gpr_step_host(self.handle, a.ctypes.data, ctypes.byref(self._host_out)))
         return self._host
+
+    @property
+    def host_final_count(self) -> int | None:
+        """After ``step_host``: None when the terminal observations were delivered densely (row = env), else the number of
+        list rows (row s of the final_* arrays belongs to env ``_final_index[s]``)."""
+        c = int(self._final_count[0]) if getattr(self, '_final_count', None) is not None else 0xFFFFFFFF
+        return None if c == 0xFFFFFFFF else c
 
     # ----------------------------------------------------------------------------------------------------------- state
     def _state_tensors(self) -> dict[str, torch.Tensor]:
@@ -428,8 +442,21 @@ class _VecEnvBase:
         return self._obs(), b['reward'], b['terminated'].bool(), b['truncated'].bool(), self._info(True)
 
     def step_host(self, action: np.ndarray):
-        """step() for callers that live on the host (NumPy in / NumPy out through ``gpr_step_host``)."""
+        """step() for callers that live on the host (NumPy in / NumPy out through ``gpr_step_host``).
+
+        ``info['final_obs']`` holds the terminal observations of the envs that finished in this step (SAME_STEP auto-reset).
+        Normally its arrays are dense — row = env, valid where terminated | truncated.  When several ranks share one host
+        (compact transport) they come as a list instead, like gymnasium's vector envs report them only for
+        the sub-envs that finished: ``info['final_obs']['index']`` (int32 env indices) is then present and row s of the other
+        arrays belongs to env ``index[s]``; ``final_obs_dense(info)`` converts either form to the dense one."""
         h = self.core.step_host(action)
+        n_list = self.core.host_final_count
+        if n_list is not None:
+            obs = {'observation': h['observation'], 'achieved_goal': h['achieved_goal'], 'desired_goal': h['desired_goal']}
+            info = {k: h[k].view(np.bool_) for k in ('is_success', 'mover_collision', 'wall_collision', 'other_collision') if k in h}
+            info['final_obs'] = {k: h['final_' + k][:n_list] for k in ('observation', 'achieved_goal', 'desired_goal')}
+            info['final_obs']['index'] = self.core._final_index[:n_list]
+            return obs, h['reward'], h['terminated'].view(np.bool_), h['truncated'].view(np.bool_), info
         if self._host_ret is None:
             # the result arrays are persistent (rewritten in place every step), so the returned structure is built once;
             # the flag arrays hold 0/1 bytes and are viewed as bool instead of converted
@@ -439,6 +466,18 @@ class _VecEnvBase:
                 info['final_obs'] = {k: h['final_' + k] for k in ('observation', 'achieved_goal', 'desired_goal')}
             self._host_ret = (obs, h['reward'], h['terminated'].view(np.bool_), h['truncated'].view(np.bool_), info)
         return self._host_ret
+
+    def final_obs_dense(self, info) -> dict[str, np.ndarray]:
+        """``info['final_obs']`` of ``step_host`` in the dense form (row = env; rows of other envs zero) whichever form it has."""
+        fo = info['final_obs']
+        if 'index' not in fo:
+            return fo
+        out = {}
+        for k in ('observation', 'achieved_goal', 'desired_goal'):
+            d = np.zeros((self.num_envs,) + fo[k].shape[1:], dtype=fo[k].dtype)
+            d[fo['index']] = fo[k]
+            out[k] = d
+        return out
 
     def compute_reward(self, achieved_goal, desired_goal, info=None):
         mc, wc = self._split_info(info)

@@ -196,6 +196,15 @@ typedef struct gpr_outputs {
     float* final_achieved_goal;
     float* final_desired_goal;
     uint8_t* other_collision; /* [num_envs] a mover touches a static obstacle (see gpr_config.num_obstacles); all 0 without obstacles */
+    /* COMPACT terminal observations — gpr_step_host only, optional (NULL = the dense form above).  Like gymnasium's vector
+       envs, which report final observations only for the sub-envs that finished, a host caller may take them as a list:
+       when the call uses the copy-engine route with compact transport (several ranks on one host, see gpr_step_host) and
+       final_index is non-NULL, row s of final_observation / final_achieved_goal / final_desired_goal belongs to env
+       final_index[s] for s < *final_count (order unspecified) and NO row is scattered on the host.  Any other route fills
+       final_* densely as usual and sets *final_count = UINT32_MAX.  Both arrays are caller-owned: final_index
+       [num_envs] int32, final_count [1] uint32. */
+    int32_t* final_index;
+    uint32_t* final_count;
 } gpr_outputs;
 
 /* Structure-of-arrays state, float64. Device pointers, caller-owned copies; NULL = skip that field.

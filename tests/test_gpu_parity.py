@@ -488,40 +488,63 @@ def test_host_calls_are_ordered_after_caller_stream_work():
 
 def test_step_host_copy_engine_route_matches(tmp_path):
     """GPR_HOST_IO=dma (results through device staging + copy engine instead of zero-copy stores; read once per process,
-    hence the subprocess) and pageable caller buffers give the same results as the default route."""
+    hence the subprocess) gives the same results as the default route — with the COMPACT transport of the sparse rows
+    (final_*, new desired_goal rows as lists scattered by the library; the default of the copy-engine route), with the dense
+    transport (GPR_HOST_COMPACT=0), with float64 outputs, 1-8 movers, and across switches between device-pointer steps,
+    host steps and resets (the library must notice when a host buffer no longer holds every env's goal)."""
     import subprocess
     import sys
 
     code = r"""
 import sys, numpy as np, torch
 sys.path[:0] = [%r, %r]
-import gymnasium_planar_robotics_b200 as gpr
-kw = dict(layout_tiles=np.ones((3, 3)), num_movers=4, std_noise=1e-5, seed=5)
-e1 = gpr.BenchmarkPlanningVecEnv(3000, device='cuda:0', **kw)
-e2 = gpr.BenchmarkPlanningVecEnv(3000, device='cuda:0', **kw)
-e1.reset(seed=5); e2.reset(seed=5)
-rng = np.random.default_rng(17)
-for _ in range(6):
-    a = rng.uniform(-10, 10, (3000, 8)).astype(np.float32)
-    o1, r1, t1, tr1, i1 = e1.step(torch.as_tensor(a, device='cuda:0'))
-    o2, r2, t2, tr2, i2 = e2.step_host(a)
-    torch.cuda.synchronize()
-    for k in ('observation', 'achieved_goal', 'desired_goal'):
-        assert np.array_equal(o1[k].cpu().numpy(), o2[k]), k
-    assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(t1.cpu().numpy(), t2) and np.array_equal(tr1.cpu().numpy(), tr2)
-    for k in ('is_success', 'mover_collision', 'wall_collision'):
-        assert np.array_equal(i1[k].cpu().numpy(), i2[k]), k
-    d = t2 | tr2
-    for k in ('observation', 'achieved_goal', 'desired_goal'):
-        assert np.array_equal(i1['final_obs'][k].cpu().numpy()[d], i2['final_obs'][k][d]), 'final ' + k
+import os, gymnasium_planar_robotics_b200 as gpr
+MODE = (os.environ['GPR_HOST_IO'], os.environ['GPR_HOST_COMPACT'])
+for N, layout, f64 in ((4, (3, 3), False), (2, (3, 3), True), (8, (5, 5), False), (3, (4, 4), False)):
+    kw = dict(layout_tiles=np.ones(layout), num_movers=N, std_noise=1e-5, seed=5, float64_outputs=f64, learn_jerk=(N == 8))
+    B = 3001
+    e1 = gpr.BenchmarkPlanningVecEnv(B, device='cuda:0', **kw)
+    e2 = gpr.BenchmarkPlanningVecEnv(B, device='cuda:0', **kw)
+    e1.reset(seed=5); e2.reset(seed=5)
+    rng = np.random.default_rng(17)
+    lim = 100.0 if N == 8 else 10.0
+    finished = lists = 0
+    for t in range(14):
+        if t == 7:           # a masked reset through the device API: new goals the host buffer has not seen
+            m = torch.as_tensor(rng.random(B) < 0.3, device='cuda:0')
+            e1.reset(options={'mask': m}); e2.reset(options={'mask': m})
+        a = rng.uniform(-lim, lim, (B, 2 * N)).astype(np.float32)
+        o1, r1, t1, tr1, i1 = e1.step(torch.as_tensor(a, device='cuda:0'))
+        if t in (5, 9):      # a device-pointer step in between: the host buffer misses the goals of the envs it resets
+            o2d, r2d, *_ = e2.step(torch.as_tensor(a, device='cuda:0'))
+            assert torch.equal(o2d['desired_goal'], o1['desired_goal']) and torch.equal(r2d, r1)
+            continue
+        o2, r2, t2, tr2, i2 = e2.step_host(a)
+        torch.cuda.synchronize()
+        for k in ('observation', 'achieved_goal', 'desired_goal'):
+            assert np.array_equal(o1[k].cpu().numpy(), o2[k]), (N, t, k)
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(t1.cpu().numpy(), t2) and np.array_equal(tr1.cpu().numpy(), tr2)
+        for k in ('is_success', 'mover_collision', 'wall_collision'):
+            assert np.array_equal(i1[k].cpu().numpy(), i2[k]), k
+        d = t2 | tr2
+        finished += int(d.sum())
+        lists += 'index' in i2['final_obs']
+        if 'index' in i2['final_obs']:
+            assert sorted(i2['final_obs']['index'].tolist()) == np.flatnonzero(d).tolist()  # exactly the finished envs, once each
+        fo = e2.final_obs_dense(i2)
+        for k in ('observation', 'achieved_goal', 'desired_goal'):
+            assert np.array_equal(i1['final_obs'][k].cpu().numpy()[d], fo[k][d]), (N, t, 'final ' + k)
+    assert finished > B // 2
+    assert (lists > 0) == (MODE == ('dma', '1')), (lists, MODE)  # the list form belongs to the compact transport only
+    e1.close(); e2.close()
 print('ok')
 """ % (ROOT, ROOT + '/oracle')
     import os
 
-    for mode in ('dma', 'zerocopy'):
-        env = dict(os.environ, GPR_HOST_IO=mode)
-        out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
-        assert out.returncode == 0 and 'ok' in out.stdout, (mode, out.stdout[-500:], out.stderr[-1500:])
+    for mode, compact in (('dma', '1'), ('dma', '0'), ('zerocopy', '1')):
+        env = dict(os.environ, GPR_HOST_IO=mode, GPR_HOST_COMPACT=compact)
+        out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
+        assert out.returncode == 0 and 'ok' in out.stdout, (mode, compact, out.stdout[-500:], out.stderr[-1500:])
 
 
 def test_desired_goal_on_change_survives_route_switches():
