@@ -766,7 +766,7 @@ static bool host_io_dma() {
         if (e && (strcmp(e, "zerocopy") == 0 || strcmp(e, "zc") == 0)) return false;
         const char* lw = getenv("LOCAL_WORLD_SIZE");
         const char* w = lw ? lw : getenv("WORLD_SIZE");
-        return w && atoi(w) > 1;
+        return w && atoi(w) > 4;  // measured (profiles/r2_bench_multi_gpu.txt): zero-copy wins at 2 and 4 ranks, the compact copy-engine route at 8
     }();
     return v;
 }

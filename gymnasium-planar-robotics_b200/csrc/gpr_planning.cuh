@@ -446,33 +446,36 @@ __device__ __forceinline__ void observe(const PlanArgs& a, const Lane<G>& ln, ui
 }
 
 // one (x, y) pair of an output row: element index `pair` of a float2 (or, with GPR_OUT_FLOAT64, double2) array
-template <class Args>
-__device__ __forceinline__ void store_pair(const Args& a, float* base, size_t pair, double x, double y) {
-    if (a.out_f64) reinterpret_cast<double2*>(base)[pair] = make_double2(x, y);
+__device__ __forceinline__ void store_pair(bool f64, float* base, size_t pair, double x, double y) {
+    if (f64) reinterpret_cast<double2*>(base)[pair] = make_double2(x, y);
     else reinterpret_cast<float2*>(base)[pair] = make_float2((float)x, (float)y);
 }
 
-// Rows of an arbitrary row index (compact transport: row = work-list slot): the general, colder form of store_obs.
+// Rows of an arbitrary row index (compact transport: row = work-list slot): the general, colder form of store_obs.  Out of
+// line on purpose: inlined at its five call sites it cost the step kernel 3 % (registers and code around the hot loop).
 template <int G>
-__device__ __forceinline__ void store_obs_row(const PlanArgs& a, const Lane<G>& ln, size_t row, float* O, float* AG, float* DG,
+static __device__ __noinline__ void store_obs_row(const PlanArgs& a, const Lane<G>& ln, size_t row, float* O, float* AG, float* DG,
                                               double2 ov, double2 acc, double2 ag, double2 goal) {
     if (!ln.active) return;
     const int N = a.N;
+    const bool f64 = a.out_f64 != 0;
     if (O) {
         const size_t rowp = row * (size_t)(N * (1 + a.learn_jerk));
-        store_pair(a, O, rowp + ln.m, ov.x, ov.y);
-        if (a.learn_jerk) store_pair(a, O, rowp + N + ln.m, acc.x, acc.y);
+        store_pair(f64, O, rowp + ln.m, ov.x, ov.y);
+        if (a.learn_jerk) store_pair(f64, O, rowp + N + ln.m, acc.x, acc.y);
     }
-    if (AG) store_pair(a, AG, row * (size_t)N + ln.m, ag.x, ag.y);
-    if (DG) store_pair(a, DG, row * (size_t)N + ln.m, goal.x, goal.y);
+    if (AG) store_pair(f64, AG, row * (size_t)N + ln.m, ag.x, ag.y);
+    if (DG) store_pair(f64, DG, row * (size_t)N + ln.m, goal.x, goal.y);
 }
 
-template <int G>
+// EXTRA = false: the kernel instantiation for plain float32 outputs written in place (the vector envs' default and the
+// benchmark configuration) carries none of the float64-output / compact-transport code: measured 1.5 % of the step each.
+template <int G, bool EXTRA = true>
 __device__ __forceinline__ void store_obs(const PlanArgs& a, const Lane<G>& ln, float* O, float* AG, float* DG, double2 ov,
                                           double2 acc, double2 ag, double2 goal) {
     if (!ln.active) return;
     const int N = a.N;
-    if (a.out_f64) {  // (cold: the vector envs use float32 outputs)
+    if (EXTRA && a.out_f64) {  // (cold: the vector envs use float32 outputs)
         store_obs_row<G>(a, ln, (size_t)ln.env, O, AG, DG, ov, acc, ag, goal);
         return;
     }
@@ -1180,7 +1183,7 @@ struct StepThreads {
     static constexpr int value = GPR_STEP_THREADS;
 };
 
-template <int G, bool BOX, bool NOISE, bool JERK>
+template <int G, bool BOX, bool NOISE, bool JERK, bool EXTRA>
 __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BOX : GPR_STEP_MINB) * 256 / StepThreads<G>::value)
     planning_step_kernel(const __grid_constant__ PlanArgs a) {
     // the auto-reset kernel that follows in the stream may become resident as soon as every CTA of this grid has started
@@ -1218,7 +1221,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         u.y = fmin(fmax((double)af.y, -a.act_lim), a.act_lim);
         // desired_goal does not change during a step: store it now, so that (when the output lives in pinned host memory)
         // this part of the result traffic crosses PCIe under the 40-cycle loop instead of in the burst at the end
-        if (!pending_reset && a.write_goal && a.out.desired_goal) store_pair(a, a.out.desired_goal, ln.idx, goal.x, goal.y);
+        if (!pending_reset && a.write_goal && a.out.desired_goal) store_pair(EXTRA && a.out_f64, a.out.desired_goal, ln.idx, goal.x, goal.y);
     }
 
     // ------------------------------------------------------------------ the 40-cycle loop (basic:1879-1905)
@@ -1463,11 +1466,11 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         const unsigned slot = slot0 + __popc(leaders & ((1u << ln.lane) - 1u));
         GPR_CHECK(a, !(need && ln.m == 0) || slot < (unsigned)a.B, DBG_LIST_SLOT);
         if (need && ln.m == 0) {
-            if (a.compact_index) a.compact_index[slot] = ln.env;
+            if (EXTRA && a.compact_index) a.compact_index[slot] = ln.env;
             *reinterpret_cast<volatile unsigned long long*>(a.reset_list + slot) =
                 ((unsigned long long)event << 32) | (unsigned long long)(uint32_t)ln.env;
         }
-        my_slot = __shfl_sync(FULL, slot, (int)(ln.lane & ~(unsigned)(G - 1)));  // from the group's lane m == 0
+        if (EXTRA && a.compact_index) my_slot = __shfl_sync(FULL, slot, (int)(ln.lane & ~(unsigned)(G - 1)));  // from the group's lane m == 0
     };
     if (a.autoreset == GPR_AUTORESET_SAME_STEP) publish();
 
@@ -1587,13 +1590,13 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
 
     // ------------------------------------------------------------------ final observation / observation rows
     if (handed) {
-        if (a.compact_index)
+        if (EXTRA && a.compact_index)
             store_obs_row<G>(a, ln, (size_t)my_slot, a.compact_final_obs, a.compact_final_ag, a.compact_final_dg, ov, acc, ag, goal);
         else
-            store_obs<G>(a, ln, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, ov, acc, ag, goal);
+            store_obs<G, EXTRA>(a, ln, a.out.final_observation, a.out.final_achieved_goal, a.out.final_desired_goal, ov, acc, ag, goal);
     }
     // (the rows of envs handed to planning_autoreset_kernel are written there: first observation of the new episode)
-    if (stepped && !handed) store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, nullptr, ov, acc, ag, goal);
+    if (stepped && !handed) store_obs<G, EXTRA>(a, ln, a.out.observation, a.out.achieved_goal, nullptr, ov, acc, ag, goal);
 
     // ------------------------------------------------------------------ state write-back
     if (ln.active && stepped && !handed) {
@@ -1628,7 +1631,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
-template <int G, bool BOX, bool NOISE>
+template <int G, bool BOX, bool NOISE, bool EXTRA>
 __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) planning_autoreset_kernel(const __grid_constant__ PlanArgs a) {
     __shared__ Tables tb;
     load_tables(tb, a.L);
@@ -1747,12 +1750,12 @@ __global__ void __launch_bounds__(128, BOX ? GPR_AR_MINB_BOX : GPR_AR_MINB) plan
         double2 ag, ov;
         int reached;
         observe<G, NOISE>(a, ln, event, p, v, goal, ag, ov, reached);
-        if (a.compact_index && a.autoreset == GPR_AUTORESET_SAME_STEP) {
+        if (EXTRA && a.compact_index && a.autoreset == GPR_AUTORESET_SAME_STEP) {
             // compact transport: the new episode's goal goes to this entry's row of the list, not to row `env`
-            store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, nullptr, ov, acc, ag, goal);
-            if (ln.active) store_pair(a, a.compact_goal, (size_t)(i0 + grp) * (size_t)a.N + ln.m, goal.x, goal.y);
+            store_obs<G, EXTRA>(a, ln, a.out.observation, a.out.achieved_goal, nullptr, ov, acc, ag, goal);
+            if (ln.active) store_pair(a.out_f64 != 0, a.compact_goal, (size_t)(i0 + grp) * (size_t)a.N + ln.m, goal.x, goal.y);
         } else {
-            store_obs<G>(a, ln, a.out.observation, a.out.achieved_goal, a.out.desired_goal, ov, acc, ag, goal);
+            store_obs<G, EXTRA>(a, ln, a.out.observation, a.out.achieved_goal, a.out.desired_goal, ov, acc, ag, goal);
         }
         if (ln.active) {
             a.pos[ln.idx] = p;

@@ -174,12 +174,12 @@ __device__ __forceinline__ void push_store_obs(const PushArgs& a, int e, float* 
                                                double2 ag, double2 goal) {
     if (O) {
         const size_t rowp = (size_t)e * (size_t)(2 + a.learn_jerk);  // in (x, y) pairs
-        store_pair(a, O, rowp + 0, obs[0], obs[1]);
-        store_pair(a, O, rowp + 1, obs[2], obs[3]);
-        if (a.learn_jerk) store_pair(a, O, rowp + 2, obs[4], obs[5]);
+        store_pair(a.out_f64 != 0, O, rowp + 0, obs[0], obs[1]);
+        store_pair(a.out_f64 != 0, O, rowp + 1, obs[2], obs[3]);
+        if (a.learn_jerk) store_pair(a.out_f64 != 0, O, rowp + 2, obs[4], obs[5]);
     }
-    if (AG) store_pair(a, AG, (size_t)e, ag.x, ag.y);
-    if (DG) store_pair(a, DG, (size_t)e, goal.x, goal.y);
+    if (AG) store_pair(a.out_f64 != 0, AG, (size_t)e, ag.x, ag.y);
+    if (DG) store_pair(a.out_f64 != 0, DG, (size_t)e, goal.x, goal.y);
 }
 
 // push:373-417 + basic:1797-1805, split in three stages so that the object-placement loop (push:392-407) can be shared by

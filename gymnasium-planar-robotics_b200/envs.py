@@ -205,7 +205,7 @@ class BatchedCore:
             # terminal observations may come back as a LIST (gpr_outputs.final_index; compact transport with several ranks
             # on one host): room for the index and the count
             self._final_index = np.zeros(self.num_envs, dtype=np.int32)
-            self._final_count = np.zeros(1, dtype=np.uint32)
+            self._final_count = np.full(1, 0xFFFFFFFF, dtype=np.uint32)  # (UINT32_MAX = dense rows; the library sets it per call)
             self._host_out = GprOutputs()
             for name in _OUT_FIELDS:
                 setattr(self._host_out, name, self._host[name].ctypes.data if name in self._host else None)
@@ -219,7 +219,9 @@ class BatchedCore:
     def host_final_count(self) -> int | None:
         """After ``step_host``: None when the terminal observations were delivered densely (row = env), else the number of
         list rows (row s of the final_* arrays belongs to env ``_final_index[s]``)."""
-        c = int(self._final_count[0]) if getattr(self, '_final_count', None) is not None else 0xFFFFFFFF
+        if getattr(self, '_final_count', None) is None or self._host is None or 'final_observation' not in self._host:
+            return None
+        c = int(self._final_count[0])
         return None if c == 0xFFFFFFFF else c
 
     # ----------------------------------------------------------------------------------------------------------- state
