@@ -503,7 +503,20 @@ __global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(c
         bool have0 = false;
         double cx, cy, qax, qay;
         push_control<BOX, NOISE>(a, s, ux, uy, env_global, event, s0, n4, have0, cx, cy);
-        gpr_push_substep_free(&a.P, &s.M, &s.O, cx, cy, &qax, &qay);  // mj_step (basic:1882), free regime
+        // mj_step (basic:1882), free regime.  A mover that has never been rotated (yaw exactly 0, yaw rate 0 — every env that
+        // has not had a contact since its reset) and an object at exact rest make everything of gpr_push_substep_free except
+        // the mover's x / y integration an exact no-op (tau = 0, every object term 0): integrate just that, with the very
+        // operations the general function applies (ux + 0 * (1/m) = ux + 0, v += dt a, x += dt v).
+        if (s.M.w == 0.0 && s.M.s == 0.0 && s.M.c == 1.0) {
+            qax = dadd(cx, 0.0);
+            qay = dadd(cy, 0.0);
+            s.M.vx = dadd(s.M.vx, dmul(a.P.dt, qax));
+            s.M.vy = dadd(s.M.vy, dmul(a.P.dt, qay));
+            s.M.x = dadd(s.M.x, dmul(a.P.dt, s.M.vx));
+            s.M.y = dadd(s.M.y, dmul(a.P.dt, s.M.vy));
+        } else {
+            gpr_push_substep_free(&a.P, &s.M, &s.O, cx, cy, &qax, &qay);
+        }
         s.acc = make_double2(qax, qay);
         wc = push_wall_cycle<BOX, NOISE>(a, tb, s, env_global, event, s0, n4, have0, cwf, gi, gj, travel, lim_w);
         if (wc) active = false;  // basic:1904

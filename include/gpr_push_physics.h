@@ -70,6 +70,7 @@ typedef struct gpr_push_params {
     /* float32 copies for the constraint solve (each the float64 value rounded once) */
     float f_hxM, f_hyM, f_hO, f_imM, f_iIM, f_imO, f_iIO, f_mu, f_B, f_K;
     float f_d0, f_dw, f_width, f_mid, f_power, f_gR, f_ginv, f_glim, f_glim2, f_D;
+    float f_inv_width, f_inv_mid, f_inv_1m_mid; /* reciprocals of the solimp shape constants (each computed in float64, rounded once) */
 } gpr_push_params;
 
 /* Derived physics parameters from the config — ONE definition shared by the CUDA host code and the CPU oracle so both
@@ -132,6 +133,9 @@ static inline void gpr_push_params_from_config(const gpr_config* c, gpr_push_par
     P->f_glim = (float)P->g_lim;
     P->f_glim2 = (float)P->g_lim * (float)P->g_lim;
     P->f_D = (float)P->obj_damping;
+    P->f_inv_width = (float)(1.0 / P->imp_width);
+    P->f_inv_mid = (float)(1.0 / P->imp_mid);
+    P->f_inv_1m_mid = (float)(1.0 / (1.0 - P->imp_mid));
 }
 
 /* per-environment solver state carried from substep to substep (warm start): contact forces (fn, ft) of up to two points,
@@ -145,16 +149,16 @@ typedef struct gpr_body2 {
 
 /* MuJoCo's impedance d(r): d0 -> dw over `width` of penetration, smooth power-law sigmoid (solimp).  float32. */
 GPR_PHD float gpr_push_impedance(const gpr_push_params* P, float r) {
-    const float x = GPR_FDIV(fabsf(r), P->f_width);
+    const float x = GPR_FMUL(fabsf(r), P->f_inv_width); /* (multiplications by precomputed reciprocals: no division on the path) */
     if (x >= 1.0f) return P->f_dw;
     if (x <= 0.0f) return P->f_d0;
     float y;
     if (P->f_power == 2.0f) { /* the default: avoids pow() */
         if (x <= P->f_mid) {
-            y = GPR_FDIV(GPR_FMUL(x, x), P->f_mid);
+            y = GPR_FMUL(GPR_FMUL(x, x), P->f_inv_mid);
         } else {
             const float u = GPR_FSUB(1.0f, x);
-            y = GPR_FSUB(1.0f, GPR_FDIV(GPR_FMUL(u, u), GPR_FSUB(1.0f, P->f_mid)));
+            y = GPR_FSUB(1.0f, GPR_FMUL(GPR_FMUL(u, u), P->f_inv_1m_mid));
         }
     } else {
         y = x; /* other powers fall back to a linear ramp (documented deviation; MuJoCo's default power is 2) */
@@ -462,8 +466,11 @@ GPR_PHD int gpr_push_substep(const gpr_push_params* P, gpr_body2* M, gpr_body2* 
         const float R = GPR_FMUL(GPR_FDIV(GPR_FSUB(1.0f, d), d), Ann);
         rn[k].R = R;
         rt[k].R = R; /* impratio 1: the friction row shares the normal row's regulariser */
-        rn[k].inv = GPR_FDIV(1.0f, GPR_FADD(Ann, R));
-        rt[k].inv = GPR_FDIV(1.0f, GPR_FADD(Att, R));
+        /* 1 / (Ann + R) and 1 / (Att + R) from ONE division: 1 / (a b), times the other factor */
+        const float den_n = GPR_FADD(Ann, R), den_t = GPR_FADD(Att, R);
+        const float inv_nt = GPR_FDIV(1.0f, GPR_FMUL(den_n, den_t));
+        rn[k].inv = GPR_FMUL(den_t, inv_nt);
+        rt[k].inv = GPR_FMUL(den_n, inv_nt);
         /* warm start: the previous substep's forces when it had the same number of contact points */
         const int keep = use_warm && (int)warm[12] == nc;
         rn[k].f = keep ? warm[2 * k] : 0.0f;
