@@ -380,6 +380,7 @@ static PlanArgs plan_args(const gpr_handle* h, const gpr_outputs* out) {
     a.env_base = (uint32_t)c.env_index_base;
     a.seed = h->seed;
     a.dt = c.cycle_time;
+    a.inv_dt = 1.0 / c.cycle_time;  // correctly rounded by the host: ddiv_rcp's premise
     a.v_max = c.v_max;
     a.a_max = c.a_max;
     a.j_max = c.j_max;
@@ -513,6 +514,7 @@ static PushArgs push_args(const gpr_handle* h, const gpr_outputs* out) {
     a.env_base = (uint32_t)c.env_index_base;
     a.seed = h->seed;
     a.dt = c.cycle_time;
+    a.inv_dt = 1.0 / c.cycle_time;  // correctly rounded by the host: ddiv_rcp's premise
     a.v_max = c.v_max;
     a.a_max = c.a_max;
     a.j_max = c.j_max;

@@ -73,6 +73,20 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+static __device__ __noinline__ double ddiv_cold(double a, double b) { return __ddiv_rn(a, b); }
+// RN(x / y) from z = RN(1 / y), y > 0, without the division sequence (a third of its instructions where one reciprocal serves
+// several quotients or y is a constant): q0 = RN(x z) is within 1.5 ulp of x / y; one FMA correction makes it faithful, and for a
+// faithful q the residual x - q y is exact and RN(q + r z) is the correctly rounded quotient (Markstein, "Computation of
+// elementary functions on the IBM RISC System/6000 processor", 1990, Theorem on FMA-based division).  Zero, tiny x (the
+// residual could underflow) and huge y go to the plain division.
+__device__ __forceinline__ double ddiv_rcp(double x, double y, double z) {
+    if (!(fabs(x) > 1e-200 && y < 1e150)) return ddiv_cold(x, y);
+    const double q0 = __dmul_rn(x, z);
+    const double r0 = __fma_rn(-q0, y, x);
+    const double q1 = __fma_rn(r0, z, q0);
+    const double r1 = __fma_rn(-q1, y, x);
+    return __fma_rn(r1, z, q1);
+}
 __device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
 
 // sqrt(s) <= t  /  sqrt(s) < t  /  sqrt(s) >= t, decided EXACTLY as the correctly rounded square root would, but the
@@ -380,7 +394,7 @@ __device__ __forceinline__ bool pair_check(unsigned lane, int m, bool part, doub
 
 // plan:610-645 ensure_max_dyn_val; the common non-clipping branch never takes the square root
 __device__ __forceinline__ void ensure_max(double cx, double cy, double maxv, double max2_lo, double dx, double dy,
-                                           double dt, double& nx, double& ny, double& ndx, double& ndy) {
+                                           double dt, double inv_dt, double& nx, double& ny, double& ndx, double& ndy) {
     const double tx = dadd(dmul(dt, dx), cx);
     const double ty = dadd(dmul(dt, dy), cy);
     const double s = dadd(dmul(tx, tx), dmul(ty, ty));
@@ -391,10 +405,11 @@ __device__ __forceinline__ void ensure_max(double cx, double cy, double maxv, do
     if (!(s < max2_lo)) {  // max2_lo = max^2 * (1 - 1e-14): below it sqrt(s) < max for certain (NaN falls through here)
         const double nrm = dsqrt(s);
         if (nrm >= maxv) {  // plan:633
-            nx = dmul(maxv, ddiv(tx, nrm));
-            ny = dmul(maxv, ddiv(ty, nrm));
-            ndx = ddiv(dsub(nx, cx), dt);
-            ndy = ddiv(dsub(ny, cy), dt);
+            const double inv_nrm = __drcp_rn(nrm);  // correctly rounded reciprocal, shared by the two quotients
+            nx = dmul(maxv, ddiv_rcp(tx, nrm, inv_nrm));
+            ny = dmul(maxv, ddiv_rcp(ty, nrm, inv_nrm));
+            ndx = ddiv_rcp(dsub(nx, cx), dt, inv_dt);  // inv_dt = RN(1 / dt), from the host
+            ndy = ddiv_rcp(dsub(ny, cy), dt, inv_dt);
         }
     }
 }

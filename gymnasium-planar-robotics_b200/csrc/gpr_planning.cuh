@@ -38,7 +38,7 @@ struct PlanArgs {
     int uniform_pairs;  // circle: one threshold for every pair (equal radii, or the basic:409 broadcast quirk)
     uint32_t env_base;
     uint64_t seed;
-    double dt, v_max, a_max, j_max, act_lim;
+    double dt, inv_dt, v_max, a_max, j_max, act_lim;  // inv_dt = RN(1 / dt), see ddiv_rcp
     double v_max2_lo, a_max2_lo;  // max^2 * (1 - 1e-14), see ensure_max
     double v_lazy2;               // (v_max - vel-noise bound)^2: below it the velocity clip cannot trigger (or -1)
     double threshold, min_goal_dist;
@@ -1284,7 +1284,7 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
         } else if (part) {
             // general path; d = derivative entering the velocity clip (action or limited acc)
             double dxv = u.x, dyv = u.y, jx = 0.0, jy = 0.0;
-            if (JERK) ensure_max(acc.x, acc.y, a.a_max, a.a_max2_lo, u.x, u.y, a.dt, dxv, dyv, jx, jy);  // plan:434
+            if (JERK) ensure_max(acc.x, acc.y, a.a_max, a.a_max2_lo, u.x, u.y, a.dt, a.inv_dt, dxv, dyv, jx, jy);  // plan:434
             double velx = v.x, vely = v.y;
             if (NOISE) {
                 // the velocity noise can only matter if the un-noised |dt*d + v| is within its bound of v_max
@@ -1297,11 +1297,11 @@ __global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BO
                 }
             }
             double t0, t1, ax, ay;
-            ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);  // plan:437 / 442
+            ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, a.inv_dt, t0, t1, ax, ay);  // plan:437 / 442
             if (JERK) {
                 if (dxv != ax || dyv != ay) {  // plan:438
-                    jx = ddiv(dsub(ax, acc.x), a.dt);
-                    jy = ddiv(dsub(ay, acc.y), a.dt);
+                    jx = ddiv_rcp(dsub(ax, acc.x), a.dt, a.inv_dt);
+                    jy = ddiv_rcp(dsub(ay, acc.y), a.dt, a.inv_dt);
                 }
                 acc.x = dadd(acc.x, dmul(a.dt, jx));  // act += dt*ctrl; qacc = act
                 acc.y = dadd(acc.y, dmul(a.dt, jy));

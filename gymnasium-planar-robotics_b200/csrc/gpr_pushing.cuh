@@ -22,7 +22,7 @@ struct PushArgs {
     int learn_jerk, num_cycles, max_episode_steps, autoreset, max_reset_attempts;
     uint32_t env_base;
     uint64_t seed;
-    double dt, v_max, a_max, j_max, act_lim;
+    double dt, inv_dt, v_max, a_max, j_max, act_lim;
     double v_max2_lo, a_max2_lo;
     double threshold;
     double min_xy[2], span_xy[2];          // mover spawn box (push:250-255)
@@ -322,7 +322,7 @@ template <bool BOX, bool NOISE>
 __device__ __forceinline__ void push_control(const PushArgs& a, PushState& s, double ux, double uy, uint32_t env_global,
                                              uint32_t event, uint32_t s0, float (&n4)[4], bool& have0, double& cx, double& cy) {
     double dxv = ux, dyv = uy, jx = 0.0, jy = 0.0;
-    if (a.learn_jerk) ensure_max(s.acc.x, s.acc.y, a.a_max, a.a_max2_lo, ux, uy, a.dt, dxv, dyv, jx, jy);  // push:432 (real qacc)
+    if (a.learn_jerk) ensure_max(s.acc.x, s.acc.y, a.a_max, a.a_max2_lo, ux, uy, a.dt, a.inv_dt, dxv, dyv, jx, jy);  // push:432 (real qacc)
     double velx = s.M.vx, vely = s.M.vy;
     if (NOISE) {
         // the velocity noise (push:428) is generated only where it can matter
@@ -335,11 +335,11 @@ __device__ __forceinline__ void push_control(const PushArgs& a, PushState& s, do
         }
     }
     double t0, t1, ax, ay;
-    ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, t0, t1, ax, ay);  // push:435 / 440
+    ensure_max(velx, vely, a.v_max, a.v_max2_lo, dxv, dyv, a.dt, a.inv_dt, t0, t1, ax, ay);  // push:435 / 440
     if (a.learn_jerk) {
         if (dxv != ax || dyv != ay) {  // push:436
-            jx = ddiv(dsub(ax, s.acc.x), a.dt);
-            jy = ddiv(dsub(ay, s.acc.y), a.dt);
+            jx = ddiv_rcp(dsub(ax, s.acc.x), a.dt, a.inv_dt);
+            jy = ddiv_rcp(dsub(ay, s.acc.y), a.dt, a.inv_dt);
         }
         // integrator actuator with actearly (push:305-311): act += dt*ctrl, force uses the new act
         s.act.x = dadd(s.act.x, dmul(a.dt, jx));
@@ -541,6 +541,9 @@ __global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(c
 #define GPR_PUSH_CONTACT_MINB 6
 #endif
 constexpr int kPushContactCta = 64;
+#ifndef GPR_PUSH_MIN_PULL
+#define GPR_PUSH_MIN_PULL 8u
+#endif
 
 template <bool BOX, bool NOISE>
 __global__ void __launch_bounds__(kPushContactCta, GPR_PUSH_CONTACT_MINB) pushing_contact_kernel(const __grid_constant__ PushArgs a) {
@@ -551,12 +554,18 @@ __global__ void __launch_bounds__(kPushContactCta, GPR_PUSH_CONTACT_MINB) pushin
     const uint32_t count = (uint32_t)a.queue_ctl[a.parity];  // final: pushing_step_kernel has completed
     uint32_t* const cursor = a.queue_cursor + a.parity;
     const float cwf = (float)a.c_wall[0][0];
+    // Envs per pull.  The kernel is bound by the LATENCY of one warp's serial substep chain, lengthened by every distinct path
+    // (0 / 1 / 2 contact points, sliding or resting corners) its lanes take: while the queue is short enough for the grid's
+    // warps to take it in one round, a warp pulls fewer envs (down to GPR_PUSH_MIN_PULL) and leaves its other lanes idle.
+    const uint32_t warps = gridDim.x * (kPushContactCta / 32);
+    uint32_t pull = 32u;
+    while (pull > GPR_PUSH_MIN_PULL && (unsigned long long)(pull >> 1) * warps >= count) pull >>= 1;
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32u);
+        if (lane == 0) base = atomicAdd(cursor, pull);
         base = __shfl_sync(FULL, base, 0);
         if (base >= count) break;
-        const bool live = base + lane < count;
+        const bool live = lane < pull && base + lane < count;
         int e = 0, cyc0 = a.num_cycles;
         PushState s;
         memset(&s, 0, sizeof(s));
