@@ -174,9 +174,15 @@ __device__ __forceinline__ void push_store_obs(const PushArgs& a, int e, float* 
                                                double2 ag, double2 goal) {
     if (O) {
         const size_t rowp = (size_t)e * (size_t)(2 + a.learn_jerk);  // in (x, y) pairs
-        store_pair(a.out_f64 != 0, O, rowp + 0, obs[0], obs[1]);
-        store_pair(a.out_f64 != 0, O, rowp + 1, obs[2], obs[3]);
-        if (a.learn_jerk) store_pair(a.out_f64 != 0, O, rowp + 2, obs[4], obs[5]);
+        if (!a.out_f64 && !a.learn_jerk && (reinterpret_cast<uintptr_t>(O) & 15u) == 0u) {
+            // the 16-byte row in ONE store: two 8-byte stores per lane leave every 32-byte sector half written twice, and
+            // on the host route (rows in page-locked host memory) each partial write is a PCIe transaction of its own
+            reinterpret_cast<float4*>(O)[e] = make_float4((float)obs[0], (float)obs[1], (float)obs[2], (float)obs[3]);
+        } else {
+            store_pair(a.out_f64 != 0, O, rowp + 0, obs[0], obs[1]);
+            store_pair(a.out_f64 != 0, O, rowp + 1, obs[2], obs[3]);
+            if (a.learn_jerk) store_pair(a.out_f64 != 0, O, rowp + 2, obs[4], obs[5]);
+        }
     }
     if (AG) store_pair(a.out_f64 != 0, AG, (size_t)e, ag.x, ag.y);
     if (DG) store_pair(a.out_f64 != 0, DG, (size_t)e, goal.x, goal.y);

@@ -1,3 +1,4 @@
+# 2- and 4-GPU calls of the round (gpurun --gpus 4): end-to-end per host route (GPR_HOST_IO=dma = compact copy engine, zerocopy).
 set -x
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29531"
