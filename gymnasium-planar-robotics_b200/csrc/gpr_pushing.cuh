@@ -389,9 +389,13 @@ __device__ __forceinline__ bool push_wall_cycle(const PushArgs& a, const Tables&
 
 // Everything after the cycle loop for one lane's env (warp-collective: EVERY lane of the warp calls it; `live` = this lane
 // holds an env that has finished its cycles here): observation, reward, flags, statistics, auto-reset, state write-back.
+// `filler` = this lane's env was parked for pushing_contact_kernel, which will write its result rows later: the lane writes
+// zeros into the dense rows now so that the warp's stores stay CONTIGUOUS.  Holes would split every store into partially
+// written 32-byte sectors, and into page-locked host memory each fragment is a PCIe write of its own (measured,
+// tools/sm_store_bw.cu: 50 GB/s for whole sectors, 0.8 G fragments/s otherwise — the fragments were 0.12 ms per step).
 template <bool BOX, bool NOISE>
-__device__ __forceinline__ void push_finish(const PushArgs& a, const Tables& tb, int e, bool live, bool pending, PushState& s,
-                                            uint32_t env_global, uint32_t event, int elapsed, bool wc) {
+__device__ __forceinline__ void push_finish(const PushArgs& a, const Tables& tb, int e, bool live, bool filler, bool pending,
+                                            PushState& s, uint32_t env_global, uint32_t event, int elapsed, bool wc) {
     double obs[6] = {0, 0, 0, 0, 0, 0};
     double2 ag = make_double2(0, 0);
     bool reached = false;
@@ -416,12 +420,14 @@ __device__ __forceinline__ void push_finish(const PushArgs& a, const Tables& tb,
             if (wc) atomicAdd(a.stats + 5, 1.0);
         }
         a.ep_return[e] = done ? 0.f : ret;
+    }
+    if (stepped || filler) {  // (a filler lane holds reward 0 and no flag)
         if (a.out.reward) a.out.reward[e] = reward;
         if (a.out.terminated) a.out.terminated[e] = term;
         if (a.out.truncated) a.out.truncated[e] = trunc;
         if (a.out.is_success) a.out.is_success[e] = succ;
         if (a.out.mover_collision) a.out.mover_collision[e] = 0;
-        if (a.out.wall_collision) a.out.wall_collision[e] = wc;
+        if (a.out.wall_collision) a.out.wall_collision[e] = stepped && wc;
     }
     // ---- auto-reset (push:373-417), stages A / B / C
     const bool need = live && ((a.autoreset == GPR_AUTORESET_SAME_STEP && done) || pending);
@@ -451,8 +457,10 @@ __device__ __forceinline__ void push_finish(const PushArgs& a, const Tables& tb,
             if (a.out.wall_collision) a.out.wall_collision[e] = rwc;
         }
     }
+    if (live || filler)
+        push_store_obs(a, e, a.out.observation, a.out.achieved_goal, (live && (a.write_goal || need)) ? a.out.desired_goal : nullptr,
+                       obs, ag, s.goal);
     if (!live) return;
-    push_store_obs(a, e, a.out.observation, a.out.achieved_goal, (a.write_goal || need) ? a.out.desired_goal : nullptr, obs, ag, s.goal);
     push_store(a, e, s);
     a.rng[e] = event;
     a.elapsed[e] = elapsed;
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(kPushCta, GPR_PUSH_MINB) pushing_step_kernel(c
             a.queue[slot0 + __popc(pm & ((1u << lane) - 1u))] = ((unsigned long long)(unsigned)parked_at << 32) | (unsigned long long)(uint32_t)e;
         }
     }
-    push_finish<BOX, NOISE>(a, tb, e, valid && !parked, pending, s, env_global, event, elapsed, wc);
+    push_finish<BOX, NOISE>(a, tb, e, valid && !parked, valid && parked, pending, s, env_global, event, elapsed, wc);
 }
 
 #ifndef GPR_PUSH_CONTACT_MINB
@@ -620,7 +628,7 @@ __global__ void __launch_bounds__(kPushContactCta, GPR_PUSH_CONTACT_MINB) pushin
 #pragma unroll
             for (int i = 0; i < GPR_PUSH_WARM; ++i) a.warm[(size_t)e * GPR_PUSH_WARM + i] = free_now ? 0.f : warm[i];
         }
-        push_finish<BOX, NOISE>(a, tb, e, live, false, s, env_global, event, elapsed, wc);  // (a reset zeroes it again)
+        push_finish<BOX, NOISE>(a, tb, e, live, false, false, s, env_global, event, elapsed, wc);  // (a reset zeroes it again)
     }
 }
 
