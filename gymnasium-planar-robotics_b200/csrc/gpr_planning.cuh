@@ -774,6 +774,8 @@ __device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables
         sf[m] = (float)a.c_mover[(GPR_MAX_MOVERS + mm) * 2 + 1];
     }
     const float mg = a.pair_mgf[0];
+    // span * 2^-32: scaling by a power of two is exact, so fmaf(span * 2^-32, w, min) IS fmaf(span, w * 2^-32, min) bit for bit
+    const float sxs = a.spanxf * 2.3283064365386963e-10f, sys = a.spanyf * 2.3283064365386963e-10f;
     const bool uni = kind == 1 || a.uniform_pairs != 0;
     const float lo2u = kind == 1 ? a.goal_lo2f : a.pair_lo2f[1][0], hi2u = kind == 1 ? a.goal_hi2f : a.pair_hi2f[1][0];
     bool found = false;
@@ -798,10 +800,25 @@ __device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables
             for (int m = 0; m < G; ++m) {
                 // (lanes of a group wider than num_movers: park the spare movers far away from everything, no branches)
                 const uint32_t wx = h ? r[m].v[2] : r[m].v[0], wy = h ? r[m].v[3] : r[m].v[1];
-                xf[m] = m < N ? fmaf(a.spanxf, (float)wx * 2.3283064365386963e-10f, a.minxf) : 1e8f * (float)(m + 1);
-                yf[m] = m < N ? fmaf(a.spanyf, (float)wy * 2.3283064365386963e-10f, a.minyf) : 0.f;
+                xf[m] = m < N ? fmaf(sxs, (float)wx, a.minxf) : 1e8f * (float)(m + 1);
+                yf[m] = m < N ? fmaf(sys, (float)wy, a.minyf) : 0.f;
             }
             bool rej = false, unc = false;
+            if (!(BOX && kind == 0) && uni) {
+                // one threshold pair for every pair of movers: classify the SMALLEST squared distance once (a min per pair
+                // instead of two compares and their logic) — rejected below lo2, too close to call up to hi2
+                float dmin = 3.0e38f;
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+#pragma unroll
+                    for (int j = i + 1; j < G; ++j) {
+                        const float dx = xf[i] - xf[j], dy = yf[i] - yf[j];
+                        dmin = fminf(dmin, dx * dx + dy * dy);
+                    }
+                }
+                rej = dmin < lo2u;
+                unc = !(dmin > hi2u);
+            } else {
 #pragma unroll
             for (int i = 0; i < G; ++i) {
 #pragma unroll
@@ -825,6 +842,7 @@ __device__ __forceinline__ void sample_env_lanes(const PlanArgs& a, const Tables
                         unc = unc || !(d2 < lo2 || d2 > hi2);
                     }
                 }
+            }
             }
             const bool valid = 2 * (int)blk + h < cap;
             if (valid && !rej) {
