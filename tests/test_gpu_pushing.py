@@ -156,18 +156,33 @@ def test_pushing_reset_failure_is_reported_not_hung():
 
 
 def test_pushing_host_api_and_single_env_form():
+    # host buffers (rows written over PCIe by BOTH kernels of the population split: the free kernel writes filler rows for the
+    # envs it parks, the contact kernel the real ones afterwards) against the device-pointer call, every output, long enough
+    # for a fifth of the envs to be in the contact regime and for episodes to end (TimeLimit 50, walls, successes)
     rng = np.random.default_rng(61)
-    e1 = gpr.BenchmarkPushingVecEnv(1024, device=DEV, seed=4)
-    e2 = gpr.BenchmarkPushingVecEnv(1024, device=DEV, seed=4)
+    B = 4099
+    e1 = gpr.BenchmarkPushingVecEnv(B, device=DEV, seed=4)
+    e2 = gpr.BenchmarkPushingVecEnv(B, device=DEV, seed=4)
     e1.reset(seed=4)
     e2.reset(seed=4)
-    for _ in range(6):
-        a = rng.uniform(-10, 10, (1024, 2)).astype(np.float32)
+    finished = moving = 0
+    for t in range(60):
+        a = rng.uniform(-10, 10, (B, 2)).astype(np.float32)
         o1, r1, t1, tr1, i1 = e1.step(torch.as_tensor(a, device=DEV))
         o2, r2, t2, tr2, i2 = e2.step_host(a)
         torch.cuda.synchronize()
-        assert np.array_equal(o1['observation'].cpu().numpy(), o2['observation']) and np.array_equal(r1.cpu().numpy(), r2)
-        assert np.array_equal(o1['achieved_goal'].cpu().numpy(), o2['achieved_goal'])
+        for k in ('observation', 'achieved_goal', 'desired_goal'):
+            assert np.array_equal(o1[k].cpu().numpy(), o2[k]), (t, k)
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(t1.cpu().numpy(), t2) and np.array_equal(tr1.cpu().numpy(), tr2), t
+        for k in ('is_success', 'mover_collision', 'wall_collision'):
+            assert np.array_equal(i1[k].cpu().numpy(), i2[k]), (t, k)
+        d = t2 | tr2
+        fo = e2.final_obs_dense(i2)
+        for k in ('observation', 'achieved_goal', 'desired_goal'):
+            assert np.array_equal(i1['final_obs'][k].cpu().numpy()[d], fo[k][d]), (t, 'final ' + k)
+        finished += int(d.sum())
+        moving += int((e1.state_dict()['object_vel'] != 0).any(dim=1).sum()) if t == 40 else 0
+    assert finished > B and moving > B // 10, (finished, moving)
     e1.close()
     e2.close()
     env = gpr.BenchmarkPushingEnv(render_mode=None, std_noise=0.0, learn_jerk=True)
