@@ -337,43 +337,46 @@ def run_b200(args, wl):
     fails = env.core.reset_failures()
 
     # ---- end to end through the host-buffer API (NumPy in / NumPy out), H2D + D2H inside the timed region
-    lim = env.j_max if env.learn_jerk else env.a_max
-    rng = np.random.default_rng(5 + rank)
-    hacts = []
-    for _ in range(4):  # page-locked host arrays (the contract's "pinned host memory"); filled on the host
-        buf = env.core.pinned_action_buffer()
-        buf[:] = rng.uniform(-lim, lim, (B, env.core.action_dim)).astype(np.float32)
-        hacts.append(buf)
-    for i in range(3):
-        env.step_host(hacts[i % 4])
-    e2e_steps = max(10, args.steps)  # (as many as the device-resident leg: a single host hiccup must not dominate)
-    e2e_blocks = []
-    d2h_written = 0
-    for r in range(args.repeats):
-        barrier()
-        t0 = time.perf_counter()
-        acc = 0.0
-        for i in range(e2e_steps):
+    def e2e_leg(env, B, steps, repeats):
+        lim = env.j_max if env.learn_jerk else env.a_max
+        rng = np.random.default_rng(5 + rank)
+        hacts = []
+        for _ in range(4):  # page-locked host arrays (the contract's "pinned host memory"); filled on the host
+            buf = env.core.pinned_action_buffer()
+            buf[:] = rng.uniform(-lim, lim, (B, env.core.action_dim)).astype(np.float32)
+            hacts.append(buf)
+        for i in range(3):
+            env.step_host(hacts[i % 4])
+        blocks = []
+        for r in range(repeats):
+            barrier()
+            t0 = time.perf_counter()
+            acc = 0.0
+            for i in range(steps):
+                out = env.step_host(hacts[i % 4])
+                acc += float(out[1][0])  # the host reads the step's result (reward of env 0) before issuing the next step
+            barrier()
+            blocks.append(allmax(time.perf_counter() - t0))
+        best = min(blocks)
+        env.core.kernel_times(True)  # device time of the same kernels when their I/O lives in pinned host memory (own pass)
+        done_rows = 0
+        for i in range(steps):
             out = env.step_host(hacts[i % 4])
-            acc += float(out[1][0])  # the host reads the step's result (reward of env 0) before issuing the next step
-        barrier()
-        e2e_blocks.append(allmax(time.perf_counter() - t0))
-    e2e_s = min(e2e_blocks)
-    env.core.kernel_times(True)  # device time of the same kernels when their I/O lives in pinned host memory (own pass)
-    done_rows = 0
-    for i in range(e2e_steps):
-        out = env.step_host(hacts[i % 4])
-        done_rows += int(np.count_nonzero(out[2] | out[3]))
-    e2e_kt = env.core.kernel_times(False)
-    e2e_value = world * B * e2e_steps / e2e_s
-    h2d = B * env.core.action_dim * 4
-    d2h_buffers = int(sum(v.nbytes for v in env.core._host.values()))
-    # bytes a step actually moves device -> host: dense rows every step, final_* and desired_goal rows only for the
-    # environments that finished (GPR_OUT_GOAL_ON_CHANGE; final rows are written for finished envs only)
-    od, gd = env.core.obs_dim, env.core.goal_dim
-    dense = 4 * (od + gd) + 4 + sum(1 for k in env.core._host if env.core._host[k].dtype == np.uint8)
-    per_done = 4 * (od + gd + gd) + 4 * gd
-    d2h_written = int(B * dense + per_done * done_rows / e2e_steps)
+            done_rows += int(np.count_nonzero(out[2] | out[3]))
+        kt = env.core.kernel_times(False)
+        # bytes a step actually moves device -> host: dense rows every step, final_* and desired_goal rows only for the
+        # environments that finished (GPR_OUT_GOAL_ON_CHANGE; final rows are written for finished envs only)
+        od, gd = env.core.obs_dim, env.core.goal_dim
+        dense = 4 * (od + gd) + 4 + sum(1 for k in env.core._host if env.core._host[k].dtype == np.uint8)
+        per_done = 4 * (od + gd + gd) + 4 * gd
+        return {'value': world * B * steps / best, 'seconds': best, 'blocks': blocks, 'steps': steps, 'kt': kt,
+                'h2d': B * env.core.action_dim * 4, 'd2h_written': int(B * dense + per_done * done_rows / steps),
+                'd2h_buffers': int(sum(v.nbytes for v in env.core._host.values()))}
+
+    e2e_steps = max(10, args.steps)  # (as many as the device-resident leg: a single host hiccup must not dominate)
+    e2e = e2e_leg(env, B, e2e_steps, args.repeats)
+    e2e_blocks, e2e_s, e2e_kt, e2e_value = e2e['blocks'], e2e['seconds'], e2e['kt'], e2e['value']
+    h2d, d2h_written, d2h_buffers = e2e['h2d'], e2e['d2h_written'], e2e['d2h_buffers']
     env.close()
 
     # context number: the same workload without sensor noise (the reference tests' parity setting).  EVERY rank runs it:
@@ -394,9 +397,12 @@ def run_b200(args, wl):
                                 ('planning4_1M', WORKLOADS['planning4'], 1048576, 10), ('pushing_1M', WORKLOADS['pushing'], 1048576, 10)):
             try:
                 r = measure(w, nb, st, 3, 3)
+                x = e2e_leg(r['env'], nb, st, 3)  # the same leg end to end (host buffers in / out)
                 r['env'].close()
                 extra_workloads[name] = {'workload': w['desc'].replace(f"{w['num_envs']:,} envs/GPU", f'{nb:,} envs/GPU'), 'envs_per_gpu': nb,
                                          'value': r['value'], 'unit': 'env-steps/s', 'ms_per_step': r['ms_per_step'], 'steps': st, 'best_of': 3,
+                                         'e2e': {'value': x['value'], 'unit': 'env-steps/s', 'ms_per_step': 1e3 * x['seconds'] / st,
+                                                 'h2d_bytes_per_step': x['h2d'], 'd2h_bytes_per_step': x['d2h_written']},
                                          'roofline': r['roofline'], 'clocks': r['clocks']}
             except Exception as exc:  # an extra leg must never take the headline line down with it
                 extra_workloads[name] = {'error': repr(exc)[:300]}
