@@ -1201,8 +1201,13 @@ struct StepThreads {
     static constexpr int value = GPR_STEP_THREADS;
 };
 
+#ifdef GPR_STEP_CTAS  // tuning experiments: resident CTAs per SM of the circle-shape step kernel, given directly
+#define GPR_STEP_MINBLOCKS(BOX, T) ((BOX) ? GPR_STEP_MINB_BOX * 256 / (T) : GPR_STEP_CTAS)
+#else
+#define GPR_STEP_MINBLOCKS(BOX, T) (((BOX) ? GPR_STEP_MINB_BOX : GPR_STEP_MINB) * 256 / (T))
+#endif
 template <int G, bool BOX, bool NOISE, bool JERK, bool EXTRA>
-__global__ void __launch_bounds__(StepThreads<G>::value, (BOX ? GPR_STEP_MINB_BOX : GPR_STEP_MINB) * 256 / StepThreads<G>::value)
+__global__ void __launch_bounds__(StepThreads<G>::value, GPR_STEP_MINBLOCKS(BOX, StepThreads<G>::value))
     planning_step_kernel(const __grid_constant__ PlanArgs a) {
     // the auto-reset kernel that follows in the stream may become resident as soon as every CTA of this grid has started
     // (programmatic dependent launch): its warps then fill the SM slots the last, partial wave of this grid leaves idle
