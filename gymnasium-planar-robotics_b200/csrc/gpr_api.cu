@@ -881,6 +881,8 @@ static int step_host_compact(gpr_handle* h, const StageLayout& L, const float* d
     for (int k = 0; k < kOutSlots; ++k)
         if (r.staged[k] && !r.pinned[k]) memcpy(*out_slot(&ho, k), hs + L.off[k], L.bytes[k]);
     const int32_t* idx = (const int32_t*)(hs + L.coff[C_INDEX]);
+    for (size_t s_ = 0; s_ < count; ++s_)  // (the scatter below indexes the caller's arrays with these)
+        if ((uint32_t)idx[s_] >= (uint32_t)h->cfg.num_envs) return fail(GPR_ERR_CUDA, "work-list entry %zu names env %d", s_, (int)idx[s_]);
     if (list_out) {
         memcpy(ho.final_index, idx, count * sizeof(int32_t));
         *ho.final_count = (uint32_t)count;
@@ -927,8 +929,10 @@ extern "C" int gpr_step_host(gpr_handle* h, const float* host_action, const gpr_
     // Measured on B200 (planning4, 65,536 envs): a copy-engine transfer of the action ahead of the kernel is slower end to
     // end than letting the kernel read the pinned buffer in place (158M vs 166M env-steps/s); splitting the step into 2-8
     // env chunks on separate streams (with or without per-chunk copy-engine transfers) changes nothing (+-3%).  What the
-    // host-I/O step pays for is the result traffic: SM stores to pinned memory sustain ~25 GB/s (the copy engine: 55),
-    // and sub-sector stores are charged like full ones — hence the CTA-coalesced flag / reward stores of the step kernel.
+    // host-I/O step pays for is the result traffic (tools/sm_store_bw.cu): SM stores to pinned memory stream at 50 GB/s as
+    // whole 32-byte sectors (the copy engine: 55), every write transaction carries ~24 B of overhead, and each FRAGMENT of
+    // a partially written sector is a transaction of its own (0.8 G/s) — hence the CTA-coalesced flag / reward stores of
+    // the step kernel, the one-store rows and the filler rows of the pushing kernels.
     rc = order_host_stream(h);
     if (rc != GPR_OK) return rc;
     // compact transport: the copy-engine route of a planning env with SAME_STEP auto-reset whose caller keeps handing in the
